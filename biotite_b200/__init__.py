@@ -1,0 +1,30 @@
+"""
+biotite_b200 - B200-native drop-in for the pairwise-alignment hot path of
+``biotite.sequence.align`` (``align_optimal`` / ``align_banded``).
+
+The public names mirror the reference's (``src/biotite/sequence/__init__.py``
+and ``src/biotite/sequence/align/__init__.py``) for everything on that path.
+"""
+
+from .alphabet import Alphabet, AlphabetError, LetterAlphabet
+from .sequence import (
+    GeneralSequence,
+    NucleotideSequence,
+    PositionalSequence,
+    ProteinSequence,
+    PurePositionalSequence,
+    Sequence,
+)
+from .matrix import SubstitutionMatrix
+from .alignment import (
+    Alignment,
+    find_terminal_gaps,
+    get_codes,
+    get_sequence_identity,
+    get_symbols,
+    remove_gaps,
+    remove_terminal_gaps,
+    score,
+)
+
+__version__ = "0.1.0"
