@@ -28,3 +28,13 @@ from .alignment import (
 )
 
 __version__ = "0.1.0"
+from .pairwise import align_optimal
+from .banded import align_banded
+from .batch import (
+    BatchResult,
+    DeviceBatch,
+    PackedSequences,
+    align_banded_batch,
+    align_optimal_batch,
+    pack_sequences,
+)

@@ -1,0 +1,337 @@
+"""
+Batched many-pairs entry points (``max_number=1`` semantics, what every in-tree
+caller of the reference uses: ``multiple.pyx:328``, ``statistics.py:208``,
+``superimpose.py:547``, ``tm.py:374``).
+
+``align_optimal_batch`` / ``align_banded_batch`` take many independent pairs,
+run them in one GPU batch through ``bt_batch_*`` of ``libb200align.so`` and
+return a :class:`BatchResult` that keeps the traces in the compact form the
+GPU produced; ``Alignment`` objects are built lazily because a million Python
+objects cost more than the DP itself.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+from .alignment import Alignment
+from .banded import crop_band
+from .matrix import SubstitutionMatrix
+from .pairwise import _check_gap_penalty
+
+__all__ = [
+    "PackedSequences",
+    "pack_sequences",
+    "DeviceBatch",
+    "BatchResult",
+    "align_optimal_batch",
+    "align_banded_batch",
+]
+
+
+class PackedSequences:
+    """
+    Many sequences in one contiguous code array: sequence ``k`` is
+    ``codes[offsets[k]:offsets[k+1]]``.  This is the layout the batch kernels
+    read, so packing once and reusing it avoids per-call Python work.
+    """
+
+    def __init__(self, codes, offsets, alphabet=None, sequences=None):
+        self.codes = np.ascontiguousarray(codes)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.alphabet = alphabet
+        self.sequences = sequences
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    @property
+    def lengths(self):
+        return np.diff(self.offsets)
+
+
+def pack_sequences(sequences, dtype=None):
+    """Concatenate the codes of `sequences` (an iterable of ``Sequence``)."""
+    if isinstance(sequences, PackedSequences):
+        return sequences
+    sequences = list(sequences)
+    if dtype is None:
+        dtype = np.uint8
+        for s in sequences:
+            dtype = np.promote_types(dtype, s.code.dtype)
+    lengths = np.fromiter((len(s) for s in sequences), dtype=np.int64, count=len(sequences))
+    offsets = np.zeros(len(sequences) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=offsets[1:])
+    codes = np.empty(int(offsets[-1]), dtype=dtype)
+    for s, a, b in zip(sequences, offsets[:-1], offsets[1:]):
+        codes[a:b] = s.code
+    alphabet = sequences[0].get_alphabet() if sequences else None
+    return PackedSequences(codes, offsets, alphabet, sequences)
+
+
+class DeviceBatch:
+    """
+    Thin handle on a ``BtBatch``: inputs are copied to the GPU on construction
+    and stay resident; :meth:`run` launches the fill and traceback kernels and
+    returns their device time; :meth:`fetch` copies the results back.
+    """
+
+    def __init__(self, codes1, off1, codes2, off2, scoring, gap_penalty,
+                 terminal_penalty=True, local=False, bands=None, score_only=False):
+        self._lib = _cabi.load()
+        self._handle = None
+        dtype = np.promote_types(codes1.dtype, codes2.dtype)
+        self.codes1 = np.ascontiguousarray(codes1, dtype)
+        self.codes2 = np.ascontiguousarray(codes2, dtype)
+        self.off1 = np.ascontiguousarray(off1, dtype=np.int64)
+        self.off2 = np.ascontiguousarray(off2, dtype=np.int64)
+        if len(self.off1) != len(self.off2):
+            raise ValueError("Both sides of the batch must hold the same number of sequences")
+        self.n_pairs = len(self.off1) - 1
+        self.bands = None if bands is None else np.ascontiguousarray(bands, dtype=np.int64)
+        self.score_only = bool(score_only)
+        self._params, self._matrix = _cabi.make_params(
+            scoring, gap_penalty, terminal_penalty, local, bands is not None, dtype)
+        handle = ctypes.c_void_p(None)
+        _cabi.check(self._lib.bt_batch_create(
+            ctypes.byref(self._params), _cabi.ptr(self.codes1), _cabi.ptr(self.off1),
+            _cabi.ptr(self.codes2), _cabi.ptr(self.off2), self.n_pairs,
+            _cabi.ptr(self._matrix), _cabi.ptr(self.bands), int(self.score_only),
+            ctypes.byref(handle)))
+        self._handle = handle
+
+    @property
+    def cells(self):
+        return int(self._lib.bt_batch_cells(self._handle))
+
+    @property
+    def launches(self):
+        return int(self._lib.bt_batch_launches(self._handle))
+
+    @property
+    def kernel(self):
+        return self._lib.bt_batch_kernel(self._handle).decode()
+
+    def run(self):
+        """Launch the kernels; returns the CUDA-event time in milliseconds."""
+        ms = ctypes.c_float(0.0)
+        _cabi.check(self._lib.bt_batch_run(self._handle, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def fetch(self, out=None):
+        """D2H copy of scores (and compact traces); returns a :class:`BatchResult`."""
+        n = self.n_pairs
+        if out is None:
+            scores = np.empty(n, dtype=np.int32)
+            trace_len = first = ops = None
+            if not self.score_only:
+                trace_len = np.empty(n, dtype=np.int64)
+                first = np.empty((n, 2), dtype=np.int32)
+                ops = np.empty(int(self.off1[-1] + self.off2[-1]), dtype=np.uint8)
+        else:
+            scores, trace_len, first, ops = out
+        _cabi.check(self._lib.bt_batch_fetch_scores(self._handle, _cabi.ptr(scores)))
+        if not self.score_only:
+            _cabi.check(self._lib.bt_batch_fetch_traces(
+                self._handle, _cabi.ptr(trace_len), _cabi.ptr(first), _cabi.ptr(ops)))
+        return BatchResult(scores, trace_len, first, ops, self.off1 + self.off2, self.bands)
+
+    def close(self):
+        if self._handle is not None:
+            self._lib.bt_batch_destroy(self._handle)
+            self._handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchResult:
+    """
+    Scores and first-optimal traces of a batch.
+
+    Attributes
+    ----------
+    scores : ndarray, int32, shape=(n,)
+    trace_len : ndarray, int64, shape=(n,) or None
+        Number of alignment columns per pair.
+    first : ndarray, int32, shape=(n,2) or None
+        DP-table coordinates of the cell of the first alignment column.
+    ops : ndarray, uint8 or None
+        Step bytes (0: both advance, 1: gap in sequence 1, 2: gap in sequence 2)
+        in end-to-start order; pair ``k`` starts at ``ops_off[k]``.
+    """
+
+    def __init__(self, scores, trace_len, first, ops, ops_off, bands=None, swapped=None,
+                 seqs1=None, seqs2=None):
+        self.scores = scores
+        self.trace_len = trace_len
+        self.first = first
+        self.ops = ops
+        self.ops_off = np.ascontiguousarray(ops_off, dtype=np.int64)
+        self.bands = bands
+        self.swapped = swapped
+        self.seqs1 = seqs1
+        self.seqs2 = seqs2
+
+    def __len__(self):
+        return len(self.scores)
+
+    def traces_flat(self):
+        """
+        All traces in one ``(sum(L), 2)`` int64 array plus the ``n+1`` row offsets.
+        """
+        if self.trace_len is None:
+            raise ValueError("The batch was computed with score_only=True")
+        lib = _cabi.load()
+        n = len(self.scores)
+        rows_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(self.trace_len, out=rows_off[1:])
+        out = np.empty((int(rows_off[-1]), 2), dtype=np.int64)
+        _cabi.check(lib.bt_expand_traces(
+            n, _cabi.ptr(self.trace_len), _cabi.ptr(np.ascontiguousarray(self.first)),
+            _cabi.ptr(self.ops), _cabi.ptr(self.ops_off), _cabi.ptr(self.bands),
+            _cabi.ptr(rows_off), _cabi.ptr(out)))
+        if self.swapped is not None and self.swapped.any():
+            flip = np.repeat(self.swapped, self.trace_len)
+            out[flip] = out[flip][:, ::-1]
+        return out, rows_off
+
+    def traces(self):
+        """List of ``(L, 2)`` int64 trace arrays (views into one buffer)."""
+        flat, rows_off = self.traces_flat()
+        return [flat[rows_off[k]:rows_off[k + 1]] for k in range(len(self.scores))]
+
+    def trace(self, k):
+        lib = _cabi.load()
+        length = np.ascontiguousarray(self.trace_len[k:k + 1])
+        rows_off = np.array([0, int(length[0])], dtype=np.int64)
+        out = np.empty((int(length[0]), 2), dtype=np.int64)
+        band = None if self.bands is None else np.ascontiguousarray(self.bands[k:k + 1])
+        _cabi.check(lib.bt_expand_traces(
+            1, _cabi.ptr(length), _cabi.ptr(np.ascontiguousarray(self.first[k:k + 1])),
+            _cabi.ptr(self.ops), _cabi.ptr(self.ops_off[k:k + 1]), _cabi.ptr(band),
+            _cabi.ptr(rows_off), _cabi.ptr(out)))
+        if self.swapped is not None and self.swapped[k]:
+            out = np.ascontiguousarray(out[:, ::-1])
+        return out
+
+    def alignment(self, k, seq1=None, seq2=None):
+        """The :class:`Alignment` of pair `k` (sequences default to the batch inputs)."""
+        if seq1 is None:
+            seq1 = self.seqs1[k]
+        if seq2 is None:
+            seq2 = self.seqs2[k]
+        return Alignment([seq1, seq2], self.trace(k), int(self.scores[k]))
+
+    def alignments(self):
+        traces = self.traces()
+        return [
+            Alignment([self.seqs1[k], self.seqs2[k]], traces[k], int(self.scores[k]))
+            for k in range(len(self.scores))
+        ]
+
+
+def _resolve_scoring(matrix, packed1, packed2):
+    if isinstance(matrix, tuple):
+        return (int(matrix[0]), int(matrix[1]))
+    if isinstance(matrix, SubstitutionMatrix):
+        for packed, alph in ((packed1, matrix.get_alphabet1()), (packed2, matrix.get_alphabet2())):
+            if packed.alphabet is not None and not alph.extends(packed.alphabet):
+                raise ValueError("The sequences' alphabets do not fit the matrix")
+        return matrix.score_matrix()
+    return np.ascontiguousarray(matrix, dtype=np.int32)
+
+
+def align_optimal_batch(seqs1, seqs2, matrix, gap_penalty=-10, terminal_penalty=True,
+                        local=False, score_only=False):
+    """
+    ``align_optimal(seqs1[k], seqs2[k], ..., max_number=1)`` for every ``k`` in
+    one GPU batch.  `seqs1` / `seqs2` are equally long lists of ``Sequence`` or
+    :class:`PackedSequences`.  Returns a :class:`BatchResult`.
+    """
+    _check_gap_penalty(gap_penalty)
+    p1, p2 = pack_sequences(seqs1), pack_sequences(seqs2)
+    if len(p1) != len(p2):
+        raise ValueError("Both lists must hold the same number of sequences")
+    scoring = _resolve_scoring(matrix, p1, p2)
+    with DeviceBatch(p1.codes, p1.offsets, p2.codes, p2.offsets, scoring, gap_penalty,
+                     terminal_penalty, local, None, score_only) as batch:
+        batch.run()
+        result = batch.fetch()
+    result.seqs1, result.seqs2 = p1.sequences, p2.sequences
+    return result
+
+
+def align_banded_batch(seqs1, seqs2, matrix, bands, gap_penalty=-10, local=False,
+                       score_only=False):
+    """
+    ``align_banded(seqs1[k], seqs2[k], matrix, bands[k], ..., max_number=1)`` for
+    every ``k``.  `bands` is one ``(lower, upper)`` tuple for all pairs or an
+    ``(n, 2)`` array.  Pairs whose second sequence is shorter are swapped
+    internally exactly as the reference does (``banded.py:215-224``) and
+    un-swapped in the returned traces.
+    """
+    _check_gap_penalty(gap_penalty)
+    p1, p2 = pack_sequences(seqs1), pack_sequences(seqs2)
+    n = len(p1)
+    if n != len(p2):
+        raise ValueError("Both lists must hold the same number of sequences")
+    bands = np.asarray(bands, dtype=np.int64)
+    if bands.ndim == 1:
+        bands = np.broadcast_to(bands, (n, 2))
+    len1, len2 = p1.lengths, p2.lengths
+    swapped = len2 < len1
+    scoring = _resolve_scoring(matrix, p1, p2)
+    if swapped.any():
+        if not swapped.all():
+            # mixed orientation: gather into shorter-first order
+            dtype = np.promote_types(p1.codes.dtype, p2.codes.dtype)
+            a_len = np.where(swapped, len2, len1)
+            b_len = np.where(swapped, len1, len2)
+            a_off = np.concatenate(([0], np.cumsum(a_len)))
+            b_off = np.concatenate(([0], np.cumsum(b_len)))
+            a_codes = np.empty(int(a_off[-1]), dtype=dtype)
+            b_codes = np.empty(int(b_off[-1]), dtype=dtype)
+            for k in range(n):
+                s1 = p1.codes[p1.offsets[k]:p1.offsets[k + 1]]
+                s2 = p2.codes[p2.offsets[k]:p2.offsets[k + 1]]
+                if swapped[k]:
+                    s1, s2 = s2, s1
+                a_codes[a_off[k]:a_off[k + 1]] = s1
+                b_codes[b_off[k]:b_off[k + 1]] = s2
+            if not isinstance(scoring, tuple) and not np.array_equal(scoring, scoring.T):
+                raise ValueError(
+                    "A batch that mixes orientations needs a symmetric substitution matrix")
+            q1 = PackedSequences(a_codes, a_off)
+            q2 = PackedSequences(b_codes, b_off)
+        else:
+            q1, q2 = p2, p1
+            if not isinstance(scoring, tuple):
+                scoring = np.ascontiguousarray(scoring.T)
+    else:
+        q1, q2 = p1, p2
+    eff = np.empty((n, 2), dtype=np.int64)
+    l1, l2 = q1.lengths, q2.lengths
+    for k in range(n):
+        band = (-int(bands[k, 0]), -int(bands[k, 1])) if swapped[k] else (
+            int(bands[k, 0]), int(bands[k, 1]))
+        eff[k] = crop_band(int(l1[k]), int(l2[k]), band)
+    with DeviceBatch(q1.codes, q1.offsets, q2.codes, q2.offsets, scoring, gap_penalty,
+                     True, local, eff, score_only) as batch:
+        batch.run()
+        result = batch.fetch()
+    result.swapped = swapped if swapped.any() else None
+    result.seqs1, result.seqs2 = p1.sequences, p2.sequences
+    return result

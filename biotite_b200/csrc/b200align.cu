@@ -1,0 +1,686 @@
+// libb200align - host side of the C ABI declared in include/b200align.h.
+//
+// Routing: every batch is served by hand-written sm_100a kernels only.
+//   interseq_s16x2 : short pairs, affine/linear, packed 16-bit DPX lanes, 4-bit
+//                    directions + GPU traceback (interseq_kernel.cuh)
+//   general_i32    : everything else - any length, band, code width, scoring
+//                    range; full direction sets (general_kernel.cuh)
+// There is no CPU path: without a device every compute call fails.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b200align.h"
+#include "common.cuh"
+#include "general_kernel.cuh"
+#include "host_trace.hpp"
+#include "interseq_kernel.cuh"
+
+using namespace bt;
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_error;
+
+static int fail(int status, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return status;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t err__ = (expr);                                                      \
+        if (err__ != cudaSuccess) {                                                      \
+            int st__ = err__ == cudaErrorMemoryAllocation ? BT_ERR_OOM : BT_ERR_CUDA;    \
+            cudaGetLastError();                                                          \
+            return fail(st__, "%s failed: %s", #expr, cudaGetErrorString(err__));        \
+        }                                                                                \
+    } while (0)
+
+extern "C" const char *bt_last_error(void) { return g_error.c_str(); }
+extern "C" const char *bt_version(void) { return "b200align 0.1 (sm_100a)"; }
+
+extern "C" int bt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int bt_set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return BT_OK;
+}
+extern "C" int bt_get_device(void) {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return d;
+}
+
+extern "C" void *bt_pinned_alloc(size_t bytes) {
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(BT_ERR_OOM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void bt_pinned_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+// ---------------------------------------------------------------------------------------
+// device buffers
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+    cudaError_t alloc(size_t n) {
+        release();
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMalloc(&ptr, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <class T> T *as() const { return (T *)ptr; }
+};
+
+static int check_params(const BtParams *P) {
+    if (!P) return fail(BT_ERR_INVALID_ARG, "params is NULL");
+    if (P->gap_open > 0 || (P->affine && P->gap_ext > 0))
+        return fail(BT_ERR_INVALID_ARG, "Gap penalty must be negative");
+    if (P->code_bytes != 1 && P->code_bytes != 2 && P->code_bytes != 4 && P->code_bytes != 8)
+        return fail(BT_ERR_INVALID_ARG, "Unsupported dtype: code_bytes=%d", P->code_bytes);
+    if (P->use_matrix && (P->n_rows <= 0 || P->n_cols <= 0))
+        return fail(BT_ERR_INVALID_ARG, "substitution matrix has an empty shape");
+    return BT_OK;
+}
+
+// pairwise.rs:585-602, banded.rs:310-314, :437-441
+static int32_t reference_neg_inf(const BtParams &P, int32_t min_score) {
+    int32_t ni = INT32_MIN;
+    if (P.affine) {
+        ni = wsub(wsub(ni, P.gap_open), P.gap_ext);
+        if (min_score < 0) ni = wsub(ni, min_score);
+    } else if (P.banded) {
+        ni = wsub(ni, P.gap_open);
+        if (min_score < 0) ni = wsub(ni, min_score);
+    }
+    return ni;
+}
+
+// ---------------------------------------------------------------------------------------
+// batch object
+// ---------------------------------------------------------------------------------------
+enum Route { ROUTE_GENERAL = 0, ROUTE_INTERSEQ = 1 };
+
+struct Chunk {
+    int64_t begin, end;   // pair range
+    int64_t dir_bytes;    // direction storage of the chunk
+    int max_n, max_m, max_w;
+};
+
+struct BtBatch {
+    BtParams P{};
+    DevParams D{};
+    int64_t n_pairs = 0;
+    int score_only = 0;
+    int device = 0;
+    Route route = ROUTE_GENERAL;
+    int64_t cells = 0, launches = 0;
+    int64_t total1 = 0, total2 = 0;
+    int min_score = 0, max_score = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<int64_t> h_off1, h_off2, h_bands, h_dir_off, h_cand_off;
+    std::vector<Chunk> chunks;
+    DevBuf codes1, codes2, off1, off2, bands, matrix, dir_off, cand_off, cand, dirs, gscratch;
+    DevBuf score, start_idx, start_state, end_vals, trace_len, first, ops, flag;
+    InterseqPlan interseq;  // state of the packed 16-bit route
+    bool ran = false;
+    ~BtBatch() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static const int64_t kDirBudget = 12ll << 30;   // direction bytes resident per chunk
+static const int kMaxSmemInts = 50 * 1024;      // 200 KB of wavefront buffers + matrix
+
+__global__ void validate_codes_kernel(const void *codes, int64_t n, int bytes, uint64_t limit,
+                                      int *flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) bad |= load_code(codes, i, bytes) >= limit;
+    if (bad) *flag = 1;
+}
+
+static BatchView make_view(BtBatch *b) {
+    BatchView V{};
+    V.codes1 = b->codes1.ptr; V.codes2 = b->codes2.ptr;
+    V.off1 = b->off1.as<int64_t>(); V.off2 = b->off2.as<int64_t>();
+    V.bands = b->P.banded ? b->bands.as<int64_t>() : nullptr;
+    V.matrix = b->P.use_matrix ? b->matrix.as<int32_t>() : nullptr;
+    V.dirs = b->dirs.as<uint8_t>();
+    V.dir_off = b->dir_off.as<int64_t>();
+    V.cand = b->cand.as<int32_t>();
+    V.cand_off = b->cand_off.as<int64_t>();
+    V.gscratch = nullptr; V.gscratch_stride = 0;
+    V.score = b->score.as<int32_t>();
+    V.start_idx = b->start_idx.as<int64_t>();
+    V.start_state = b->start_state.as<int32_t>();
+    V.end_vals = b->end_vals.as<int32_t>();
+    V.trace_len = b->trace_len.as<int64_t>();
+    V.first = b->first.as<int32_t>();
+    V.ops = b->ops.as<uint8_t>();
+    return V;
+}
+
+template <bool AFFINE, bool BANDED>
+static cudaError_t launch_general_fill(const DevParams &D, const BatchView &V, int grid, int threads,
+                                       size_t smem, cudaStream_t s) {
+    auto kernel = general_fill_kernel<AFFINE, BANDED>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kernel<<<grid, threads, smem, s>>>(D, V);
+    return cudaGetLastError();
+}
+
+static cudaError_t dispatch_general_fill(const DevParams &D, const BatchView &V, int grid, int threads,
+                                         size_t smem, cudaStream_t s) {
+    if (D.affine) {
+        return D.banded ? launch_general_fill<true, true>(D, V, grid, threads, smem, s)
+                        : launch_general_fill<true, false>(D, V, grid, threads, smem, s);
+    }
+    return D.banded ? launch_general_fill<false, true>(D, V, grid, threads, smem, s)
+                    : launch_general_fill<false, false>(D, V, grid, threads, smem, s);
+}
+
+static cudaError_t dispatch_general_traceback(const DevParams &D, const BatchView &V, int64_t count,
+                                              cudaStream_t s) {
+    const int threads = 128;
+    const int grid = (int)((count + threads - 1) / threads);
+    if (D.affine) {
+        if (D.banded) general_traceback_kernel<true, true><<<grid, threads, 0, s>>>(V);
+        else general_traceback_kernel<true, false><<<grid, threads, 0, s>>>(V);
+    } else {
+        if (D.banded) general_traceback_kernel<false, true><<<grid, threads, 0, s>>>(V);
+        else general_traceback_kernel<false, false><<<grid, threads, 0, s>>>(V);
+    }
+    return cudaGetLastError();
+}
+
+// Runs fill (+ first-optimal traceback) of the general route for every chunk.
+static int run_general(BtBatch *b, bool traceback) {
+    const bool affine = b->P.affine != 0;
+    const int NS = affine ? 3 : 1;
+    const int mat_ints = b->P.use_matrix ? b->P.n_rows * b->P.n_cols : 0;
+    for (const Chunk &c : b->chunks) {
+        BatchView V = make_view(b);
+        DevParams D = b->D;
+        const int slots = b->P.banded ? c.max_w + 2 : c.max_n + 1;
+        const int64_t wave_ints = 3ll * slots * NS;
+        D.matrix_in_smem = (mat_ints > 0 && mat_ints <= 4096) ? 1 : 0;
+        const int64_t smem_ints = wave_ints + (D.matrix_in_smem ? mat_ints : 0);
+        const int diag_len = b->P.banded ? (c.max_w + 1) / 2 : std::min(c.max_n, c.max_m);
+        int threads = std::min(512, std::max(64, (diag_len + 31) / 32 * 32));
+        if (!b->score_only && b->P.banded)
+            CUDA_TRY(cudaMemsetAsync(b->dirs.ptr, 0, (size_t)c.dir_bytes, b->stream));
+        if (smem_ints <= kMaxSmemInts) {
+            V.pair_begin = c.begin; V.pair_end = c.end;
+            CUDA_TRY(dispatch_general_fill(D, V, (int)(c.end - c.begin), threads,
+                                           (size_t)smem_ints * 4, b->stream));
+            b->launches++;
+        } else {
+            // wavefront buffers in global memory, a bounded number of blocks at a time
+            const int64_t per_launch = 512;
+            if (b->gscratch.bytes < (size_t)(per_launch * wave_ints * 4))
+                CUDA_TRY(b->gscratch.alloc((size_t)(per_launch * wave_ints * 4)));
+            V.gscratch = b->gscratch.as<int32_t>();
+            V.gscratch_stride = wave_ints;
+            for (int64_t p0 = c.begin; p0 < c.end; p0 += per_launch) {
+                V.pair_begin = p0; V.pair_end = std::min(c.end, p0 + per_launch);
+                CUDA_TRY(dispatch_general_fill(D, V, (int)(V.pair_end - V.pair_begin), threads,
+                                               (size_t)(D.matrix_in_smem ? mat_ints : 0) * 4,
+                                               b->stream));
+                b->launches++;
+            }
+        }
+        if (traceback && !b->score_only) {
+            V.pair_begin = c.begin; V.pair_end = c.end;
+            CUDA_TRY(dispatch_general_traceback(D, V, c.end - c.begin, b->stream));
+            b->launches++;
+        }
+    }
+    return BT_OK;
+}
+
+static int build_chunks(BtBatch *b) {
+    const int64_t n = b->n_pairs;
+    b->h_dir_off.assign(n, 0);
+    b->h_cand_off.assign(n, 0);
+    b->chunks.clear();
+    Chunk cur{0, 0, 0, 0, 0, 0};
+    int64_t cand_total = 0;
+    b->cells = 0;
+    for (int64_t k = 0; k < n; k++) {
+        const int64_t l1 = b->h_off1[k + 1] - b->h_off1[k], l2 = b->h_off2[k + 1] - b->h_off2[k];
+        if (l1 < 0 || l2 < 0) return fail(BT_ERR_INVALID_ARG, "offsets must be non-decreasing");
+        if (l1 > INT32_MAX / 2 - 2 || l2 > INT32_MAX / 2 - 2)
+            return fail(BT_ERR_INVALID_ARG, "sequence too long");
+        int64_t bytes, w = 0;
+        if (b->P.banded) {
+            const int64_t lo = b->h_bands[2 * k], up = b->h_bands[2 * k + 1];
+            w = up - lo + 1;
+            if (w < 1) return fail(BT_ERR_INVALID_ARG, "The width of the band is 0");
+            if (lo < -l1 || up > l2)
+                return fail(BT_ERR_INVALID_ARG, "Alignment band is out of range (crop it to the sequences)");
+            bytes = (l1 + 1) * (w + 2);
+            // cells: in-band, in-sequence positions (banded.rs:199-207)
+            for (int64_t i = 0; i < l1; i++) {
+                int64_t j0 = std::max<int64_t>(i + lo, 0), j1 = std::min<int64_t>(i + up + 1, l2);
+                if (j1 > j0) b->cells += j1 - j0;
+            }
+            b->h_cand_off[k] = cand_total;
+            cand_total += 3 * (w + 2);
+        } else {
+            bytes = (l1 + 1) * (l2 + 1);
+            b->cells += l1 * l2;
+        }
+        if (b->score_only) bytes = 0;
+        if (cur.end > cur.begin && cur.dir_bytes + bytes > kDirBudget) {
+            b->chunks.push_back(cur);
+            cur = Chunk{k, k, 0, 0, 0, 0};
+        }
+        b->h_dir_off[k] = cur.dir_bytes;
+        cur.dir_bytes += bytes;
+        cur.end = k + 1;
+        cur.max_n = std::max<int>(cur.max_n, (int)l1);
+        cur.max_m = std::max<int>(cur.max_m, (int)l2);
+        cur.max_w = std::max<int>(cur.max_w, (int)w);
+    }
+    if (cur.end > cur.begin) b->chunks.push_back(cur);
+    int64_t max_dir = 0;
+    for (const Chunk &c : b->chunks) max_dir = std::max(max_dir, c.dir_bytes);
+    if (!b->score_only) CUDA_TRY(b->dirs.alloc((size_t)max_dir));
+    if (b->P.banded) CUDA_TRY(b->cand.alloc((size_t)cand_total * 4));
+    return BT_OK;
+}
+
+static int batch_create_impl(const BtParams *params, const void *codes1, const int64_t *off1,
+                             const void *codes2, const int64_t *off2, int64_t n_pairs,
+                             const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                             bool force_general, BtBatch **batch_out) {
+    if (!batch_out) return fail(BT_ERR_INVALID_ARG, "batch_out is NULL");
+    *batch_out = nullptr;
+    int st = check_params(params);
+    if (st) return st;
+    if (n_pairs < 0 || !off1 || !off2) return fail(BT_ERR_INVALID_ARG, "bad pair offsets");
+    if (params->use_matrix && !matrix) return fail(BT_ERR_INVALID_ARG, "matrix is NULL");
+    if (params->banded && !bands) return fail(BT_ERR_INVALID_ARG, "bands is NULL");
+    if (bt_device_count() <= 0)
+        return fail(BT_ERR_CUDA, "no CUDA device available (libb200align has no CPU fallback)");
+
+    std::unique_ptr<BtBatch> b(new BtBatch());
+    b->P = *params;
+    b->n_pairs = n_pairs;
+    b->score_only = score_only ? 1 : 0;
+    b->device = bt_get_device();
+    b->h_off1.assign(off1, off1 + n_pairs + 1);
+    b->h_off2.assign(off2, off2 + n_pairs + 1);
+    if (params->banded) b->h_bands.assign(bands, bands + 2 * n_pairs);
+    b->total1 = b->h_off1[n_pairs] - b->h_off1[0];
+    b->total2 = b->h_off2[n_pairs] - b->h_off2[0];
+    if (b->h_off1[0] != 0 || b->h_off2[0] != 0)
+        return fail(BT_ERR_INVALID_ARG, "offsets must start at 0");
+
+    int32_t mn = 0, mx = 0;
+    if (params->use_matrix) {
+        const int64_t cnt = (int64_t)params->n_rows * params->n_cols;
+        mn = mx = matrix[0];
+        for (int64_t k = 1; k < cnt; k++) { mn = std::min(mn, matrix[k]); mx = std::max(mx, matrix[k]); }
+    } else {
+        mn = std::min(params->match_score, params->mismatch_score);
+        mx = std::max(params->match_score, params->mismatch_score);
+    }
+    b->min_score = mn; b->max_score = mx;
+
+    DevParams &D = b->D;
+    D.affine = params->affine; D.local = params->local;
+    D.terminal = params->banded ? 1 : params->terminal_penalty;
+    D.use_matrix = params->use_matrix; D.banded = params->banded; D.score_only = b->score_only;
+    D.gap_open = params->gap_open; D.gap_ext = params->affine ? params->gap_ext : params->gap_open;
+    D.match = params->match_score; D.mismatch = params->mismatch_score;
+    D.neg_inf = reference_neg_inf(*params, mn);
+    D.n_rows = params->n_rows; D.n_cols = params->n_cols; D.code_bytes = params->code_bytes;
+    D.mark = 0; D.mark_value = 0; D.matrix_in_smem = 0;
+
+    CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&b->ev0));
+    CUDA_TRY(cudaEventCreate(&b->ev1));
+
+    // route: packed 16-bit inter-sequence kernels when they are provably exact
+    b->route = ROUTE_GENERAL;
+    if (!force_general && interseq_eligible(*params, b->h_off1, b->h_off2, n_pairs, mn, mx))
+        b->route = ROUTE_INTERSEQ;
+
+    const size_t cb = (size_t)params->code_bytes;
+    CUDA_TRY(b->codes1.alloc((size_t)b->total1 * cb));
+    CUDA_TRY(b->codes2.alloc((size_t)b->total2 * cb));
+    CUDA_TRY(b->off1.alloc((size_t)(n_pairs + 1) * 8));
+    CUDA_TRY(b->off2.alloc((size_t)(n_pairs + 1) * 8));
+    CUDA_TRY(b->score.alloc((size_t)n_pairs * 4));
+    CUDA_TRY(b->flag.alloc(4));
+    CUDA_TRY(cudaMemsetAsync(b->flag.ptr, 0, 4, b->stream));
+    cudaStream_t s = b->stream;
+    CUDA_TRY(cudaMemcpyAsync(b->codes1.ptr, codes1, (size_t)b->total1 * cb, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->codes2.ptr, codes2, (size_t)b->total2 * cb, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->off1.ptr, off1, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (params->use_matrix) {
+        const size_t mb = (size_t)params->n_rows * params->n_cols * 4;
+        CUDA_TRY(b->matrix.alloc(mb));
+        CUDA_TRY(cudaMemcpyAsync(b->matrix.ptr, matrix, mb, cudaMemcpyHostToDevice, s));
+    }
+    if (!b->score_only) {
+        CUDA_TRY(b->trace_len.alloc((size_t)n_pairs * 8));
+        CUDA_TRY(b->first.alloc((size_t)n_pairs * 8));
+        CUDA_TRY(b->ops.alloc((size_t)(b->total1 + b->total2)));
+    }
+
+    if (b->route == ROUTE_INTERSEQ) {
+        st = interseq_prepare(b->interseq, *params, b->h_off1, b->h_off2, n_pairs, b->score_only, mn, mx,
+                              &b->cells, s);
+        if (st == BT_ERR_OOM) return fail(st, "out of device memory (inter-sequence plan)");
+        if (st) return fail(st, "inter-sequence plan failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } else {
+        st = build_chunks(b.get());
+        if (st) return st;
+        CUDA_TRY(b->dir_off.alloc((size_t)n_pairs * 8));
+        CUDA_TRY(b->cand_off.alloc((size_t)n_pairs * 8));
+        CUDA_TRY(b->start_idx.alloc((size_t)n_pairs * 8));
+        CUDA_TRY(b->start_state.alloc((size_t)n_pairs * 4));
+        CUDA_TRY(b->end_vals.alloc((size_t)n_pairs * 12));
+        CUDA_TRY(cudaMemcpyAsync(b->dir_off.ptr, b->h_dir_off.data(), (size_t)n_pairs * 8,
+                                 cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(b->cand_off.ptr, b->h_cand_off.data(), (size_t)n_pairs * 8,
+                                 cudaMemcpyHostToDevice, s));
+        if (params->banded) {
+            CUDA_TRY(b->bands.alloc((size_t)n_pairs * 16));
+            CUDA_TRY(cudaMemcpyAsync(b->bands.ptr, bands, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, s));
+        }
+    }
+    // code validation on the device (the reference panics on an out-of-range lookup, scoring.rs:63)
+    if (params->use_matrix) {
+        if (b->total1 > 0) {
+            validate_codes_kernel<<<(int)std::min<int64_t>(1184, (b->total1 + 255) / 256), 256, 0, s>>>(
+                b->codes1.ptr, b->total1, params->code_bytes, (uint64_t)params->n_rows, b->flag.as<int>());
+        }
+        if (b->total2 > 0) {
+            validate_codes_kernel<<<(int)std::min<int64_t>(1184, (b->total2 + 255) / 256), 256, 0, s>>>(
+                b->codes2.ptr, b->total2, params->code_bytes, (uint64_t)params->n_cols, b->flag.as<int>());
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, b->flag.ptr, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (flag) return fail(BT_ERR_INVALID_CODE, "a sequence code is outside the substitution matrix");
+    *batch_out = b.release();
+    return BT_OK;
+}
+
+extern "C" int bt_batch_create(const BtParams *params, const void *codes1, const int64_t *off1,
+                               const void *codes2, const int64_t *off2, int64_t n_pairs,
+                               const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                               BtBatch **batch_out) {
+    return batch_create_impl(params, codes1, off1, codes2, off2, n_pairs, matrix, bands, score_only,
+                             false, batch_out);
+}
+
+extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
+    if (!b) return fail(BT_ERR_INVALID_ARG, "batch is NULL");
+    CUDA_TRY(cudaSetDevice(b->device));
+    b->launches = 0;
+    CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+    int st = BT_OK;
+    if (b->n_pairs > 0) {
+        if (b->route == ROUTE_INTERSEQ) {
+            InterseqIO io{b->codes1.ptr, b->codes2.ptr, b->off1.as<int64_t>(), b->off2.as<int64_t>(),
+                          b->matrix.as<int32_t>(), b->score.as<int32_t>(), b->trace_len.as<int64_t>(),
+                          b->first.as<int32_t>(), b->ops.as<uint8_t>()};
+            cudaError_t e = interseq_run(b->interseq, io, b->stream, &b->launches);
+            if (e != cudaSuccess) st = fail(BT_ERR_CUDA, "inter-sequence kernels: %s", cudaGetErrorString(e));
+        } else {
+            st = run_general(b, true);
+        }
+    }
+    if (st) return st;
+    CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, b->ev0, b->ev1));
+    b->ran = true;
+    return BT_OK;
+}
+
+extern "C" int bt_batch_fetch_scores(BtBatch *b, int32_t *scores_out) {
+    if (!b || !scores_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (!b->ran) return fail(BT_ERR_INVALID_ARG, "bt_batch_run has not been called");
+    CUDA_TRY(cudaMemcpyAsync(scores_out, b->score.ptr, (size_t)b->n_pairs * 4, cudaMemcpyDeviceToHost,
+                             b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return BT_OK;
+}
+
+extern "C" int bt_batch_fetch_traces(BtBatch *b, int64_t *trace_len_out, int32_t *first_out,
+                                     uint8_t *ops_out) {
+    if (!b) return fail(BT_ERR_INVALID_ARG, "batch is NULL");
+    if (b->score_only) return fail(BT_ERR_INVALID_ARG, "batch was created score_only");
+    if (!b->ran) return fail(BT_ERR_INVALID_ARG, "bt_batch_run has not been called");
+    cudaStream_t s = b->stream;
+    if (trace_len_out)
+        CUDA_TRY(cudaMemcpyAsync(trace_len_out, b->trace_len.ptr, (size_t)b->n_pairs * 8, cudaMemcpyDeviceToHost, s));
+    if (first_out)
+        CUDA_TRY(cudaMemcpyAsync(first_out, b->first.ptr, (size_t)b->n_pairs * 8, cudaMemcpyDeviceToHost, s));
+    if (ops_out)
+        CUDA_TRY(cudaMemcpyAsync(ops_out, b->ops.ptr, (size_t)(b->total1 + b->total2), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return BT_OK;
+}
+
+extern "C" int64_t bt_batch_cells(const BtBatch *b) { return b ? b->cells : 0; }
+extern "C" int64_t bt_batch_launches(const BtBatch *b) { return b ? b->launches : 0; }
+extern "C" const char *bt_batch_kernel(const BtBatch *b) {
+    if (!b) return "";
+    return b->route == ROUTE_INTERSEQ ? "interseq_s16x2" : "general_i32";
+}
+extern "C" void bt_batch_destroy(BtBatch *b) { delete b; }
+
+extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const int64_t *off1,
+                              const void *codes2, const int64_t *off2, int64_t n_pairs,
+                              const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                              int32_t *scores_out, int64_t *trace_len_out, int32_t *first_out,
+                              uint8_t *ops_out) {
+    BtBatch *raw = nullptr;
+    int st = bt_batch_create(params, codes1, off1, codes2, off2, n_pairs, matrix, bands, score_only, &raw);
+    if (st) return st;
+    std::unique_ptr<BtBatch> b(raw);
+    st = bt_batch_run(b.get(), nullptr);
+    if (st) return st;
+    if (scores_out) { st = bt_batch_fetch_scores(b.get(), scores_out); if (st) return st; }
+    if (!score_only && (trace_len_out || first_out || ops_out))
+        st = bt_batch_fetch_traces(b.get(), trace_len_out, first_out, ops_out);
+    return st;
+}
+
+extern "C" int bt_expand_traces(int64_t n_pairs, const int64_t *trace_len, const int32_t *first,
+                                const uint8_t *ops, const int64_t *ops_off, const int64_t *bands,
+                                const int64_t *rows_off, int64_t *out) {
+    if (!trace_len || !first || !ops || !ops_off || !rows_off || !out)
+        return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    for (int64_t k = 0; k < n_pairs; k++) {
+        const int64_t lower = bands ? bands[2 * k] : 0;
+        int64_t rows = expand_ops(trace_len[k], first[2 * k], first[2 * k + 1], ops + ops_off[k],
+                                  bands != nullptr, lower, out + 2 * rows_off[k]);
+        if (rows != trace_len[k]) return fail(BT_ERR_INVALID_ARG, "degenerate trace row in pair %lld", (long long)k);
+    }
+    return BT_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// single pair: the reference's FFI contract, including co-optimal enumeration
+// ---------------------------------------------------------------------------------------
+struct BtTraceList {
+    std::vector<std::vector<int64_t>> traces;  // each 2*L values
+};
+
+extern "C" int64_t bt_tracelist_count(const BtTraceList *l) { return l ? (int64_t)l->traces.size() : 0; }
+extern "C" int64_t bt_tracelist_length(const BtTraceList *l, int64_t k) {
+    if (!l || k < 0 || k >= (int64_t)l->traces.size()) return -1;
+    return (int64_t)l->traces[k].size() / 2;
+}
+extern "C" int bt_tracelist_copy(const BtTraceList *l, int64_t k, int64_t *out) {
+    if (!l || k < 0 || k >= (int64_t)l->traces.size() || !out) return fail(BT_ERR_INVALID_ARG, "bad trace index");
+    if (!l->traces[k].empty()) memcpy(out, l->traces[k].data(), l->traces[k].size() * 8);
+    return BT_OK;
+}
+extern "C" void bt_tracelist_free(BtTraceList *l) { delete l; }
+
+extern "C" int bt_align_pair(const BtParams *params, const void *code1, int64_t len1, const void *code2,
+                             int64_t len2, const int32_t *matrix, int64_t lower_diag, int64_t upper_diag,
+                             int32_t score_only, int64_t max_number, int32_t *score_out,
+                             BtTraceList **traces_out) {
+    if (!score_out) return fail(BT_ERR_INVALID_ARG, "score_out is NULL");
+    if (traces_out) *traces_out = nullptr;
+    if (!score_only && !traces_out) return fail(BT_ERR_INVALID_ARG, "traces_out is NULL");
+    if (max_number < 1) return fail(BT_ERR_INVALID_ARG, "Maximum number of returned alignments must be at least 1");
+    const int64_t off1[2] = {0, len1}, off2[2] = {0, len2};
+    const int64_t band[2] = {lower_diag, upper_diag};
+    // the single-pair path always uses full direction sets (general route)
+    BtParams P = *params;
+    BtBatch *raw = nullptr;
+    int st = batch_create_impl(&P, code1, off1, code2, off2, 1, matrix, P.banded ? band : nullptr,
+                               score_only, true, &raw);
+    if (st) return st;
+    std::unique_ptr<BtBatch> b(raw);
+    const bool first_only = (max_number == 1);
+    CUDA_TRY(cudaSetDevice(b->device));
+    st = run_general(b.get(), first_only);
+    if (st) return st;
+    b->ran = true;
+    int32_t score = 0;
+    CUDA_TRY(cudaMemcpyAsync(&score, b->score.ptr, 4, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    *score_out = score;
+    if (score_only) return BT_OK;
+
+    std::unique_ptr<BtTraceList> list(new BtTraceList());
+    const bool banded = P.banded != 0, affine = P.affine != 0;
+    const int64_t W = upper_diag - lower_diag + 1;
+    const int64_t rs = banded ? W + 2 : len2 + 1;
+    if (first_only) {
+        int64_t len = 0; int32_t first[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(&len, b->trace_len.ptr, 8, cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaMemcpyAsync(first, b->first.ptr, 8, cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        std::vector<uint8_t> ops((size_t)std::max<int64_t>(len, 1));
+        if (len > 0) CUDA_TRY(cudaMemcpy(ops.data(), b->ops.ptr, (size_t)len, cudaMemcpyDeviceToHost));
+        std::vector<int64_t> rows((size_t)(2 * len));
+        int64_t nrows = expand_ops(len, first[0], first[1], ops.data(), banded, lower_diag, rows.data());
+        rows.resize((size_t)(2 * nrows));
+        list->traces.push_back(std::move(rows));
+        *traces_out = list.release();
+        return BT_OK;
+    }
+
+    // ---- co-optimal enumeration on the host over the direction table ------------------
+    if (P.local) {
+        // second pass tags every cell whose M equals the optimum (pairwise.rs:536-551)
+        b->D.mark = 1; b->D.mark_value = score;
+        st = run_general(b.get(), false);
+        if (st) return st;
+    }
+    const int64_t table = (len1 + 1) * rs;
+    std::vector<uint8_t> dir((size_t)table);
+    CUDA_TRY(cudaMemcpyAsync(dir.data(), b->dirs.ptr, (size_t)table, cudaMemcpyDeviceToHost, b->stream));
+    std::vector<int32_t> cand;
+    int32_t endv[3] = {0, 0, 0};
+    if (banded && !P.local) {
+        cand.resize((size_t)(3 * (W + 2)));
+        CUDA_TRY(cudaMemcpyAsync(cand.data(), b->cand.ptr, cand.size() * 4, cudaMemcpyDeviceToHost, b->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(endv, b->end_vals.ptr, 12, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+
+    std::vector<Start> starts;
+    if (P.local) {
+        for (int64_t idx = 0; idx < table && (int64_t)starts.size() < max_number; idx++) {
+            bool is_start = (dir[idx] & DIR_MARK) != 0;
+            if (!is_start && banded && score == 0) {
+                // never-filled in-band cells keep the edge value M = 0 (banded.rs:184)
+                const int64_t i = idx / rs, c = idx % rs;
+                if (c >= 1 && c <= W) {
+                    const int64_t sj = c + i - 2 + lower_diag;
+                    is_start = (i == 0) || sj < 0 || sj >= len2;
+                }
+            }
+            if (is_start) starts.push_back({idx, ST_MATCH});
+        }
+    } else if (!banded) {
+        const int64_t corner = len1 * rs + len2;
+        if (affine) {
+            for (int stt = 0; stt < 3; stt++)
+                if (endv[stt] == score) starts.push_back({corner, stt});
+        } else {
+            starts.push_back({corner, 0});
+        }
+    } else {
+        const int ns = affine ? 3 : 1;
+        for (int stt = 0; stt < ns; stt++) {
+            for (int64_t j = 1; j <= W; j++) {
+                if (cand[(size_t)(stt * (W + 2) + j)] != score) continue;
+                const int64_t sj = j + (len1 - 1) + lower_diag - 1;
+                const int64_t i = sj < len2 ? len1 : len2 - j - lower_diag + 1;
+                starts.push_back({i * rs + j, stt});
+            }
+        }
+    }
+    const int64_t off[3] = {banded ? -rs : -(rs + 1), -1, banded ? -rs + 1 : -rs};
+    std::vector<Path> paths;
+    for (const Start &s0 : starts) {
+        enumerate_from(dir.data(), affine, off, s0, max_number, max_number, paths);
+        if ((int64_t)paths.size() >= max_number) break;
+    }
+    if ((int64_t)paths.size() > max_number) paths.resize((size_t)max_number);
+    std::vector<int64_t> rows;
+    for (const Path &path : paths) {
+        path_to_trace(path, rs, banded, lower_diag, rows);
+        list->traces.push_back(rows);
+    }
+    *traces_out = list.release();
+    return BT_OK;
+}

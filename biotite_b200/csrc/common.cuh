@@ -1,0 +1,68 @@
+// Shared device/host definitions of libb200align.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bt {
+
+// Direction bits, identical to the reference's bitflags
+// (src/rust/sequence/align/cell.rs:44-80) so that direction tables can be
+// traced with the reference's rules.
+enum : uint8_t {
+    L_MATCH = 1, L_GAP1 = 2, L_GAP2 = 4,
+    A_MM = 1, A_G1M = 2, A_G2M = 4, A_MG1 = 8, A_G1G1 = 16, A_MG2 = 32, A_G2G2 = 64,
+    DIR_MARK = 128  // "M of this cell equals the optimum" (local start enumeration)
+};
+enum : int { ST_MATCH = 0, ST_GAP1 = 1, ST_GAP2 = 2 };
+enum : uint8_t { OP_DIAG = 0, OP_TO1 = 1, OP_TO2 = 2 };
+
+// Mode of one launch (device copy of BtParams plus derived values).
+struct DevParams {
+    int affine, local, terminal, use_matrix, banded, score_only;
+    int32_t gap_open, gap_ext, match, mismatch, neg_inf;
+    int n_rows, n_cols, code_bytes;
+    int mark;            // second pass of local enumeration: tag cells whose M == mark_value
+    int32_t mark_value;
+    int matrix_in_smem;  // matrix staged in shared memory
+};
+
+// Device views of one batch (or one chunk of it).
+struct BatchView {
+    const void *codes1, *codes2;
+    const int64_t *off1, *off2;   // n_pairs+1 element offsets
+    const int64_t *bands;         // 2*n_pairs (lower, upper) or nullptr
+    const int32_t *matrix;        // n_rows*n_cols or nullptr
+    uint8_t *dirs;                // direction table storage of this chunk
+    const int64_t *dir_off;       // per pair byte offset into dirs (relative to chunk)
+    int32_t *cand;                // banded semi-global end candidates
+    const int64_t *cand_off;      // per pair offset into cand (ints)
+    int32_t *gscratch;            // per block wavefront buffers when they exceed smem
+    int64_t gscratch_stride;      // ints per block
+    // results
+    int32_t *score;
+    int64_t *start_idx;
+    int32_t *start_state;
+    int32_t *end_vals;            // 3 per pair: M, G1, G2 of the global end cell
+    int64_t *trace_len;
+    int32_t *first;               // 2 per pair
+    uint8_t *ops;                 // compact traces, pair k at off1[k]+off2[k]
+    int64_t pair_begin, pair_end; // pairs handled by this launch
+};
+
+__host__ __device__ inline int32_t wadd(int32_t a, int32_t b) {
+    return (int32_t)((uint32_t)a + (uint32_t)b);  // i32 wraps in the reference
+}
+__host__ __device__ inline int32_t wsub(int32_t a, int32_t b) {
+    return (int32_t)((uint32_t)a - (uint32_t)b);
+}
+
+__device__ __forceinline__ uint64_t load_code(const void *base, int64_t idx, int bytes) {
+    switch (bytes) {
+    case 1: return ((const uint8_t *)base)[idx];
+    case 2: return ((const uint16_t *)base)[idx];
+    case 4: return ((const uint32_t *)base)[idx];
+    default: return ((const uint64_t *)base)[idx];
+    }
+}
+
+}  // namespace bt

@@ -1,0 +1,149 @@
+/*
+ * b200align.h - C ABI of libb200align.so, the B200 (sm_100a) implementation of
+ * the pairwise dynamic-programming alignment hot path of biotite.
+ *
+ * This is the drop-in boundary.  It replaces the two native entry points the
+ * reference exports from its PyO3 module `biotite.rust.sequence.align`
+ * (registered at src/rust/sequence/align/mod.rs:23-24):
+ *
+ *   align_optimal(code1, code2, scoring, gap_penalty, terminal_penalty, local,
+ *                 score_only, max_number)        src/rust/sequence/align/pairwise.rs:57-70
+ *   align_banded (code1, code2, scoring, gap_penalty, lower_diag, upper_diag,
+ *                 local, score_only, max_number) src/rust/sequence/align/banded.rs:63-77
+ *
+ * and adds the batched many-pairs entry points the north star asks for.  All
+ * functions take plain pointers and sizes; the caller owns every buffer it
+ * passes in.  All functions return BT_OK (0) or a negative BtStatus; the
+ * message of the last failure on the calling thread is bt_last_error().
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with BT_ERR_CUDA.
+ */
+#ifndef B200ALIGN_H
+#define B200ALIGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum BtStatus {
+    BT_OK = 0,
+    BT_ERR_INVALID_ARG = -1,  /* -> ValueError  */
+    BT_ERR_INVALID_CODE = -2, /* a symbol code indexes outside the matrix -> ValueError */
+    BT_ERR_CUDA = -3,         /* -> RuntimeError */
+    BT_ERR_OOM = -4,          /* -> MemoryError  */
+    BT_ERR_RANGE = -5         /* scores may leave the exact integer range -> OverflowError */
+} BtStatus;
+
+/*
+ * Alignment mode.  The fields mirror the reference's run-time switches and
+ * const generics: scoring scheme (scoring.rs:130-147), gap model
+ * (GapPenalty::{Linear,Affine}), LOCAL / TERMINAL_PENALTY (pairwise.rs:348,563)
+ * and full table vs. band (pairwise.rs vs. banded.rs).
+ */
+typedef struct BtParams {
+    int32_t affine;           /* 0: linear gap penalty (gap_open), 1: affine (gap_open, gap_ext) */
+    int32_t gap_open;         /* <= 0 */
+    int32_t gap_ext;          /* <= 0; ignored when !affine */
+    int32_t local;            /* Smith-Waterman instead of Needleman-Wunsch */
+    int32_t terminal_penalty; /* 0: semi-global (terminal gaps free); ignored when local or banded */
+    int32_t use_matrix;       /* 1: substitution matrix, 0: (match, mismatch) */
+    int32_t match_score;
+    int32_t mismatch_score;
+    int32_t n_rows;           /* matrix shape = (alphabet1 size, alphabet2 size) */
+    int32_t n_cols;
+    int32_t banded;           /* 0: align_optimal, 1: align_banded */
+    int32_t code_bytes;       /* element size of the code arrays: 1, 2, 4 or 8 (util.rs:37-52) */
+} BtParams;
+
+/* ---- library / device ------------------------------------------------------------ */
+
+const char *bt_last_error(void);
+const char *bt_version(void);
+int bt_device_count(void);          /* number of CUDA devices, 0 if none / no driver */
+int bt_set_device(int device);      /* device used by the calling thread */
+int bt_get_device(void);
+
+/* page-locked host memory for full-speed asynchronous copies (cudaHostAlloc / cudaFreeHost) */
+void *bt_pinned_alloc(size_t bytes);
+void bt_pinned_free(void *ptr);
+
+/* ---- single pair: the reference's FFI contract -------------------------------------
+ *
+ * code1/code2: contiguous arrays of `code_bytes`-wide unsigned codes (len1, len2
+ * elements).  matrix: row-major int32 (n_rows x n_cols) or NULL when
+ * !use_matrix.  lower_diag/upper_diag: the (already cropped) band, banded only;
+ * len1 <= len2 is the caller's job as in banded.py:215-236.
+ * score_out receives the optimal score.  Unless score_only, *traces_out
+ * receives a trace list holding at most max_number traces in the reference's
+ * emission order (trace.rs:46-92); release it with bt_tracelist_free().
+ */
+typedef struct BtTraceList BtTraceList;
+
+int bt_align_pair(const BtParams *params, const void *code1, int64_t len1,
+                  const void *code2, int64_t len2, const int32_t *matrix,
+                  int64_t lower_diag, int64_t upper_diag, int32_t score_only,
+                  int64_t max_number, int32_t *score_out, BtTraceList **traces_out);
+
+int64_t bt_tracelist_count(const BtTraceList *list);
+int64_t bt_tracelist_length(const BtTraceList *list, int64_t k); /* rows L of trace k */
+/* copies trace k as C-order int64 (L, 2) with -1 gaps (trace.rs:103-130) */
+int bt_tracelist_copy(const BtTraceList *list, int64_t k, int64_t *out);
+void bt_tracelist_free(BtTraceList *list);
+
+/* ---- batch of independent pairs (max_number = 1 semantics) --------------------------
+ *
+ * Pair k aligns codes1[off1[k] .. off1[k+1]) with codes2[off2[k] .. off2[k+1]).
+ * bands: NULL, or 2*n_pairs int64 (lower, upper) per pair, cropped as above.
+ * A batch object keeps its inputs and results resident in HBM:
+ *   create  : validate, H2D copies
+ *   run     : fill + traceback kernels; *device_ms (may be NULL) receives the
+ *             CUDA-event time of exactly those kernels on the batch's stream
+ *   fetch_* : D2H of results
+ * Results: scores (int32 per pair) and, unless score_only, one first-optimal
+ * trace per pair in compact form: trace_len[k] = L, first[2k..2k+1] = table
+ * coordinates of the first alignment column's cell, ops = L step bytes
+ * (0 = both advance, 1 = gap in sequence 1, 2 = gap in sequence 2) in
+ * end-to-start order starting at ops_off[k] = off1[k] + off2[k]
+ * (capacity len1 + len2).  bt_expand_traces() turns them into (L,2) int64.
+ */
+typedef struct BtBatch BtBatch;
+
+int bt_batch_create(const BtParams *params, const void *codes1, const int64_t *off1,
+                    const void *codes2, const int64_t *off2, int64_t n_pairs,
+                    const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                    BtBatch **batch_out);
+int bt_batch_run(BtBatch *batch, float *device_ms);
+int bt_batch_fetch_scores(BtBatch *batch, int32_t *scores_out);
+int bt_batch_fetch_traces(BtBatch *batch, int64_t *trace_len_out, int32_t *first_out,
+                          uint8_t *ops_out);
+/* DP cells the batch updates per run (sum of len1*len2, or in-band in-sequence cells) */
+int64_t bt_batch_cells(const BtBatch *batch);
+/* launches issued by the last bt_batch_run (this library's own kernels only) */
+int64_t bt_batch_launches(const BtBatch *batch);
+/* name of the fill kernel family the batch was routed to ("general_i32", "interseq_s16x2", ...) */
+const char *bt_batch_kernel(const BtBatch *batch);
+void bt_batch_destroy(BtBatch *batch);
+
+/* one-shot convenience: create + run + fetch + destroy; any output may be NULL */
+int bt_align_batch(const BtParams *params, const void *codes1, const int64_t *off1,
+                   const void *codes2, const int64_t *off2, int64_t n_pairs,
+                   const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                   int32_t *scores_out, int64_t *trace_len_out, int32_t *first_out,
+                   uint8_t *ops_out);
+
+/*
+ * Host-side expansion of compact traces into the reference's (L,2) int64 layout.
+ * rows_off[k] (n_pairs+1 entries) = prefix sum of trace_len; out has 2*rows_off[n_pairs]
+ * entries.  bands as in bt_batch_create (NULL for align_optimal).
+ */
+int bt_expand_traces(int64_t n_pairs, const int64_t *trace_len, const int32_t *first,
+                     const uint8_t *ops, const int64_t *ops_off, const int64_t *bands,
+                     const int64_t *rows_off, int64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ALIGN_H */

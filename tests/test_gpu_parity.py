@@ -1,0 +1,361 @@
+"""
+GPU parity tests proper: the CUDA path, called through the C ABI, against the
+CPU oracle and against the committed golden vectors.  Bit-exact scores,
+identical traces (integer work: no tolerance).
+"""
+
+import numpy as np
+import pytest
+
+import biotite_b200 as bt
+from oracle import oracle
+from tests.test_oracle_golden import KNOWN_ANSWERS
+from tests.util import (
+    cas9_sequences,
+    gap_param,
+    golden,
+    oracle_align_banded,
+    oracle_align_optimal,
+)
+
+pytestmark = pytest.mark.gpu
+
+NUC = bt.SubstitutionMatrix.std_nucleotide_matrix
+BLOSUM = bt.SubstitutionMatrix.std_protein_matrix
+
+
+def _same(alis, refs):
+    assert len(alis) == len(refs)
+    for a, r in zip(alis, refs):
+        assert a.score == r.score
+        assert np.array_equal(a.trace, r.trace)
+
+
+# ---- reference golden vectors (every 3rd pair to bound the run time; all param sets) ----
+
+def _golden_subset(method):
+    cases = [c for c in golden()["cases"] if c["method"] == method]
+    pairs = sorted({tuple(c["seq_indices"]) for c in cases})[::3]
+    return [c for c in cases if tuple(c["seq_indices"]) in pairs]
+
+
+@pytest.mark.parametrize("case", _golden_subset("align_optimal"), ids=lambda c: c["file"])
+def test_golden_align_optimal(case):
+    seqs = cas9_sequences()
+    i, j = case["seq_indices"]
+    p = case["params"]
+    gap = gap_param(p["gap_penalty"])
+    ali = bt.align_optimal(seqs[i], seqs[j], BLOSUM(), gap_penalty=gap,
+                           terminal_penalty=p["terminal_penalty"], local=p["local"],
+                           max_number=1)[0]
+    assert ali.get_gapped_sequences() == case["gapped"]
+    assert ali.score == bt.score(ali, BLOSUM(), gap, p["terminal_penalty"])
+    assert ali.score == bt.align_optimal(
+        seqs[i], seqs[j], BLOSUM(), gap_penalty=gap, terminal_penalty=p["terminal_penalty"],
+        local=p["local"], score_only=True)
+
+
+@pytest.mark.parametrize("case", _golden_subset("align_banded"), ids=lambda c: c["file"])
+def test_golden_align_banded(case):
+    seqs = cas9_sequences()
+    i, j = case["seq_indices"]
+    p = case["params"]
+    gap = gap_param(p["gap_penalty"])
+    ali = bt.align_banded(seqs[i], seqs[j], BLOSUM(), tuple(p["band"]), gap_penalty=gap,
+                          local=p["local"], max_number=1)[0]
+    assert ali.get_gapped_sequences() == case["gapped"]
+    assert ali.score == bt.score(ali, BLOSUM(), gap, terminal_penalty=False)
+
+
+def test_golden_batch_all_cases():
+    """All 540 golden alignments through the batched entry points."""
+    seqs = cas9_sequences()
+    cases = golden()["cases"]
+    groups = {}
+    for c in cases:
+        p = c["params"]
+        key = (c["method"], str(p["gap_penalty"]), p["local"], p.get("terminal_penalty", True))
+        groups.setdefault(key, []).append(c)
+    for (method, _, local, term), group in groups.items():
+        gap = gap_param(group[0]["params"]["gap_penalty"])
+        s1 = [seqs[c["seq_indices"][0]] for c in group]
+        s2 = [seqs[c["seq_indices"][1]] for c in group]
+        if method == "align_optimal":
+            res = bt.align_optimal_batch(s1, s2, BLOSUM(), gap, term, local)
+        else:
+            bands = np.array([c["params"]["band"] for c in group])
+            res = bt.align_banded_batch(s1, s2, BLOSUM(), bands, gap, local)
+        for k, c in enumerate(group):
+            assert res.alignment(k).get_gapped_sequences() == c["gapped"], c["file"]
+
+
+# ---- known answers: full co-optimal sets, ordered enumeration ------------------------------
+
+@pytest.mark.parametrize("local,term,gap,s1,s2,expect,score", KNOWN_ANSWERS)
+def test_known_answers(local, term, gap, s1, s2, expect, score):
+    seq1, seq2 = bt.NucleotideSequence(s1), bt.NucleotideSequence(s2)
+    alis = bt.align_optimal(seq1, seq2, NUC(), gap_penalty=gap, terminal_penalty=term, local=local)
+    refs = oracle_align_optimal(seq1, seq2, NUC(), gap_penalty=gap, terminal_penalty=term, local=local)
+    assert {str(a) for a in alis} == expect
+    _same(alis, refs)
+    assert all(a.score == score for a in alis)
+
+
+def test_readme_example_enumeration_order():
+    g = golden()["readme_avidin_streptavidin"]
+    top, bottom = g["gapped"]
+    seq1 = bt.ProteinSequence(top.replace("-", ""))
+    seq2 = bt.ProteinSequence(bottom.replace("-", ""))
+    alis = bt.align_optimal(seq1, seq2, BLOSUM(), gap_penalty=(-10, -1), terminal_penalty=False)
+    assert len(alis) == 6 and alis[0].score == 133
+    assert alis[0].get_gapped_sequences() == [top, bottom]
+
+
+# ---- randomised property tests against the oracle ----------------------------------------------
+
+def _random_seq(rng, n, alphabet_size=4, cls=None):
+    if cls is None:
+        seq = bt.NucleotideSequence()
+    else:
+        seq = cls()
+    seq.code = rng.integers(0, alphabet_size, n)
+    return seq
+
+
+@pytest.mark.parametrize("local", [False, True])
+@pytest.mark.parametrize("term", [False, True])
+@pytest.mark.parametrize("gap", [-5, -8, (-8, -8), (-7, -1), (-1, -1), (0, 0), (-3, 0)])
+@pytest.mark.parametrize("seed", range(3))
+def test_random_nucleotide_pairs(local, term, gap, seed):
+    rng = np.random.default_rng(seed)
+    seq1 = _random_seq(rng, rng.integers(1, 60))
+    seq2 = _random_seq(rng, rng.integers(1, 60))
+    for scoring in (NUC(), (5, -5)):
+        alis = bt.align_optimal(seq1, seq2, scoring, gap_penalty=gap, terminal_penalty=term,
+                                local=local, max_number=50)
+        refs = oracle_align_optimal(seq1, seq2, scoring, gap_penalty=gap, terminal_penalty=term,
+                                    local=local, max_number=50)
+        _same(alis, refs)
+        assert bt.align_optimal(seq1, seq2, scoring, gap_penalty=gap, terminal_penalty=term,
+                                local=local, score_only=True) == refs[0].score
+
+
+@pytest.mark.parametrize("n,m", [(0, 0), (0, 5), (5, 0), (1, 1), (1, 7), (7, 1)])
+@pytest.mark.parametrize("local", [False, True])
+@pytest.mark.parametrize("gap", [-6, (-6, -2)])
+def test_edge_shapes(n, m, local, gap):
+    rng = np.random.default_rng(n * 10 + m)
+    seq1, seq2 = _random_seq(rng, n), _random_seq(rng, m)
+    for term in (True, False):
+        alis = bt.align_optimal(seq1, seq2, NUC(), gap_penalty=gap, terminal_penalty=term,
+                                local=local, max_number=5)
+        refs = oracle_align_optimal(seq1, seq2, NUC(), gap_penalty=gap, terminal_penalty=term,
+                                    local=local, max_number=5)
+        _same(alis, refs)
+
+
+def test_all_ties_and_all_negative():
+    a = bt.NucleotideSequence("AAAAAAAA")
+    c = bt.NucleotideSequence("CCCCCC")
+    for seq1, seq2 in ((a, a), (a, c)):
+        for local in (False, True):
+            for gap in (-4, (-4, -4), (-5, -1)):
+                alis = bt.align_optimal(seq1, seq2, NUC(), gap_penalty=gap, local=local, max_number=30)
+                refs = oracle_align_optimal(seq1, seq2, NUC(), gap_penalty=gap, local=local, max_number=30)
+                _same(alis, refs)
+
+
+def test_wide_codes_and_positional_matrix():
+    rng = np.random.default_rng(5)
+    p1 = _random_seq(rng, 70, 20, bt.ProteinSequence)
+    p2 = _random_seq(rng, 90, 20, bt.ProteinSequence)
+    pos_matrix, q1, q2 = BLOSUM().as_positional(p1, p2)
+    plain = bt.align_optimal(p1, p2, BLOSUM(), gap_penalty=(-10, -1), max_number=1)[0]
+    # PositionalSequence codes are uint8 here; force a wide dtype through a big alphabet
+    alph = bt.Alphabet(range(70000))
+    w1 = bt.GeneralSequence(alph); w1.code = q1.code
+    w2 = bt.GeneralSequence(alph); w2.code = q2.code
+    big = np.zeros((70, 90), dtype=np.int32) + pos_matrix.score_matrix()
+    from biotite_b200.pairwise import _native_align_pair
+    traces, score = _native_align_pair(
+        np.ascontiguousarray(w1.code, np.uint32), np.ascontiguousarray(w2.code, np.uint32),
+        big, (-10, -1), True, False, False, 1)
+    assert score == plain.score and np.array_equal(traces[0], plain.trace)
+    pos = bt.align_optimal(q1, q2, pos_matrix, gap_penalty=(-10, -1), max_number=1)[0]
+    assert pos.score == plain.score and np.array_equal(pos.trace, plain.trace)
+
+
+def test_scaled_scores_need_int32():
+    # test_statistics.py:118-177 scales scores x1000 -> 16-bit lanes would overflow
+    rng = np.random.default_rng(11)
+    s1 = _random_seq(rng, 300, 20, bt.ProteinSequence)
+    s2 = _random_seq(rng, 300, 20, bt.ProteinSequence)
+    alph = bt.ProteinSequence.alphabet
+    scaled = bt.SubstitutionMatrix(alph, alph, BLOSUM().score_matrix() * 1000)
+    for local in (False, True):
+        got = bt.align_optimal(s1, s2, scaled, gap_penalty=(-10000, -1000), local=local, max_number=1)
+        ref = oracle_align_optimal(s1, s2, scaled, gap_penalty=(-10000, -1000), local=local, max_number=1)
+        _same(got, ref)
+        res = bt.align_optimal_batch([s1, s2], [s2, s1], scaled, (-10000, -1000), True, local)
+        assert res.scores[0] == ref[0].score and np.array_equal(res.trace(0), ref[0].trace)
+
+
+def test_invalid_code_is_rejected():
+    seq1 = bt.NucleotideSequence("ACGT")
+    seq2 = bt.NucleotideSequence("ACGT")
+    seq2.code = np.array([0, 1, 2, 200], dtype=np.uint8)
+    with pytest.raises(ValueError, match="outside the substitution matrix"):
+        bt.align_optimal(seq1, seq2, NUC())
+
+
+# ---- banded -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("gap", [-10, (-10, -1)])
+@pytest.mark.parametrize("local", [False, True])
+@pytest.mark.parametrize("band_width", [2, 5, 20, 100])
+def test_banded_cyclotide_like(gap, local, band_width):
+    # same shape as tests/sequence/align/test_banded.py:11-43 (31 vs 30 residues)
+    s1 = bt.ProteinSequence("gvpcgescvfipcisaaigcsckskvcyrnasdf".upper()[:31])
+    s2 = bt.ProteinSequence("gipcgescvwipcitsaigcsckskvcyrnsd".upper()[:30])
+    for a, b in ((s1, s2), (s2, s1)):
+        got = bt.align_banded(a, b, BLOSUM(), (-band_width, band_width), gap_penalty=gap,
+                              local=local, max_number=20)
+        ref = oracle_align_banded(a, b, BLOSUM(), (-band_width, band_width), gap_penalty=gap,
+                                  local=local, max_number=20)
+        _same(got, ref)
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("gap", [-7, (-7, -2)])
+@pytest.mark.parametrize("local", [False, True])
+def test_banded_random(seed, gap, local):
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(5, 80)), int(rng.integers(5, 80))
+    seq1, seq2 = _random_seq(rng, n), _random_seq(rng, m)
+    lo = int(rng.integers(-n, m))
+    band = (lo, lo + int(rng.integers(0, 30)))
+    try:
+        ref = oracle_align_banded(seq1, seq2, NUC(), band, gap_penalty=gap, local=local, max_number=10)
+    except ValueError:
+        with pytest.raises(ValueError):
+            bt.align_banded(seq1, seq2, NUC(), band, gap_penalty=gap, local=local)
+        return
+    got = bt.align_banded(seq1, seq2, NUC(), band, gap_penalty=gap, local=local, max_number=10)
+    _same(got, ref)
+    assert bt.align_banded(seq1, seq2, NUC(), band, gap_penalty=gap, local=local,
+                           score_only=True) == ref[0].score
+
+
+def test_banded_long_excerpt_maps_back():
+    # tests/sequence/align/test_banded.py:46-78 (shortened target)
+    rng = np.random.default_rng(0)
+    target = _random_seq(rng, 20000)
+    start = 11111
+    query = target[start:start + 500]
+    diag = start
+    alis = bt.align_banded(query, target, NUC(), (diag - 100 + 30, diag + 100 + 30))
+    assert len(alis) == 1
+    trace = alis[0].trace
+    trace = trace[(trace != -1).all(axis=1)]
+    assert np.array_equal(trace[:, 1] - trace[:, 0], np.full(len(trace), start))
+    assert len(trace) == 500
+
+
+# ---- batched entry points ---------------------------------------------------------------------------
+
+def _random_batch(rng, n_pairs, lo, hi, alphabet=20):
+    len1 = rng.integers(lo, hi, n_pairs)
+    len2 = rng.integers(lo, hi, n_pairs)
+    off1 = np.concatenate(([0], np.cumsum(len1))).astype(np.int64)
+    off2 = np.concatenate(([0], np.cumsum(len2))).astype(np.int64)
+    codes1 = rng.integers(0, alphabet, off1[-1]).astype(np.uint8)
+    codes2 = rng.integers(0, alphabet, off2[-1]).astype(np.uint8)
+    return codes1, off1, codes2, off2
+
+
+@pytest.mark.parametrize("gap", [(-10, -1), -10, (-4, -4), (-11, 0)])
+@pytest.mark.parametrize("local,term", [(False, True), (False, False), (True, True)])
+def test_batch_matches_oracle(gap, local, term):
+    rng = np.random.default_rng(42)
+    codes1, off1, codes2, off2 = _random_batch(rng, 300, 1, 200)
+    matrix = BLOSUM().score_matrix()
+    # make a third of the pairs homologous so that traces have real structure
+    for k in range(0, 300, 3):
+        n = min(off1[k + 1] - off1[k], off2[k + 1] - off2[k])
+        codes2[off2[k]:off2[k] + n] = codes1[off1[k]:off1[k] + n]
+        flip = rng.random(n) < 0.15
+        codes2[off2[k]:off2[k] + n][flip] = rng.integers(0, 20, int(flip.sum()))
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, gap, term, local) as batch:
+        batch.run()
+        res = batch.fetch()
+    ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, matrix, gap, term, local)
+    assert np.array_equal(res.scores, ref_scores)
+    traces = res.traces()
+    for k in range(300):
+        assert np.array_equal(traces[k], ref_traces[k]), k
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, gap, term, local, score_only=True) as batch:
+        batch.run()
+        assert np.array_equal(batch.fetch().scores, ref_scores)
+
+
+def test_batch_c2_shape_properties():
+    """BASELINE config 2 shape (global affine BLOSUM62, ~300 aa) at a size the
+    oracle cannot check exhaustively: re-score every trace instead."""
+    rng = np.random.default_rng(1)
+    n_pairs = 20000
+    codes1, off1, codes2, off2 = _random_batch(rng, n_pairs, 200, 400)
+    matrix = BLOSUM().score_matrix()
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, (-10, -1), True, False) as batch:
+        batch.run()
+        res = batch.fetch()
+    flat, rows_off = res.traces_flat()
+    # every trace consumes both sequences completely, in order
+    for col, off in ((0, off1), (1, off2)):
+        present = flat[:, col] != -1
+        counts = np.add.reduceat(present.astype(np.int64), rows_off[:-1])
+        assert np.array_equal(counts, np.diff(off))
+    # rescoring: substitution scores + affine gap costs == reported score
+    pair_of_row = np.repeat(np.arange(n_pairs), np.diff(rows_off))
+    a, b = flat[:, 0], flat[:, 1]
+    both = (a != -1) & (b != -1)
+    sub = np.zeros(len(flat), dtype=np.int64)
+    sub[both] = matrix[codes1[off1[pair_of_row[both]] + a[both]], codes2[off2[pair_of_row[both]] + b[both]]]
+    total = np.add.reduceat(sub, rows_off[:-1])
+    for col in (a, b):
+        gap = col == -1
+        prev = np.concatenate(([False], gap[:-1]))
+        prev[rows_off[:-1]] = False
+        total += np.add.reduceat(np.where(gap, np.where(prev, -1, -10), 0), rows_off[:-1])
+    assert np.array_equal(total, res.scores.astype(np.int64))
+    # spot-check against the oracle
+    idx = rng.choice(n_pairs, 64, replace=False)
+    for k in idx:
+        t, s = oracle.align_optimal(codes1[off1[k]:off1[k + 1]], codes2[off2[k]:off2[k + 1]],
+                                    matrix, (-10, -1), True, False, False, 1)
+        assert s == res.scores[k] and np.array_equal(t[0], res.trace(k))
+
+
+def test_banded_batch_matches_oracle():
+    rng = np.random.default_rng(3)
+    n_pairs = 40
+    seqs1, seqs2, bands = [], [], []
+    for k in range(n_pairs):
+        n = int(rng.integers(300, 700))
+        s1 = _random_seq(rng, n)
+        code2 = s1.code.copy()
+        mut = rng.random(n) < 0.05
+        code2[mut] = rng.integers(0, 4, int(mut.sum()))
+        keep = rng.random(n) > 0.01
+        s2 = bt.NucleotideSequence()
+        s2.code = code2[keep]
+        if k % 2:
+            s1, s2 = s2, s1
+        seqs1.append(s1); seqs2.append(s2); bands.append((-16, 16))
+    for gap in ((-10, -1), -6):
+        for local in (False, True):
+            res = bt.align_banded_batch(seqs1, seqs2, NUC(), np.array(bands), gap, local)
+            for k in range(n_pairs):
+                ref = oracle_align_banded(seqs1[k], seqs2[k], NUC(), bands[k], gap_penalty=gap,
+                                          local=local, max_number=1)[0]
+                assert res.scores[k] == ref.score
+                assert np.array_equal(res.trace(k), ref.trace)
