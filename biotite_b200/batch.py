@@ -121,6 +121,12 @@ class DeviceBatch:
         _cabi.check(self._lib.bt_batch_run(self._handle, ctypes.byref(ms)))
         return float(ms.value)
 
+    def timings(self):
+        """``(fill_ms, traceback_ms)`` of the last :meth:`run` (CUDA events)."""
+        fill, back = ctypes.c_float(0.0), ctypes.c_float(0.0)
+        _cabi.check(self._lib.bt_batch_timings(self._handle, ctypes.byref(fill), ctypes.byref(back)))
+        return float(fill.value), float(back.value)
+
     def fetch(self, out=None):
         """D2H copy of scores (and compact traces); returns a :class:`BatchResult`."""
         n = self.n_pairs

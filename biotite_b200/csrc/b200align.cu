@@ -19,6 +19,7 @@
 #include "general_kernel.cuh"
 #include "host_trace.hpp"
 #include "interseq_kernel.cuh"
+#include "microbench.cuh"
 
 using namespace bt;
 
@@ -157,7 +158,21 @@ struct BtBatch {
     DevBuf score, start_idx, start_state, end_vals, trace_len, first, ops, flag;
     InterseqPlan interseq;  // state of the packed 16-bit route
     bool ran = false;
+    // per-phase device timing: events[3k..3k+2] bracket fill and traceback of step k
+    std::vector<cudaEvent_t> phase_events;
+    size_t phase_used = 0;
+    float fill_ms = 0.f, traceback_ms = 0.f;
+    cudaError_t mark_phase() {
+        if (phase_used == phase_events.size()) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return err;
+            phase_events.push_back(e);
+        }
+        return cudaEventRecord(phase_events[phase_used++], stream);
+    }
     ~BtBatch() {
+        for (cudaEvent_t e : phase_events) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -250,6 +265,7 @@ static int run_general(BtBatch *b, bool traceback) {
         int threads = std::min(512, std::max(64, (diag_len + 31) / 32 * 32));
         if (!b->score_only && b->P.banded)
             CUDA_TRY(cudaMemsetAsync(b->dirs.ptr, 0, (size_t)c.dir_bytes, b->stream));
+        CUDA_TRY(b->mark_phase());
         if (smem_ints <= kMaxSmemInts) {
             V.pair_begin = c.begin; V.pair_end = c.end;
             CUDA_TRY(dispatch_general_fill(D, V, (int)(c.end - c.begin), threads,
@@ -270,11 +286,13 @@ static int run_general(BtBatch *b, bool traceback) {
                 b->launches++;
             }
         }
+        CUDA_TRY(b->mark_phase());
         if (traceback && !b->score_only) {
             V.pair_begin = c.begin; V.pair_end = c.end;
             CUDA_TRY(dispatch_general_traceback(D, V, c.end - c.begin, b->stream));
             b->launches++;
         }
+        CUDA_TRY(b->mark_phase());
     }
     return BT_OK;
 }
@@ -466,6 +484,7 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
     if (!b) return fail(BT_ERR_INVALID_ARG, "batch is NULL");
     CUDA_TRY(cudaSetDevice(b->device));
     b->launches = 0;
+    b->phase_used = 0;
     CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
     int st = BT_OK;
     if (b->n_pairs > 0) {
@@ -473,7 +492,11 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
             InterseqIO io{b->codes1.ptr, b->codes2.ptr, b->off1.as<int64_t>(), b->off2.as<int64_t>(),
                           b->matrix.as<int32_t>(), b->score.as<int32_t>(), b->trace_len.as<int64_t>(),
                           b->first.as<int32_t>(), b->ops.as<uint8_t>()};
-            cudaError_t e = interseq_run(b->interseq, io, b->stream, &b->launches);
+            cudaError_t e = b->mark_phase();
+            if (e == cudaSuccess) e = interseq_run_fill(b->interseq, io, b->stream, &b->launches);
+            if (e == cudaSuccess) e = b->mark_phase();
+            if (e == cudaSuccess) e = interseq_run_traceback(b->interseq, io, b->stream, &b->launches);
+            if (e == cudaSuccess) e = b->mark_phase();
             if (e != cudaSuccess) st = fail(BT_ERR_CUDA, "inter-sequence kernels: %s", cudaGetErrorString(e));
         } else {
             st = run_general(b, true);
@@ -483,7 +506,22 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
     CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, b->ev0, b->ev1));
+    b->fill_ms = b->traceback_ms = 0.f;
+    for (size_t k = 0; k + 2 < b->phase_used; k += 3) {
+        float f = 0.f, t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&f, b->phase_events[k], b->phase_events[k + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&t, b->phase_events[k + 1], b->phase_events[k + 2]));
+        b->fill_ms += f;
+        b->traceback_ms += t;
+    }
     b->ran = true;
+    return BT_OK;
+}
+
+extern "C" int bt_batch_timings(const BtBatch *b, float *fill_ms, float *traceback_ms) {
+    if (!b || !b->ran) return fail(BT_ERR_INVALID_ARG, "bt_batch_run has not been called");
+    if (fill_ms) *fill_ms = b->fill_ms;
+    if (traceback_ms) *traceback_ms = b->traceback_ms;
     return BT_OK;
 }
 
@@ -589,6 +627,7 @@ extern "C" int bt_align_pair(const BtParams *params, const void *code1, int64_t 
     std::unique_ptr<BtBatch> b(raw);
     const bool first_only = (max_number == 1);
     CUDA_TRY(cudaSetDevice(b->device));
+    b->phase_used = 0;
     st = run_general(b.get(), first_only);
     if (st) return st;
     b->ran = true;
@@ -621,6 +660,7 @@ extern "C" int bt_align_pair(const BtParams *params, const void *code1, int64_t 
     if (P.local) {
         // second pass tags every cell whose M equals the optimum (pairwise.rs:536-551)
         b->D.mark = 1; b->D.mark_value = score;
+        b->phase_used = 0;
         st = run_general(b.get(), false);
         if (st) return st;
     }
@@ -682,5 +722,41 @@ extern "C" int bt_align_pair(const BtParams *params, const void *code1, int64_t 
         list->traces.push_back(rows);
     }
     *traces_out = list.release();
+    return BT_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// roofline denominators
+// ---------------------------------------------------------------------------------------
+extern "C" int bt_microbench(int kind, double *lane_instr_per_s) {
+    if (!lane_instr_per_s || kind < 0 || kind > 2) return fail(BT_ERR_INVALID_ARG, "bad microbench kind");
+    if (bt_device_count() <= 0) return fail(BT_ERR_CUDA, "no CUDA device available");
+    cudaDeviceProp prop;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;
+    DevBuf out;
+    CUDA_TRY(out.alloc((size_t)threads * blocks * 4));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        if (kind == 0) microbench_kernel<0><<<blocks, threads>>>(out.as<uint32_t>(), iters, 12345u);
+        else if (kind == 1) microbench_kernel<1><<<blocks, threads>>>(out.as<uint32_t>(), iters, 12345u);
+        else microbench_kernel<2><<<blocks, threads>>>(out.as<uint32_t>(), iters, 12345u);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double instr = (double)threads * blocks * iters * microbench_instr_per_iter(kind);
+        if (rep > 0) best = std::max(best, instr / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *lane_instr_per_s = best;
     return BT_OK;
 }

@@ -14,7 +14,10 @@ inline bool interseq_eligible(const BtParams &, const std::vector<int64_t> &, co
 inline int interseq_prepare(InterseqPlan &, const BtParams &, const std::vector<int64_t> &,
                             const std::vector<int64_t> &, int64_t, int, int32_t, int32_t, int64_t *,
                             cudaStream_t) { return BT_ERR_INVALID_ARG; }
-inline cudaError_t interseq_run(InterseqPlan &, const InterseqIO &, cudaStream_t, int64_t *) {
+inline cudaError_t interseq_run_fill(InterseqPlan &, const InterseqIO &, cudaStream_t, int64_t *) {
+    return cudaErrorNotSupported;
+}
+inline cudaError_t interseq_run_traceback(InterseqPlan &, const InterseqIO &, cudaStream_t, int64_t *) {
     return cudaErrorNotSupported;
 }
 }  // namespace bt

@@ -119,6 +119,8 @@ int bt_batch_run(BtBatch *batch, float *device_ms);
 int bt_batch_fetch_scores(BtBatch *batch, int32_t *scores_out);
 int bt_batch_fetch_traces(BtBatch *batch, int64_t *trace_len_out, int32_t *first_out,
                           uint8_t *ops_out);
+/* device time of the last run split into DP fill and traceback kernels (CUDA events) */
+int bt_batch_timings(const BtBatch *batch, float *fill_ms, float *traceback_ms);
 /* DP cells the batch updates per run (sum of len1*len2, or in-band in-sequence cells) */
 int64_t bt_batch_cells(const BtBatch *batch);
 /* launches issued by the last bt_batch_run (this library's own kernels only) */
@@ -142,6 +144,18 @@ int bt_align_batch(const BtParams *params, const void *codes1, const int64_t *of
 int bt_expand_traces(int64_t n_pairs, const int64_t *trace_len, const int32_t *first,
                      const uint8_t *ops, const int64_t *ops_off, const int64_t *bands,
                      const int64_t *rows_off, int64_t *out);
+
+/*
+ * Roofline denominators measured on the current device: register-only loops of
+ * the instructions the fill kernels are made of.
+ *   kind 0: packed 16-bit DPX (VIADDMNMX.S16x2 / VIMNMX3.S16x2), result in
+ *           lane-instructions per second (one lane-instruction updates two
+ *           16-bit values)
+ *   kind 1: 32-bit DPX (VIADDMNMX / VIMNMX3), lane-instructions per second
+ *   kind 2: mixed ALU + FMA-pipe integer stream (VIADDMNMX.S16x2 + IMAD), lane-
+ *           instructions per second - the issue-rate ceiling
+ */
+int bt_microbench(int kind, double *lane_instr_per_s);
 
 #ifdef __cplusplus
 }
