@@ -1,23 +1,444 @@
-// placeholder, replaced by the packed 16-bit inter-sequence kernels
+// Inter-sequence packed 16-bit kernels: the throughput path for batches of short
+// pairs (BASELINE config 2: 10^6 pairs of ~300 aa, global affine, score + trace).
+//
+// Mapping.  Pairs are sorted by (len1, len2) and dealt to warps in groups of 64.
+// Every lane owns TWO pairs, one in each 16-bit half of its registers, and sweeps
+// their DP tables in stripes of R rows, column by column: the stripe's left
+// neighbours (M, F1, H of the previous column) live in registers, the row above
+// the stripe comes from a lane-interleaved row buffer, the substitution scores
+// come from a bank-conflict-free shared-memory table (one private copy per lane),
+// and the recurrence runs on the packed DPX instructions VIADD.16x2 / VIMNMX.S16x2
+// / VIADDMNMX.S16x2.  There is no intra-warp communication.
+//
+// Recurrence (reference: src/rust/sequence/align/pairwise.rs:608-681).  The
+// reference keeps three states M, G1, G2 per cell, with G1 fed from M and G1
+// only.  The kernel carries M, F1 = G1 - open, F2 = G2 - open and
+// H = max(M, G1, G2):
+//     M  = H(i-1,j-1) + sim
+//     F1 = max(M(i,j-1), F1(i,j-1) + ext)        o1 = [M(i,j-1) >= F1(i,j-1) + ext]
+//     F2 = max(M(i-1,j), F2(i-1,j) + ext)        o2 = [M(i-1,j) >= F2(i-1,j) + ext]
+//     T  = max(F1, F2)                           hG = [F1 >= F2]
+//     H  = max(M, T + open)                      hM = [M >= T + open]
+// The four predicates are exactly the reference's first-priority choices
+// (cell.rs:219-254, :331-394: Match <- M, G1, G2 in that order; Gap1 <- M before
+// G1; Gap2 <- M before G2) and are stored as one nibble per cell; the traceback
+// kernel walks them.  Sixteen-bit lanes are used only when the host has proven
+// that no finite value can leave the exact range (interseq_eligible).
 #pragma once
+#include <algorithm>
+#include <cstring>
 #include <vector>
+
 #include "../../include/b200align.h"
 #include "common.cuh"
+
 namespace bt {
-struct InterseqPlan {};
-struct InterseqIO {
-    const void *codes1, *codes2; const int64_t *off1, *off2; const int32_t *matrix;
-    int32_t *score; int64_t *trace_len; int32_t *first; uint8_t *ops;
+
+constexpr int IS_R = 16;            // rows per stripe
+constexpr int IS_THREADS = 128;     // 4 warps per block
+constexpr int IS_MAX_LEN = 2000;    // longest sequence routed here
+constexpr int IS_ROWW = 128;        // bytes per table entry row: 32 lanes x 4 bytes
+
+// One group of 64 pairs handled by one warp.
+struct WarpDesc {
+    int64_t dir_off;      // first 32-bit word of the group's direction nibbles
+    int64_t rowbuf_off;   // first entry of the group's row buffer
+    int64_t rowcode_off;  // first uint16 of the group's lane-interleaved row codes
+    int64_t colcode_off;  // first uint16 of the group's lane-interleaved column codes
+    int32_t nmax, mmax;   // longest first / second sequence of the group
+    int32_t stripes, pad;
 };
-inline bool interseq_eligible(const BtParams &, const std::vector<int64_t> &, const std::vector<int64_t> &,
-                              int64_t, int32_t, int32_t) { return false; }
-inline int interseq_prepare(InterseqPlan &, const BtParams &, const std::vector<int64_t> &,
-                            const std::vector<int64_t> &, int64_t, int, int32_t, int32_t, int64_t *,
-                            cudaStream_t) { return BT_ERR_INVALID_ARG; }
-inline cudaError_t interseq_run_fill(InterseqPlan &, const InterseqIO &, cudaStream_t, int64_t *) {
-    return cudaErrorNotSupported;
+
+struct InterseqConst {
+    int32_t gap_open, gap_ext, neg;  // neg: the 16-bit "minus infinity"
+    int32_t n_rows, n_cols;
+    int32_t score_only;
+};
+
+// Host-side plan of one batch.
+struct InterseqPlan {
+    int64_t n_pairs = 0, n_groups = 0;
+    int64_t dir_words = 0, rowbuf_entries = 0, rowcodes = 0, colcodes = 0;
+    InterseqConst C{};
+    std::vector<int32_t> order;        // sorted position -> pair id (padded with -1)
+    std::vector<WarpDesc> desc;
+    void *d_order = nullptr, *d_desc = nullptr, *d_rowcodes = nullptr, *d_colcodes = nullptr;
+    void *d_dirs = nullptr, *d_rowbuf = nullptr, *d_table = nullptr;
+    ~InterseqPlan() {
+        for (void *p : {d_order, d_desc, d_rowcodes, d_colcodes, d_dirs, d_rowbuf, d_table})
+            if (p) cudaFree(p);
+    }
+};
+
+struct InterseqIO {
+    const void *codes1, *codes2;
+    const int64_t *off1, *off2;
+    const int32_t *matrix;
+    int32_t *score;
+    int64_t *trace_len;
+    int32_t *first;
+    uint8_t *ops;
+};
+
+// ---------------------------------------------------------------------------------------
+// eligibility: proven-exact 16-bit range (see DESIGN.md "16-bit safety")
+// ---------------------------------------------------------------------------------------
+inline bool interseq_eligible(const BtParams &P, const std::vector<int64_t> &off1,
+                              const std::vector<int64_t> &off2, int64_t n_pairs, int32_t min_score,
+                              int32_t max_score) {
+    if (!P.affine || P.banded || P.local || !P.terminal_penalty || !P.use_matrix) return false;
+    if (P.code_bytes != 1 || n_pairs < 64) return false;
+    if ((int64_t)P.n_rows * P.n_cols * IS_ROWW > 96 * 1024 || P.n_rows > 255 || P.n_cols > 255) return false;
+    int64_t nmax = 0, mmax = 0;
+    for (int64_t k = 0; k < n_pairs; k++) {
+        const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
+        if (n < 1 || m < 1 || n > IS_MAX_LEN || m > IS_MAX_LEN) return false;
+        nmax = std::max(nmax, n); mmax = std::max(mmax, m);
+    }
+    const int64_t open = P.gap_open, ext = P.gap_ext;
+    const int64_t mn = std::min<int64_t>(min_score, 0), mx = std::max<int64_t>(max_score, 0);
+    const int64_t neg = -32768 - open - ext - mn;                         // one open/ext and one sim may be added
+    const int64_t lowest = 3 * open + (nmax + mmax + 2 + IS_R) * ext + 2 * mn;  // lowest finite value
+    const int64_t highest = std::min(nmax, mmax) * mx - open + mx;        // highest finite value (F = G - open)
+    return lowest > neg + 1 && highest < 32767;
 }
-inline cudaError_t interseq_run_traceback(InterseqPlan &, const InterseqIO &, cudaStream_t, int64_t *) {
-    return cudaErrorNotSupported;
+
+// ---------------------------------------------------------------------------------------
+// batch packer: lane-interleaved codes of each group
+// ---------------------------------------------------------------------------------------
+__global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes2, const int64_t *off1,
+                                     const int64_t *off2, const int32_t *order, const WarpDesc *desc,
+                                     uint16_t *rowcodes, uint16_t *colcodes, int64_t n_groups) {
+    const int64_t g = blockIdx.x;
+    if (g >= n_groups) return;
+    const WarpDesc d = desc[g];
+    const int rows = d.stripes * IS_R;
+    // thread t serves lane t & 31 and walks positions with stride blockDim/32
+    const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5, nsub = blockDim.x >> 5;
+    const int32_t p_lo = order[g * 64 + 2 * lane], p_hi = order[g * 64 + 2 * lane + 1];
+    int64_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
+    int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
+    if (p_lo >= 0) { a_lo = off1[p_lo]; n_lo = (int)(off1[p_lo + 1] - a_lo); b_lo = off2[p_lo]; m_lo = (int)(off2[p_lo + 1] - b_lo); }
+    if (p_hi >= 0) { a_hi = off1[p_hi]; n_hi = (int)(off1[p_hi + 1] - a_hi); b_hi = off2[p_hi]; m_hi = (int)(off2[p_hi + 1] - b_hi); }
+    for (int i = sub; i < rows; i += nsub) {
+        const uint32_t lo = i < n_lo ? codes1[a_lo + i] : 0, hi = i < n_hi ? codes1[a_hi + i] : 0;
+        rowcodes[d.rowcode_off + (int64_t)i * 32 + lane] = (uint16_t)(lo | (hi << 8));
+    }
+    for (int j = sub; j < d.mmax; j += nsub) {
+        const uint32_t lo = j < m_lo ? codes2[b_lo + j] : 0, hi = j < m_hi ? codes2[b_hi + j] : 0;
+        colcodes[d.colcode_off + (int64_t)j * 32 + lane] = (uint16_t)(lo | (hi << 8));
+    }
 }
+
+// ---------------------------------------------------------------------------------------
+// fill
+// ---------------------------------------------------------------------------------------
+
+// max of two packed s16 pairs; adds `c_lo` / `c_hi` to `acc` where the FIRST operand attains
+// the maximum of the low / high half (a >= b).  ptxas fuses the compare pattern into one
+// VIMNMX.S16x2 with two predicate outputs.
+#define BT_MAX_PRED(out, a, b, acc_lo, acc_hi, c)                                        \
+    asm("{\n\t.reg .pred pl, ph;\n\t.reg .s16 x0, x1, y0, y1;\n\t"                      \
+        "max.s16x2 %0, %3, %4;\n\t"                                                      \
+        "mov.b32 {x0, x1}, %0;\n\tmov.b32 {y0, y1}, %3;\n\t"                             \
+        "setp.eq.s16 pl, x0, y0;\n\tsetp.eq.s16 ph, x1, y1;\n\t"                         \
+        "@pl add.u32 %1, %1, %5;\n\t@ph add.u32 %2, %2, %5;\n\t}"                        \
+        : "=r"(out), "+r"(acc_lo), "+r"(acc_hi)                                          \
+        : "r"(a), "r"(b), "r"(c))
+
+template <bool TRACED>
+__global__ void __launch_bounds__(IS_THREADS)
+interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
+                     const int32_t *__restrict__ order, const int64_t *__restrict__ off1,
+                     const int64_t *__restrict__ off2, const int32_t *__restrict__ matrix,
+                     const uint16_t *__restrict__ rowcodes, const uint16_t *__restrict__ colcodes,
+                     uint32_t *__restrict__ rowbuf, uint32_t *__restrict__ dirs,
+                     int32_t *__restrict__ score, int64_t n_groups) {
+    extern __shared__ uint32_t table[];  // [b][a][lane]: zero-extended s16 score, one copy per lane
+    const int lane = threadIdx.x & 31;
+    {
+        const int entries = C.n_rows * C.n_cols;
+        for (int e = threadIdx.x >> 5; e < entries; e += IS_THREADS / 32) {
+            const int a = e / C.n_cols, b = e % C.n_cols;
+            table[(b * C.n_rows + a) * 32 + lane] = (uint32_t)matrix[e] & 0xffffu;
+        }
+    }
+    __syncthreads();
+    const int64_t g = (int64_t)blockIdx.x * (IS_THREADS / 32) + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    const WarpDesc d = desc[g];
+    const int32_t p_lo = order[g * 64 + 2 * lane], p_hi = order[g * 64 + 2 * lane + 1];
+    int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
+    if (p_lo >= 0) { n_lo = (int)(off1[p_lo + 1] - off1[p_lo]); m_lo = (int)(off2[p_lo + 1] - off2[p_lo]); }
+    if (p_hi >= 0) { n_hi = (int)(off1[p_hi + 1] - off1[p_hi]); m_hi = (int)(off2[p_hi + 1] - off2[p_hi]); }
+
+    const uint32_t ext2 = ((uint32_t)C.gap_ext & 0xffffu) * 0x10001u;
+    const uint32_t open2 = ((uint32_t)C.gap_open & 0xffffu) * 0x10001u;
+    const uint32_t neg2 = ((uint32_t)C.neg & 0xffffu) * 0x10001u;
+    const uint32_t col_stride = (uint32_t)C.n_rows * IS_ROWW;  // bytes between column letters
+    const char *tbase = (const char *)table + lane * 4;
+
+    const uint16_t *rc = rowcodes + d.rowcode_off + lane;
+    const uint16_t *cc = colcodes + d.colcode_off + lane;
+    uint32_t *rb_m = rowbuf + d.rowbuf_off * 3 + lane;            // [j][lane] planes: M, F2, H
+    uint32_t *rb_f = rb_m + (int64_t)d.mmax * 32;
+    uint32_t *rb_h = rb_f + (int64_t)d.mmax * 32;
+    uint4 *dir = TRACED ? (uint4 *)(dirs + d.dir_off) + lane : nullptr;
+
+    int32_t best_lo = 0, best_hi = 0;
+    for (int s = 0; s < d.stripes; s++) {
+        const int r0 = s * IS_R;  // rows r0+1 .. r0+R of the DP table
+        uint32_t rp_lo[IS_R], rp_hi[IS_R], Ml[IS_R], F1l[IS_R], Hl[IS_R];
+#pragma unroll
+        for (int r = 0; r < IS_R; r++) {
+            const uint32_t v = rc[(int64_t)(r0 + r) * 32];
+            rp_lo[r] = (v & 0xffu) * IS_ROWW;
+            rp_hi[r] = (v >> 8) * IS_ROWW;
+            // column 0 (pairwise.rs:707-745): M = G1 = -inf, H = G2 = open + (i-1)*ext
+            Ml[r] = neg2;
+            F1l[r] = neg2;
+            Hl[r] = ((uint32_t)(C.gap_open + (r0 + r) * C.gap_ext) & 0xffffu) * 0x10001u;
+        }
+        // H(r0, 0): the origin for the first stripe, else column 0 of the row above
+        uint32_t hu_prev = s == 0 ? 0u : ((uint32_t)(C.gap_open + (r0 - 1) * C.gap_ext) & 0xffffu) * 0x10001u;
+        uint32_t h_row0 = open2;  // H(0, j) = open + (j-1)*ext (pairwise.rs:747-780)
+        uint32_t nxt = cc[0];
+        // the row above the stripe is prefetched one column ahead: its L2/HBM latency hides
+        // behind the 16 rows of the current column
+        uint32_t nx_m = neg2, nx_f = neg2, nx_h = 0;
+        if (s > 0) { nx_m = rb_m[0]; nx_f = rb_f[0]; nx_h = rb_h[0]; }
+        for (int j = 0; j < d.mmax; j++) {
+            const uint32_t v = nxt;
+            uint32_t up_m = nx_m, up_f2 = nx_f, hu = nx_h;
+            if (j + 1 < d.mmax) {
+                nxt = cc[(int64_t)(j + 1) * 32];
+                if (s > 0) {
+                    nx_m = rb_m[(int64_t)(j + 1) * 32]; nx_f = rb_f[(int64_t)(j + 1) * 32];
+                    nx_h = rb_h[(int64_t)(j + 1) * 32];
+                }
+            }
+            const char *t_lo = tbase + (v & 0xffu) * col_stride;
+            const char *t_hi = tbase + (v >> 8) * col_stride;
+            if (s == 0) { hu = h_row0; h_row0 = __vadd2(h_row0, ext2); }
+            uint32_t diag = hu_prev;
+            hu_prev = hu;
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // nibbles: lo rows 0-7, lo rows 8-15, hi rows 0-7, hi rows 8-15
+#pragma unroll
+            for (int r = 0; r < IS_R; r++) {
+                const uint32_t s_lo = *(const uint32_t *)(t_lo + rp_lo[r]);
+                const uint32_t s_hi = *(const uint32_t *)(t_hi + rp_hi[r]);
+                const uint32_t sim = s_hi * 65536u + s_lo;
+                const uint32_t m = __vadd2(diag, sim);
+                const uint32_t fe = __vadd2(F1l[r], ext2);
+                const uint32_t fv = __vadd2(up_f2, ext2);
+                uint32_t f1, f2, t, h;
+                if (TRACED) {
+                    uint32_t &lo_acc = r < 8 ? a0 : a1;
+                    uint32_t &hi_acc = r < 8 ? a2 : a3;
+                    constexpr uint32_t one = 1u;
+                    const int sh = 4 * (r & 7);
+                    BT_MAX_PRED(f1, Ml[r], fe, lo_acc, hi_acc, (one << 2) << sh);   // o1
+                    BT_MAX_PRED(f2, up_m, fv, lo_acc, hi_acc, (one << 3) << sh);    // o2
+                    BT_MAX_PRED(t, f1, f2, lo_acc, hi_acc, (one << 1) << sh);       // hG
+                    const uint32_t to = __vadd2(t, open2);
+                    BT_MAX_PRED(h, m, to, lo_acc, hi_acc, one << sh);               // hM
+                } else {
+                    f1 = __vmaxs2(Ml[r], fe);
+                    f2 = __vmaxs2(up_m, fv);
+                    t = __vmaxs2(f1, f2);
+                    h = __viaddmax_s16x2(t, open2, m);
+                }
+                diag = Hl[r];
+                Hl[r] = h; Ml[r] = m; F1l[r] = f1;
+                up_m = m; up_f2 = f2;
+            }
+            if (s + 1 < d.stripes) {
+                rb_m[(int64_t)j * 32] = up_m; rb_f[(int64_t)j * 32] = up_f2; rb_h[(int64_t)j * 32] = Hl[IS_R - 1];
+            }
+            if (TRACED) dir[((int64_t)s * d.mmax + j) * 32] = make_uint4(a0, a1, a2, a3);
+            // optimum: H(n, m) (pairwise.rs:866-879)
+            if ((j + 1 == m_lo && (n_lo - 1) / IS_R == s) || (j + 1 == m_hi && (n_hi - 1) / IS_R == s)) {
+#pragma unroll
+                for (int r = 0; r < IS_R; r++) {
+                    if (j + 1 == m_lo && r0 + r + 1 == n_lo) best_lo = (int16_t)(Hl[r] & 0xffffu);
+                    if (j + 1 == m_hi && r0 + r + 1 == n_hi) best_hi = (int16_t)(Hl[r] >> 16);
+                }
+            }
+        }
+    }
+    if (p_lo >= 0) score[p_lo] = best_lo;
+    if (p_hi >= 0) score[p_hi] = best_hi;
+}
+
+// ---------------------------------------------------------------------------------------
+// traceback over the nibbles: one thread per pair, first-priority steps only
+// (trace.rs:59-90 with max_number = 1; step order cell.rs:219-254)
+// ---------------------------------------------------------------------------------------
+__global__ void interseq_traceback_kernel(const WarpDesc *__restrict__ desc,
+                                          const int32_t *__restrict__ order,
+                                          const int64_t *__restrict__ off1,
+                                          const int64_t *__restrict__ off2,
+                                          const uint32_t *__restrict__ dirs, int64_t *__restrict__ trace_len,
+                                          int32_t *__restrict__ first, uint8_t *__restrict__ ops,
+                                          int64_t n_slots) {
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const int32_t p = order[slot];
+    if (p < 0) return;
+    const int64_t g = slot >> 6;
+    const int lane = (int)(slot & 63) >> 1, half = (int)(slot & 1);
+    const WarpDesc d = desc[g];
+    const int n = (int)(off1[p + 1] - off1[p]), m = (int)(off2[p + 1] - off2[p]);
+    const uint32_t *base = dirs + d.dir_off + lane * 4 + half * 2;
+    uint8_t *out = ops + off1[p] + off2[p];
+    auto nibble = [&](int i, int j) -> uint32_t {  // 1-based table cell (i, j)
+        const int rg = i - 1, s = rg / IS_R, r = rg % IS_R;
+        const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 128 + (r >> 3)];
+        return (w >> (4 * (r & 7))) & 0xfu;
+    };
+    auto h_state = [&](int i, int j) -> int {  // state with the best score at cell (i, j), priority M, G1, G2
+        if (i == 0) return j == 0 ? ST_MATCH : ST_GAP1;
+        if (j == 0) return ST_GAP2;
+        const uint32_t nb = nibble(i, j);
+        return (nb & 1u) ? ST_MATCH : ((nb & 2u) ? ST_GAP1 : ST_GAP2);
+    };
+    int i = n, j = m, len = 0;
+    int st = h_state(i, j);
+    int fi = 0, fj = 0;
+    while (i > 0 || j > 0) {
+        fi = i; fj = j;
+        if (i == 0) { out[len++] = OP_TO1; j--; continue; }   // first row: leading gap in sequence 1
+        if (j == 0) { out[len++] = OP_TO2; i--; continue; }   // first column
+        if (st == ST_MATCH) {
+            out[len++] = OP_DIAG;
+            i--; j--;
+            st = h_state(i, j);
+        } else if (st == ST_GAP1) {
+            const uint32_t nb = nibble(i, j);
+            out[len++] = OP_TO1;
+            j--;
+            st = (nb & 4u) ? ST_MATCH : ST_GAP1;
+        } else {
+            const uint32_t nb = nibble(i, j);
+            out[len++] = OP_TO2;
+            i--;
+            st = (nb & 8u) ? ST_MATCH : ST_GAP2;
+        }
+    }
+    trace_len[p] = len;
+    first[2 * p] = fi;
+    first[2 * p + 1] = fj;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const std::vector<int64_t> &off1,
+                            const std::vector<int64_t> &off2, int64_t n_pairs, int score_only,
+                            int32_t min_score, int32_t max_score, int64_t *cells_out, cudaStream_t stream) {
+    (void)max_score;
+    plan.n_pairs = n_pairs;
+    plan.n_groups = (n_pairs + 63) / 64;
+    plan.C.gap_open = P.gap_open; plan.C.gap_ext = P.gap_ext;
+    plan.C.neg = -32768 - P.gap_open - P.gap_ext - std::min(min_score, 0);
+    plan.C.n_rows = P.n_rows; plan.C.n_cols = P.n_cols; plan.C.score_only = score_only;
+
+    // counting sort by (len1, len2): two stable passes over 16-bit keys
+    std::vector<int32_t> tmp((size_t)n_pairs), sorted((size_t)n_pairs);
+    int64_t cells = 0;
+    {
+        std::vector<int32_t> count(IS_MAX_LEN + 2, 0);
+        for (int64_t k = 0; k < n_pairs; k++) count[(size_t)(off2[k + 1] - off2[k]) + 1]++;
+        for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
+        for (int64_t k = 0; k < n_pairs; k++) tmp[(size_t)count[(size_t)(off2[k + 1] - off2[k])]++] = (int32_t)k;
+        std::fill(count.begin(), count.end(), 0);
+        for (int64_t k = 0; k < n_pairs; k++) count[(size_t)(off1[k + 1] - off1[k]) + 1]++;
+        for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
+        for (int64_t q = 0; q < n_pairs; q++) {
+            const int32_t k = tmp[(size_t)q];
+            sorted[(size_t)count[(size_t)(off1[k + 1] - off1[k])]++] = k;
+        }
+    }
+    plan.order.assign((size_t)plan.n_groups * 64, -1);
+    std::copy(sorted.begin(), sorted.end(), plan.order.begin());
+    plan.desc.resize((size_t)plan.n_groups);
+    int64_t dir_words = 0, rowbuf = 0, rowcodes = 0, colcodes = 0;
+    for (int64_t g = 0; g < plan.n_groups; g++) {
+        int nmax = 1, mmax = 1;
+        for (int q = 0; q < 64; q++) {
+            const int32_t k = plan.order[(size_t)(g * 64 + q)];
+            if (k < 0) continue;
+            const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
+            nmax = std::max<int>(nmax, (int)n); mmax = std::max<int>(mmax, (int)m);
+            cells += n * m;
+        }
+        WarpDesc &d = plan.desc[(size_t)g];
+        d.nmax = nmax; d.mmax = mmax; d.stripes = (nmax + IS_R - 1) / IS_R; d.pad = 0;
+        d.dir_off = dir_words; d.rowbuf_off = rowbuf; d.rowcode_off = rowcodes; d.colcode_off = colcodes;
+        if (!score_only) dir_words += (int64_t)d.stripes * mmax * 128;   // uint4 per lane, column and stripe
+        rowbuf += (int64_t)mmax * 32;
+        rowcodes += (int64_t)d.stripes * IS_R * 32;
+        colcodes += (int64_t)mmax * 32;
+    }
+    plan.dir_words = dir_words; plan.rowbuf_entries = rowbuf; plan.rowcodes = rowcodes; plan.colcodes = colcodes;
+    if (cells_out) *cells_out = cells;
+
+    auto alloc = [](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 1); };
+    cudaError_t e;
+    if ((e = alloc(&plan.d_order, plan.order.size() * 4)) != cudaSuccess) goto oom;
+    if ((e = alloc(&plan.d_desc, plan.desc.size() * sizeof(WarpDesc))) != cudaSuccess) goto oom;
+    if ((e = alloc(&plan.d_rowcodes, (size_t)rowcodes * 2)) != cudaSuccess) goto oom;
+    if ((e = alloc(&plan.d_colcodes, (size_t)colcodes * 2)) != cudaSuccess) goto oom;
+    if ((e = alloc(&plan.d_rowbuf, (size_t)rowbuf * 12)) != cudaSuccess) goto oom;
+    if ((e = alloc(&plan.d_dirs, (size_t)dir_words * 4)) != cudaSuccess) goto oom;
+    if ((e = cudaMemcpyAsync(plan.d_order, plan.order.data(), plan.order.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) goto oom;
+    if ((e = cudaMemcpyAsync(plan.d_desc, plan.desc.data(), plan.desc.size() * sizeof(WarpDesc), cudaMemcpyHostToDevice, stream)) != cudaSuccess) goto oom;
+    return BT_OK;
+oom:
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? BT_ERR_OOM : BT_ERR_CUDA;
+}
+
+inline cudaError_t interseq_run_fill(InterseqPlan &plan, const InterseqIO &io, cudaStream_t stream,
+                                     int64_t *launches) {
+    interseq_pack_kernel<<<(unsigned)plan.n_groups, 256, 0, stream>>>(
+        (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.off1, io.off2, (const int32_t *)plan.d_order,
+        (const WarpDesc *)plan.d_desc, (uint16_t *)plan.d_rowcodes, (uint16_t *)plan.d_colcodes, plan.n_groups);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    (*launches)++;
+    const size_t smem = (size_t)plan.C.n_rows * plan.C.n_cols * IS_ROWW;
+    const unsigned grid = (unsigned)((plan.n_groups + IS_THREADS / 32 - 1) / (IS_THREADS / 32));
+    if (plan.C.score_only) {
+        e = cudaFuncSetAttribute(interseq_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        interseq_fill_kernel<false><<<grid, IS_THREADS, smem, stream>>>(
+            plan.C, (const WarpDesc *)plan.d_desc, (const int32_t *)plan.d_order, io.off1, io.off2, io.matrix,
+            (const uint16_t *)plan.d_rowcodes, (const uint16_t *)plan.d_colcodes, (uint32_t *)plan.d_rowbuf,
+            (uint32_t *)plan.d_dirs, io.score, plan.n_groups);
+    } else {
+        e = cudaFuncSetAttribute(interseq_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        interseq_fill_kernel<true><<<grid, IS_THREADS, smem, stream>>>(
+            plan.C, (const WarpDesc *)plan.d_desc, (const int32_t *)plan.d_order, io.off1, io.off2, io.matrix,
+            (const uint16_t *)plan.d_rowcodes, (const uint16_t *)plan.d_colcodes, (uint32_t *)plan.d_rowbuf,
+            (uint32_t *)plan.d_dirs, io.score, plan.n_groups);
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) (*launches)++;
+    return e;
+}
+
+inline cudaError_t interseq_run_traceback(InterseqPlan &plan, const InterseqIO &io, cudaStream_t stream,
+                                          int64_t *launches) {
+    if (plan.C.score_only) return cudaSuccess;
+    const int64_t slots = plan.n_groups * 64;
+    interseq_traceback_kernel<<<(unsigned)((slots + 127) / 128), 128, 0, stream>>>(
+        (const WarpDesc *)plan.d_desc, (const int32_t *)plan.d_order, io.off1, io.off2,
+        (const uint32_t *)plan.d_dirs, io.trace_len, io.first, io.ops, slots);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) (*launches)++;
+    return e;
+}
+
 }  // namespace bt
