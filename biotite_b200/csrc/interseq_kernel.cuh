@@ -143,11 +143,11 @@ __global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes
         "mov.b32 {x0, x1}, %0;\n\tmov.b32 {y0, y1}, %3;\n\t"                             \
         "setp.eq.s16 pl, x0, y0;\n\tsetp.eq.s16 ph, x1, y1;\n\t"                         \
         "@pl add.u32 %1, %1, %5;\n\t@ph add.u32 %2, %2, %5;\n\t}"                        \
-        : "=r"(out), "+r"(acc_lo), "+r"(acc_hi)                                          \
+        : "=&r"(out), "+r"(acc_lo), "+r"(acc_hi)                                          \
         : "r"(a), "r"(b), "r"(c))
 
 template <bool TRACED>
-__global__ void __launch_bounds__(IS_THREADS)
+__global__ void __launch_bounds__(IS_THREADS, 3)
 interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
                      const int32_t *__restrict__ order, const int64_t *__restrict__ off1,
                      const int64_t *__restrict__ off2, const int32_t *__restrict__ matrix,
@@ -188,6 +188,9 @@ interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
     int32_t best_lo = 0, best_hi = 0;
     for (int s = 0; s < d.stripes; s++) {
         const int r0 = s * IS_R;  // rows r0+1 .. r0+R of the DP table
+        // column step at which this stripe holds the end cell (n, m) of the low / high pair
+        const int j_lo = (n_lo - 1) / IS_R == s ? m_lo - 1 : -1;
+        const int j_hi = (n_hi - 1) / IS_R == s ? m_hi - 1 : -1;
         uint32_t rp_lo[IS_R], rp_hi[IS_R], Ml[IS_R], F1l[IS_R], Hl[IS_R];
 #pragma unroll
         for (int r = 0; r < IS_R; r++) {
@@ -220,48 +223,55 @@ interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
             const char *t_lo = tbase + (v & 0xffu) * col_stride;
             const char *t_hi = tbase + (v >> 8) * col_stride;
             if (s == 0) { hu = h_row0; h_row0 = __vadd2(h_row0, ext2); }
-            uint32_t diag = hu_prev;
-            hu_prev = hu;
-            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // nibbles: lo rows 0-7, lo rows 8-15, hi rows 0-7, hi rows 8-15
+            // Rows are software-pipelined so that every state array is updated in place:
+            // F1 and M of row r+1 are formed (from the previous column's M and H) before
+            // H of row r overwrites Hl[r].
+            uint32_t acc[4] = {0, 0, 0, 0};  // nibbles: lo rows 0-7, lo rows 8-15, hi rows 0-7, hi rows 8-15
+            uint32_t sim[IS_R];
 #pragma unroll
             for (int r = 0; r < IS_R; r++) {
                 const uint32_t s_lo = *(const uint32_t *)(t_lo + rp_lo[r]);
                 const uint32_t s_hi = *(const uint32_t *)(t_hi + rp_hi[r]);
-                const uint32_t sim = s_hi * 65536u + s_lo;
-                const uint32_t m = __vadd2(diag, sim);
-                const uint32_t fe = __vadd2(F1l[r], ext2);
+                sim[r] = s_hi * 65536u + s_lo;
+            }
+#define BT_ACC_LO(r) acc[(r) >> 3]
+#define BT_ACC_HI(r) acc[2 + ((r) >> 3)]
+#define BT_BIT(r, b) ((1u << (b)) << (4 * ((r) & 7)))
+#define BT_ROW_F1_M(r, diag_h)                                                               \
+    {                                                                                        \
+        const uint32_t fe = __vadd2(F1l[r], ext2);                                           \
+        if (TRACED) { BT_MAX_PRED(F1l[r], Ml[r], fe, BT_ACC_LO(r), BT_ACC_HI(r), BT_BIT(r, 2)); } \
+        else F1l[r] = __vmaxs2(Ml[r], fe);                                                   \
+        Ml[r] = __vadd2(diag_h, sim[r]);                                                     \
+    }
+            BT_ROW_F1_M(0, hu_prev);
+            hu_prev = hu;
+#pragma unroll
+            for (int r = 0; r < IS_R; r++) {
+                if (r + 1 < IS_R) BT_ROW_F1_M(r + 1, Hl[r]);
                 const uint32_t fv = __vadd2(up_f2, ext2);
-                uint32_t f1, f2, t, h;
                 if (TRACED) {
-                    uint32_t &lo_acc = r < 8 ? a0 : a1;
-                    uint32_t &hi_acc = r < 8 ? a2 : a3;
-                    constexpr uint32_t one = 1u;
-                    const int sh = 4 * (r & 7);
-                    BT_MAX_PRED(f1, Ml[r], fe, lo_acc, hi_acc, (one << 2) << sh);   // o1
-                    BT_MAX_PRED(f2, up_m, fv, lo_acc, hi_acc, (one << 3) << sh);    // o2
-                    BT_MAX_PRED(t, f1, f2, lo_acc, hi_acc, (one << 1) << sh);       // hG
+                    uint32_t t;
+                    BT_MAX_PRED(up_f2, up_m, fv, BT_ACC_LO(r), BT_ACC_HI(r), BT_BIT(r, 3));     // o2
+                    BT_MAX_PRED(t, F1l[r], up_f2, BT_ACC_LO(r), BT_ACC_HI(r), BT_BIT(r, 1));   // hG
                     const uint32_t to = __vadd2(t, open2);
-                    BT_MAX_PRED(h, m, to, lo_acc, hi_acc, one << sh);               // hM
+                    BT_MAX_PRED(Hl[r], Ml[r], to, BT_ACC_LO(r), BT_ACC_HI(r), BT_BIT(r, 0));   // hM
                 } else {
-                    f1 = __vmaxs2(Ml[r], fe);
-                    f2 = __vmaxs2(up_m, fv);
-                    t = __vmaxs2(f1, f2);
-                    h = __viaddmax_s16x2(t, open2, m);
+                    up_f2 = __vmaxs2(up_m, fv);
+                    Hl[r] = __viaddmax_s16x2(__vmaxs2(F1l[r], up_f2), open2, Ml[r]);
                 }
-                diag = Hl[r];
-                Hl[r] = h; Ml[r] = m; F1l[r] = f1;
-                up_m = m; up_f2 = f2;
+                up_m = Ml[r];
             }
             if (s + 1 < d.stripes) {
                 rb_m[(int64_t)j * 32] = up_m; rb_f[(int64_t)j * 32] = up_f2; rb_h[(int64_t)j * 32] = Hl[IS_R - 1];
             }
-            if (TRACED) dir[((int64_t)s * d.mmax + j) * 32] = make_uint4(a0, a1, a2, a3);
+            if (TRACED) dir[((int64_t)s * d.mmax + j) * 32] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
             // optimum: H(n, m) (pairwise.rs:866-879)
-            if ((j + 1 == m_lo && (n_lo - 1) / IS_R == s) || (j + 1 == m_hi && (n_hi - 1) / IS_R == s)) {
+            if (j == j_lo || j == j_hi) {
 #pragma unroll
                 for (int r = 0; r < IS_R; r++) {
-                    if (j + 1 == m_lo && r0 + r + 1 == n_lo) best_lo = (int16_t)(Hl[r] & 0xffffu);
-                    if (j + 1 == m_hi && r0 + r + 1 == n_hi) best_hi = (int16_t)(Hl[r] >> 16);
+                    if (j == j_lo && r0 + r + 1 == n_lo) best_lo = (int16_t)(Hl[r] & 0xffffu);
+                    if (j == j_hi && r0 + r + 1 == n_hi) best_hi = (int16_t)(Hl[r] >> 16);
                 }
             }
         }
