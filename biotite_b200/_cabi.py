@@ -11,12 +11,13 @@ fallback, a missing library or a missing GPU raises.
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libb200align.so"
+LIB_PATH = Path(os.environ.get("B200ALIGN_LIB", _PKG / "libb200align.so"))
 
 BT_OK = 0
 BT_ERR_INVALID_ARG = -1

@@ -38,6 +38,7 @@ constexpr int IS_R = 16;            // rows per stripe
 constexpr int IS_THREADS = 128;     // 4 warps per block
 constexpr int IS_MAX_LEN = 2000;    // longest sequence routed here
 constexpr int IS_ROWW = 128;        // bytes per table entry row: 32 lanes x 4 bytes
+constexpr int IS_PREFETCH = 6;      // columns of L2 prefetch distance for the row buffer
 
 // One group of 64 pairs handled by one warp.
 struct WarpDesc {
@@ -213,12 +214,20 @@ interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
         for (int j = 0; j < d.mmax; j++) {
             const uint32_t v = nxt;
             uint32_t up_m = nx_m, up_f2 = nx_f, hu = nx_h;
+            if (s > 0 && j + IS_PREFETCH < d.mmax) {
+                // pull the row buffer towards L2 well ahead of the register prefetch below
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb_m + (int64_t)(j + IS_PREFETCH) * 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb_f + (int64_t)(j + IS_PREFETCH) * 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb_h + (int64_t)(j + IS_PREFETCH) * 32));
+            }
             if (j + 1 < d.mmax) {
                 nxt = cc[(int64_t)(j + 1) * 32];
+#if !defined(BT_EXP) || BT_EXP != 1
                 if (s > 0) {
                     nx_m = rb_m[(int64_t)(j + 1) * 32]; nx_f = rb_f[(int64_t)(j + 1) * 32];
                     nx_h = rb_h[(int64_t)(j + 1) * 32];
                 }
+#endif
             }
             const char *t_lo = tbase + (v & 0xffu) * col_stride;
             const char *t_hi = tbase + (v >> 8) * col_stride;
