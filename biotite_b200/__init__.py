@@ -34,6 +34,7 @@ from .batch import (
     BatchResult,
     DeviceBatch,
     PackedSequences,
+    align_batch_arrays,
     align_banded_batch,
     align_optimal_batch,
     pack_sequences,

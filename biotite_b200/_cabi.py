@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "bt_tracelist_free", "bt_batch_create", "bt_batch_run", "bt_batch_fetch_scores",
     "bt_batch_fetch_traces", "bt_batch_timings", "bt_microbench", "bt_batch_cells", "bt_batch_launches", "bt_batch_kernel",
     "bt_batch_destroy", "bt_align_batch", "bt_expand_traces", "bt_pinned_alloc",
-    "bt_pinned_free",
+    "bt_pinned_free", "bt_pool_trim",
 ]
 
 
@@ -109,6 +109,7 @@ def load():
     lib.bt_pinned_alloc.argtypes = [ctypes.c_size_t]
     lib.bt_pinned_free.restype = None
     lib.bt_pinned_free.argtypes = [_vp]
+    lib.bt_pool_trim.restype = None
     _lib = lib
     return lib
 

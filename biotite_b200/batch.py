@@ -27,6 +27,7 @@ __all__ = [
     "pack_sequences",
     "DeviceBatch",
     "BatchResult",
+    "align_batch_arrays",
     "align_optimal_batch",
     "align_banded_batch",
 ]
@@ -163,6 +164,42 @@ class DeviceBatch:
             pass
 
 
+def align_batch_arrays(codes1, off1, codes2, off2, scoring, gap_penalty, terminal_penalty=True,
+                       local=False, bands=None, score_only=False, out=None):
+    """
+    One call from host arrays to host results (``bt_align_batch``): H2D copies, kernels
+    and D2H copies are pipelined inside the library.  `out` may supply preallocated
+    (ideally page-locked, see ``_cabi.pinned_empty``) result arrays
+    ``(scores, trace_len, first, ops)``.  Returns a :class:`BatchResult`.
+    """
+    lib = _cabi.load()
+    dtype = np.promote_types(codes1.dtype, codes2.dtype)
+    codes1 = np.ascontiguousarray(codes1, dtype)
+    codes2 = np.ascontiguousarray(codes2, dtype)
+    off1 = np.ascontiguousarray(off1, dtype=np.int64)
+    off2 = np.ascontiguousarray(off2, dtype=np.int64)
+    if len(off1) != len(off2):
+        raise ValueError("Both sides of the batch must hold the same number of sequences")
+    n = len(off1) - 1
+    bands = None if bands is None else np.ascontiguousarray(bands, dtype=np.int64)
+    params, matrix = _cabi.make_params(scoring, gap_penalty, terminal_penalty, local,
+                                       bands is not None, dtype)
+    if out is None:
+        scores = np.empty(n, dtype=np.int32)
+        trace_len = first = ops = None
+        if not score_only:
+            trace_len = np.empty(n, dtype=np.int64)
+            first = np.empty((n, 2), dtype=np.int32)
+            ops = np.empty(int(off1[-1] + off2[-1]), dtype=np.uint8)
+    else:
+        scores, trace_len, first, ops = out
+    _cabi.check(lib.bt_align_batch(
+        ctypes.byref(params), _cabi.ptr(codes1), _cabi.ptr(off1), _cabi.ptr(codes2),
+        _cabi.ptr(off2), n, _cabi.ptr(matrix), _cabi.ptr(bands), int(bool(score_only)),
+        _cabi.ptr(scores), _cabi.ptr(trace_len), _cabi.ptr(first), _cabi.ptr(ops)))
+    return BatchResult(scores, trace_len, first, ops, off1 + off2, bands)
+
+
 class BatchResult:
     """
     Scores and first-optimal traces of a batch.
@@ -272,10 +309,8 @@ def align_optimal_batch(seqs1, seqs2, matrix, gap_penalty=-10, terminal_penalty=
     if len(p1) != len(p2):
         raise ValueError("Both lists must hold the same number of sequences")
     scoring = _resolve_scoring(matrix, p1, p2)
-    with DeviceBatch(p1.codes, p1.offsets, p2.codes, p2.offsets, scoring, gap_penalty,
-                     terminal_penalty, local, None, score_only) as batch:
-        batch.run()
-        result = batch.fetch()
+    result = align_batch_arrays(p1.codes, p1.offsets, p2.codes, p2.offsets, scoring, gap_penalty,
+                                terminal_penalty, local, None, score_only)
     result.seqs1, result.seqs2 = p1.sequences, p2.sequences
     return result
 
@@ -334,10 +369,8 @@ def align_banded_batch(seqs1, seqs2, matrix, bands, gap_penalty=-10, local=False
         band = (-int(bands[k, 0]), -int(bands[k, 1])) if swapped[k] else (
             int(bands[k, 0]), int(bands[k, 1]))
         eff[k] = crop_band(int(l1[k]), int(l2[k]), band)
-    with DeviceBatch(q1.codes, q1.offsets, q2.codes, q2.offsets, scoring, gap_penalty,
-                     True, local, eff, score_only) as batch:
-        batch.run()
-        result = batch.fetch()
+    result = align_batch_arrays(q1.codes, q1.offsets, q2.codes, q2.offsets, scoring, gap_penalty,
+                                True, local, eff, score_only)
     result.swapped = swapped if swapped.any() else None
     result.seqs1, result.seqs2 = p1.sequences, p2.sequences
     return result

@@ -16,6 +16,7 @@
 
 #include "../../include/b200align.h"
 #include "common.cuh"
+#include "pool.cuh"
 #include "general_kernel.cuh"
 #include "host_trace.hpp"
 #include "interseq_kernel.cuh"
@@ -83,28 +84,6 @@ extern "C" void bt_pinned_free(void *ptr) {
 // ---------------------------------------------------------------------------------------
 // device buffers
 // ---------------------------------------------------------------------------------------
-struct DevBuf {
-    void *ptr = nullptr;
-    size_t bytes = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-    ~DevBuf() { release(); }
-    void release() {
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        bytes = 0;
-    }
-    cudaError_t alloc(size_t n) {
-        release();
-        if (n == 0) n = 1;
-        cudaError_t e = cudaMalloc(&ptr, n);
-        if (e == cudaSuccess) bytes = n;
-        return e;
-    }
-    template <class T> T *as() const { return (T *)ptr; }
-};
-
 static int check_params(const BtParams *P) {
     if (!P) return fail(BT_ERR_INVALID_ARG, "params is NULL");
     if (P->gap_open > 0 || (P->affine && P->gap_ext > 0))
@@ -432,7 +411,7 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
 
     if (b->route == ROUTE_INTERSEQ) {
         st = interseq_prepare(b->interseq, *params, b->h_off1, b->h_off2, n_pairs, b->score_only, mn, mx,
-                              &b->cells, s);
+                              &b->cells, 1, s);
         if (st == BT_ERR_OOM) return fail(st, "out of device memory (inter-sequence plan)");
         if (st) return fail(st, "inter-sequence plan failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
@@ -492,11 +471,14 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
             InterseqIO io{b->codes1.ptr, b->codes2.ptr, b->off1.as<int64_t>(), b->off2.as<int64_t>(),
                           b->matrix.as<int32_t>(), b->score.as<int32_t>(), b->trace_len.as<int64_t>(),
                           b->first.as<int32_t>(), b->ops.as<uint8_t>()};
-            cudaError_t e = b->mark_phase();
-            if (e == cudaSuccess) e = interseq_run_fill(b->interseq, io, b->stream, &b->launches);
-            if (e == cudaSuccess) e = b->mark_phase();
-            if (e == cudaSuccess) e = interseq_run_traceback(b->interseq, io, b->stream, &b->launches);
-            if (e == cudaSuccess) e = b->mark_phase();
+            cudaError_t e = cudaSuccess;
+            for (const Window &win : b->interseq.windows) {
+                if (e == cudaSuccess) e = b->mark_phase();
+                if (e == cudaSuccess) e = interseq_fill_window(b->interseq, win, 0, io, b->stream, &b->launches);
+                if (e == cudaSuccess) e = b->mark_phase();
+                if (e == cudaSuccess) e = interseq_traceback_window(b->interseq, win, 0, io, b->stream, &b->launches);
+                if (e == cudaSuccess) e = b->mark_phase();
+            }
             if (e != cudaSuccess) st = fail(BT_ERR_CUDA, "inter-sequence kernels: %s", cudaGetErrorString(e));
         } else {
             st = run_general(b, true);
@@ -558,13 +540,111 @@ extern "C" const char *bt_batch_kernel(const BtBatch *b) {
 }
 extern "C" void bt_batch_destroy(BtBatch *b) { delete b; }
 
+// One-shot path for the packed inter-sequence route: windows of consecutive pairs are
+// streamed through two slots (stream + scratch each), so the H2D copy of window k+1 and the
+// D2H copy of window k-1 overlap the kernels of window k.
+static int align_batch_pipelined(const BtParams *params, const void *codes1, const int64_t *off1,
+                                 const void *codes2, const int64_t *off2, int64_t n_pairs,
+                                 const int32_t *matrix, int32_t score_only, int32_t mn, int32_t mx,
+                                 const std::vector<int64_t> &h_off1, const std::vector<int64_t> &h_off2,
+                                 int32_t *scores_out, int64_t *trace_len_out, int32_t *first_out,
+                                 uint8_t *ops_out) {
+    const int64_t total1 = h_off1[n_pairs], total2 = h_off2[n_pairs];
+    DevBuf d_codes1, d_codes2, d_off1, d_off2, d_matrix, d_score, d_len, d_first, d_ops, d_flag;
+    CUDA_TRY(d_codes1.alloc((size_t)total1));
+    CUDA_TRY(d_codes2.alloc((size_t)total2));
+    CUDA_TRY(d_off1.alloc((size_t)(n_pairs + 1) * 8));
+    CUDA_TRY(d_off2.alloc((size_t)(n_pairs + 1) * 8));
+    const size_t mb = (size_t)params->n_rows * params->n_cols * 4;
+    CUDA_TRY(d_matrix.alloc(mb));
+    CUDA_TRY(d_score.alloc((size_t)n_pairs * 4));
+    CUDA_TRY(d_flag.alloc(4));
+    if (!score_only) {
+        CUDA_TRY(d_len.alloc((size_t)n_pairs * 8));
+        CUDA_TRY(d_first.alloc((size_t)n_pairs * 8));
+        CUDA_TRY(d_ops.alloc((size_t)(total1 + total2)));
+    }
+    struct Streams {
+        cudaStream_t s[2] = {nullptr, nullptr};
+        cudaEvent_t ready = nullptr;
+        ~Streams() {
+            for (cudaStream_t x : s) if (x) cudaStreamDestroy(x);
+            if (ready) cudaEventDestroy(ready);
+        }
+    } st;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st.s[0], cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&st.s[1], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&st.ready, cudaEventDisableTiming));
+
+    InterseqPlan plan;
+    int64_t cells = 0;
+    int rc = interseq_prepare(plan, *params, h_off1, h_off2, n_pairs, score_only, mn, mx, &cells, 2, st.s[0]);
+    if (rc == BT_ERR_OOM) return fail(rc, "out of device memory (inter-sequence plan)");
+    if (rc) return fail(rc, "inter-sequence plan failed");
+    CUDA_TRY(cudaMemsetAsync(d_flag.ptr, 0, 4, st.s[0]));
+    CUDA_TRY(cudaMemcpyAsync(d_off1.ptr, off1, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.s[0]));
+    CUDA_TRY(cudaMemcpyAsync(d_off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.s[0]));
+    CUDA_TRY(cudaMemcpyAsync(d_matrix.ptr, matrix, mb, cudaMemcpyHostToDevice, st.s[0]));
+    CUDA_TRY(cudaEventRecord(st.ready, st.s[0]));
+    CUDA_TRY(cudaStreamWaitEvent(st.s[1], st.ready, 0));
+
+    InterseqIO io{d_codes1.ptr, d_codes2.ptr, d_off1.as<int64_t>(), d_off2.as<int64_t>(), d_matrix.as<int32_t>(),
+                  d_score.as<int32_t>(), d_len.as<int64_t>(), d_first.as<int32_t>(), d_ops.as<uint8_t>()};
+    int64_t launches = 0;
+    for (size_t w = 0; w < plan.windows.size(); w++) {
+        const Window &win = plan.windows[w];
+        const int slot = (int)(w & 1);
+        cudaStream_t s = st.s[slot];
+        const int64_t a1 = h_off1[win.pair_begin], b1 = h_off1[win.pair_end];
+        const int64_t a2 = h_off2[win.pair_begin], b2 = h_off2[win.pair_end];
+        const int64_t np = win.pair_end - win.pair_begin;
+        CUDA_TRY(cudaMemcpyAsync((char *)d_codes1.ptr + a1, (const char *)codes1 + a1, (size_t)(b1 - a1), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync((char *)d_codes2.ptr + a2, (const char *)codes2 + a2, (size_t)(b2 - a2), cudaMemcpyHostToDevice, s));
+        validate_codes_kernel<<<(int)std::min<int64_t>(592, (b1 - a1 + 255) / 256), 256, 0, s>>>(
+            (const char *)d_codes1.ptr + a1, b1 - a1, 1, (uint64_t)params->n_rows, d_flag.as<int>());
+        validate_codes_kernel<<<(int)std::min<int64_t>(592, (b2 - a2 + 255) / 256), 256, 0, s>>>(
+            (const char *)d_codes2.ptr + a2, b2 - a2, 1, (uint64_t)params->n_cols, d_flag.as<int>());
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(interseq_fill_window(plan, win, slot, io, s, &launches));
+        CUDA_TRY(interseq_traceback_window(plan, win, slot, io, s, &launches));
+        if (scores_out)
+            CUDA_TRY(cudaMemcpyAsync(scores_out + win.pair_begin, d_score.as<int32_t>() + win.pair_begin, (size_t)np * 4, cudaMemcpyDeviceToHost, s));
+        if (!score_only) {
+            if (trace_len_out)
+                CUDA_TRY(cudaMemcpyAsync(trace_len_out + win.pair_begin, d_len.as<int64_t>() + win.pair_begin, (size_t)np * 8, cudaMemcpyDeviceToHost, s));
+            if (first_out)
+                CUDA_TRY(cudaMemcpyAsync(first_out + 2 * win.pair_begin, d_first.as<int32_t>() + 2 * win.pair_begin, (size_t)np * 8, cudaMemcpyDeviceToHost, s));
+            if (ops_out)
+                CUDA_TRY(cudaMemcpyAsync(ops_out + a1 + a2, d_ops.as<uint8_t>() + a1 + a2, (size_t)(b1 - a1 + b2 - a2), cudaMemcpyDeviceToHost, s));
+        }
+    }
+    int flag = 0;
+    CUDA_TRY(cudaStreamSynchronize(st.s[0]));
+    CUDA_TRY(cudaStreamSynchronize(st.s[1]));
+    CUDA_TRY(cudaMemcpy(&flag, d_flag.ptr, 4, cudaMemcpyDeviceToHost));
+    if (flag) return fail(BT_ERR_INVALID_CODE, "a sequence code is outside the substitution matrix");
+    return BT_OK;
+}
+
 extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const int64_t *off1,
                               const void *codes2, const int64_t *off2, int64_t n_pairs,
                               const int32_t *matrix, const int64_t *bands, int32_t score_only,
                               int32_t *scores_out, int64_t *trace_len_out, int32_t *first_out,
                               uint8_t *ops_out) {
+    int st = check_params(params);
+    if (st) return st;
+    if (n_pairs >= 64 && off1 && off2 && params->use_matrix && matrix && !params->banded &&
+        bt_device_count() > 0) {
+        std::vector<int64_t> h1(off1, off1 + n_pairs + 1), h2(off2, off2 + n_pairs + 1);
+        const int64_t cnt = (int64_t)params->n_rows * params->n_cols;
+        int32_t mn = matrix[0], mx = matrix[0];
+        for (int64_t k = 1; k < cnt; k++) { mn = std::min(mn, matrix[k]); mx = std::max(mx, matrix[k]); }
+        if (h1[0] == 0 && h2[0] == 0 && interseq_eligible(*params, h1, h2, n_pairs, mn, mx))
+            return align_batch_pipelined(params, codes1, off1, codes2, off2, n_pairs, matrix, score_only, mn, mx,
+                                         h1, h2, scores_out, trace_len_out, first_out, ops_out);
+    }
     BtBatch *raw = nullptr;
-    int st = bt_batch_create(params, codes1, off1, codes2, off2, n_pairs, matrix, bands, score_only, &raw);
+    st = bt_batch_create(params, codes1, off1, codes2, off2, n_pairs, matrix, bands, score_only, &raw);
     if (st) return st;
     std::unique_ptr<BtBatch> b(raw);
     st = bt_batch_run(b.get(), nullptr);
@@ -760,3 +840,5 @@ extern "C" int bt_microbench(int kind, double *lane_instr_per_s) {
     *lane_instr_per_s = best;
     return BT_OK;
 }
+
+extern "C" void bt_pool_trim(void) { DevicePool::instance().trim(); }

@@ -31,6 +31,7 @@
 
 #include "../../include/b200align.h"
 #include "common.cuh"
+#include "pool.cuh"
 
 namespace bt {
 
@@ -56,19 +57,30 @@ struct InterseqConst {
     int32_t score_only;
 };
 
+// A window is a run of consecutive pairs (in input order) that is sorted, packed, filled and
+// traced as one unit; its inputs and outputs are contiguous ranges of the batch arrays, so
+// windows can be streamed (H2D, kernels, D2H) independently of each other.
+struct Window {
+    int64_t pair_begin, pair_end;
+    int64_t group_begin, group_end;
+    int64_t dir_words, rowbuf_entries, rowcodes, colcodes;  // scratch the window needs
+};
+
+// Scratch buffers of one in-flight window.
+struct SlotBuffers {
+    DevBuf rowcodes, colcodes, dirs, rowbuf;
+};
+
 // Host-side plan of one batch.
 struct InterseqPlan {
     int64_t n_pairs = 0, n_groups = 0;
-    int64_t dir_words = 0, rowbuf_entries = 0, rowcodes = 0, colcodes = 0;
+    int64_t max_dir_words = 0, max_rowbuf = 0, max_rowcodes = 0, max_colcodes = 0;
     InterseqConst C{};
-    std::vector<int32_t> order;        // sorted position -> pair id (padded with -1)
-    std::vector<WarpDesc> desc;
-    void *d_order = nullptr, *d_desc = nullptr, *d_rowcodes = nullptr, *d_colcodes = nullptr;
-    void *d_dirs = nullptr, *d_rowbuf = nullptr, *d_table = nullptr;
-    ~InterseqPlan() {
-        for (void *p : {d_order, d_desc, d_rowcodes, d_colcodes, d_dirs, d_rowbuf, d_table})
-            if (p) cudaFree(p);
-    }
+    std::vector<int32_t> order;        // group slot -> pair id (-1 = padding), window by window
+    std::vector<WarpDesc> desc;        // offsets are relative to the window's scratch
+    std::vector<Window> windows;
+    DevBuf d_order, d_desc;
+    SlotBuffers slots[2];
 };
 
 struct InterseqIO {
@@ -352,109 +364,146 @@ __global__ void interseq_traceback_kernel(const WarpDesc *__restrict__ desc,
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+
+// Groups per window: a whole number of full waves of the fill kernel (3 blocks of 4 warps
+// per SM), so that windows launched one after the other lose little to partial waves.
+inline int64_t interseq_window_groups() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int64_t)sms * 3 * (IS_THREADS / 32) * 3;
+}
+
 inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const std::vector<int64_t> &off1,
                             const std::vector<int64_t> &off2, int64_t n_pairs, int score_only,
-                            int32_t min_score, int32_t max_score, int64_t *cells_out, cudaStream_t stream) {
+                            int32_t min_score, int32_t max_score, int64_t *cells_out, int n_slots,
+                            cudaStream_t stream) {
     (void)max_score;
     plan.n_pairs = n_pairs;
-    plan.n_groups = (n_pairs + 63) / 64;
     plan.C.gap_open = P.gap_open; plan.C.gap_ext = P.gap_ext;
     plan.C.neg = -32768 - P.gap_open - P.gap_ext - std::min(min_score, 0);
     plan.C.n_rows = P.n_rows; plan.C.n_cols = P.n_cols; plan.C.score_only = score_only;
 
-    // counting sort by (len1, len2): two stable passes over 16-bit keys
-    std::vector<int32_t> tmp((size_t)n_pairs), sorted((size_t)n_pairs);
+    const int64_t win_pairs = interseq_window_groups() * 64;
+    const int64_t n_windows = (n_pairs + win_pairs - 1) / win_pairs;
+    // balance the windows (all about the same number of waves)
+    const int64_t per_window = ((n_pairs + n_windows - 1) / n_windows + 63) / 64 * 64;
+    plan.windows.clear();
+    plan.order.clear();
+    plan.desc.clear();
+    std::vector<int32_t> tmp, sorted, count(IS_MAX_LEN + 2);
     int64_t cells = 0;
-    {
-        std::vector<int32_t> count(IS_MAX_LEN + 2, 0);
-        for (int64_t k = 0; k < n_pairs; k++) count[(size_t)(off2[k + 1] - off2[k]) + 1]++;
-        for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
-        for (int64_t k = 0; k < n_pairs; k++) tmp[(size_t)count[(size_t)(off2[k + 1] - off2[k])]++] = (int32_t)k;
+    for (int64_t w0 = 0; w0 < n_pairs; w0 += per_window) {
+        const int64_t w1 = std::min(n_pairs, w0 + per_window), cnt = w1 - w0;
+        // counting sort of the window by (len1, len2): two stable passes over 16-bit keys
+        tmp.resize((size_t)cnt); sorted.resize((size_t)cnt);
         std::fill(count.begin(), count.end(), 0);
-        for (int64_t k = 0; k < n_pairs; k++) count[(size_t)(off1[k + 1] - off1[k]) + 1]++;
+        for (int64_t k = w0; k < w1; k++) count[(size_t)(off2[k + 1] - off2[k]) + 1]++;
         for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
-        for (int64_t q = 0; q < n_pairs; q++) {
+        for (int64_t k = w0; k < w1; k++) tmp[(size_t)count[(size_t)(off2[k + 1] - off2[k])]++] = (int32_t)k;
+        std::fill(count.begin(), count.end(), 0);
+        for (int64_t k = w0; k < w1; k++) count[(size_t)(off1[k + 1] - off1[k]) + 1]++;
+        for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
+        for (int64_t q = 0; q < cnt; q++) {
             const int32_t k = tmp[(size_t)q];
             sorted[(size_t)count[(size_t)(off1[k + 1] - off1[k])]++] = k;
         }
-    }
-    plan.order.assign((size_t)plan.n_groups * 64, -1);
-    std::copy(sorted.begin(), sorted.end(), plan.order.begin());
-    plan.desc.resize((size_t)plan.n_groups);
-    int64_t dir_words = 0, rowbuf = 0, rowcodes = 0, colcodes = 0;
-    for (int64_t g = 0; g < plan.n_groups; g++) {
-        int nmax = 1, mmax = 1;
-        for (int q = 0; q < 64; q++) {
-            const int32_t k = plan.order[(size_t)(g * 64 + q)];
-            if (k < 0) continue;
-            const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
-            nmax = std::max<int>(nmax, (int)n); mmax = std::max<int>(mmax, (int)m);
-            cells += n * m;
+        Window win{};
+        win.pair_begin = w0; win.pair_end = w1;
+        win.group_begin = (int64_t)plan.desc.size();
+        const int64_t groups = (cnt + 63) / 64;
+        win.group_end = win.group_begin + groups;
+        const size_t base = plan.order.size();
+        plan.order.resize(base + (size_t)groups * 64, -1);
+        // longest pairs first: the block scheduler hands out groups in index order, so the
+        // tail of every window consists of its cheapest groups
+        std::copy(sorted.rbegin(), sorted.rend(), plan.order.begin() + (std::ptrdiff_t)base);
+        for (int64_t g = 0; g < groups; g++) {
+            int nmax = 1, mmax = 1;
+            for (int q = 0; q < 64; q++) {
+                const int32_t k = plan.order[base + (size_t)(g * 64 + q)];
+                if (k < 0) continue;
+                const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
+                nmax = std::max<int>(nmax, (int)n); mmax = std::max<int>(mmax, (int)m);
+                cells += n * m;
+            }
+            WarpDesc d{};
+            d.nmax = nmax; d.mmax = mmax; d.stripes = (nmax + IS_R - 1) / IS_R; d.pad = 0;
+            d.dir_off = win.dir_words; d.rowbuf_off = win.rowbuf_entries;
+            d.rowcode_off = win.rowcodes; d.colcode_off = win.colcodes;
+            if (!score_only) win.dir_words += (int64_t)d.stripes * mmax * 128;  // uint4 per lane, column, stripe
+            win.rowbuf_entries += (int64_t)mmax * 32;
+            win.rowcodes += (int64_t)d.stripes * IS_R * 32;
+            win.colcodes += (int64_t)mmax * 32;
+            plan.desc.push_back(d);
         }
-        WarpDesc &d = plan.desc[(size_t)g];
-        d.nmax = nmax; d.mmax = mmax; d.stripes = (nmax + IS_R - 1) / IS_R; d.pad = 0;
-        d.dir_off = dir_words; d.rowbuf_off = rowbuf; d.rowcode_off = rowcodes; d.colcode_off = colcodes;
-        if (!score_only) dir_words += (int64_t)d.stripes * mmax * 128;   // uint4 per lane, column and stripe
-        rowbuf += (int64_t)mmax * 32;
-        rowcodes += (int64_t)d.stripes * IS_R * 32;
-        colcodes += (int64_t)mmax * 32;
+        plan.max_dir_words = std::max(plan.max_dir_words, win.dir_words);
+        plan.max_rowbuf = std::max(plan.max_rowbuf, win.rowbuf_entries);
+        plan.max_rowcodes = std::max(plan.max_rowcodes, win.rowcodes);
+        plan.max_colcodes = std::max(plan.max_colcodes, win.colcodes);
+        plan.windows.push_back(win);
     }
-    plan.dir_words = dir_words; plan.rowbuf_entries = rowbuf; plan.rowcodes = rowcodes; plan.colcodes = colcodes;
+    plan.n_groups = (int64_t)plan.desc.size();
     if (cells_out) *cells_out = cells;
 
-    auto alloc = [](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 1); };
     cudaError_t e;
-    if ((e = alloc(&plan.d_order, plan.order.size() * 4)) != cudaSuccess) goto oom;
-    if ((e = alloc(&plan.d_desc, plan.desc.size() * sizeof(WarpDesc))) != cudaSuccess) goto oom;
-    if ((e = alloc(&plan.d_rowcodes, (size_t)rowcodes * 2)) != cudaSuccess) goto oom;
-    if ((e = alloc(&plan.d_colcodes, (size_t)colcodes * 2)) != cudaSuccess) goto oom;
-    if ((e = alloc(&plan.d_rowbuf, (size_t)rowbuf * 12)) != cudaSuccess) goto oom;
-    if ((e = alloc(&plan.d_dirs, (size_t)dir_words * 4)) != cudaSuccess) goto oom;
-    if ((e = cudaMemcpyAsync(plan.d_order, plan.order.data(), plan.order.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) goto oom;
-    if ((e = cudaMemcpyAsync(plan.d_desc, plan.desc.data(), plan.desc.size() * sizeof(WarpDesc), cudaMemcpyHostToDevice, stream)) != cudaSuccess) goto oom;
+    if ((e = plan.d_order.alloc(plan.order.size() * 4)) != cudaSuccess) goto fail;
+    if ((e = plan.d_desc.alloc(plan.desc.size() * sizeof(WarpDesc))) != cudaSuccess) goto fail;
+    for (int sl = 0; sl < n_slots; sl++) {
+        SlotBuffers &b = plan.slots[sl];
+        if ((e = b.rowcodes.alloc((size_t)plan.max_rowcodes * 2)) != cudaSuccess) goto fail;
+        if ((e = b.colcodes.alloc((size_t)plan.max_colcodes * 2)) != cudaSuccess) goto fail;
+        if ((e = b.rowbuf.alloc((size_t)plan.max_rowbuf * 12)) != cudaSuccess) goto fail;
+        if ((e = b.dirs.alloc((size_t)plan.max_dir_words * 4)) != cudaSuccess) goto fail;
+    }
+    if ((e = cudaMemcpyAsync(plan.d_order.ptr, plan.order.data(), plan.order.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) goto fail;
+    if ((e = cudaMemcpyAsync(plan.d_desc.ptr, plan.desc.data(), plan.desc.size() * sizeof(WarpDesc), cudaMemcpyHostToDevice, stream)) != cudaSuccess) goto fail;
     return BT_OK;
-oom:
+fail:
     cudaGetLastError();
     return e == cudaErrorMemoryAllocation ? BT_ERR_OOM : BT_ERR_CUDA;
 }
 
-inline cudaError_t interseq_run_fill(InterseqPlan &plan, const InterseqIO &io, cudaStream_t stream,
-                                     int64_t *launches) {
-    interseq_pack_kernel<<<(unsigned)plan.n_groups, 256, 0, stream>>>(
-        (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.off1, io.off2, (const int32_t *)plan.d_order,
-        (const WarpDesc *)plan.d_desc, (uint16_t *)plan.d_rowcodes, (uint16_t *)plan.d_colcodes, plan.n_groups);
+// pack + fill of one window into the scratch of `slot`
+inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, int slot, const InterseqIO &io,
+                                        cudaStream_t stream, int64_t *launches) {
+    SlotBuffers &b = plan.slots[slot];
+    const int64_t groups = win.group_end - win.group_begin;
+    const int32_t *order = plan.d_order.as<int32_t>() + win.group_begin * 64;
+    const WarpDesc *desc = plan.d_desc.as<WarpDesc>() + win.group_begin;
+    interseq_pack_kernel<<<(unsigned)groups, 256, 0, stream>>>(
+        (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.off1, io.off2, order, desc,
+        b.rowcodes.as<uint16_t>(), b.colcodes.as<uint16_t>(), groups);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     (*launches)++;
     const size_t smem = (size_t)plan.C.n_rows * plan.C.n_cols * IS_ROWW;
-    const unsigned grid = (unsigned)((plan.n_groups + IS_THREADS / 32 - 1) / (IS_THREADS / 32));
+    const unsigned grid = (unsigned)((groups + IS_THREADS / 32 - 1) / (IS_THREADS / 32));
     if (plan.C.score_only) {
         e = cudaFuncSetAttribute(interseq_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         interseq_fill_kernel<false><<<grid, IS_THREADS, smem, stream>>>(
-            plan.C, (const WarpDesc *)plan.d_desc, (const int32_t *)plan.d_order, io.off1, io.off2, io.matrix,
-            (const uint16_t *)plan.d_rowcodes, (const uint16_t *)plan.d_colcodes, (uint32_t *)plan.d_rowbuf,
-            (uint32_t *)plan.d_dirs, io.score, plan.n_groups);
+            plan.C, desc, order, io.off1, io.off2, io.matrix, b.rowcodes.as<uint16_t>(), b.colcodes.as<uint16_t>(),
+            b.rowbuf.as<uint32_t>(), b.dirs.as<uint32_t>(), io.score, groups);
     } else {
         e = cudaFuncSetAttribute(interseq_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         interseq_fill_kernel<true><<<grid, IS_THREADS, smem, stream>>>(
-            plan.C, (const WarpDesc *)plan.d_desc, (const int32_t *)plan.d_order, io.off1, io.off2, io.matrix,
-            (const uint16_t *)plan.d_rowcodes, (const uint16_t *)plan.d_colcodes, (uint32_t *)plan.d_rowbuf,
-            (uint32_t *)plan.d_dirs, io.score, plan.n_groups);
+            plan.C, desc, order, io.off1, io.off2, io.matrix, b.rowcodes.as<uint16_t>(), b.colcodes.as<uint16_t>(),
+            b.rowbuf.as<uint32_t>(), b.dirs.as<uint32_t>(), io.score, groups);
     }
     e = cudaGetLastError();
     if (e == cudaSuccess) (*launches)++;
     return e;
 }
 
-inline cudaError_t interseq_run_traceback(InterseqPlan &plan, const InterseqIO &io, cudaStream_t stream,
-                                          int64_t *launches) {
+inline cudaError_t interseq_traceback_window(InterseqPlan &plan, const Window &win, int slot,
+                                             const InterseqIO &io, cudaStream_t stream, int64_t *launches) {
     if (plan.C.score_only) return cudaSuccess;
-    const int64_t slots = plan.n_groups * 64;
+    const int64_t slots = (win.group_end - win.group_begin) * 64;
     interseq_traceback_kernel<<<(unsigned)((slots + 127) / 128), 128, 0, stream>>>(
-        (const WarpDesc *)plan.d_desc, (const int32_t *)plan.d_order, io.off1, io.off2,
-        (const uint32_t *)plan.d_dirs, io.trace_len, io.first, io.ops, slots);
+        plan.d_desc.as<WarpDesc>() + win.group_begin, plan.d_order.as<int32_t>() + win.group_begin * 64, io.off1,
+        io.off2, plan.slots[slot].dirs.as<uint32_t>(), io.trace_len, io.first, io.ops, slots);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) (*launches)++;
     return e;

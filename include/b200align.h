@@ -70,6 +70,10 @@ int bt_get_device(void);
 void *bt_pinned_alloc(size_t bytes);
 void bt_pinned_free(void *ptr);
 
+/* Device buffers of finished batches are cached per device for reuse; this returns them to
+ * the driver (cudaFree). */
+void bt_pool_trim(void);
+
 /* ---- single pair: the reference's FFI contract -------------------------------------
  *
  * code1/code2: contiguous arrays of `code_bytes`-wide unsigned codes (len1, len2

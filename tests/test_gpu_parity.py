@@ -296,6 +296,12 @@ def test_batch_matches_oracle(gap, local, term):
     with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, gap, term, local, score_only=True) as batch:
         batch.run()
         assert np.array_equal(batch.fetch().scores, ref_scores)
+    # the pipelined one-shot entry point must agree with the resident-batch object
+    one = bt.align_batch_arrays(codes1, off1, codes2, off2, matrix, gap, term, local)
+    assert np.array_equal(one.scores, ref_scores)
+    assert np.array_equal(one.trace_len, res.trace_len) and np.array_equal(one.first, res.first)
+    assert np.array_equal(one.ops, res.ops) or all(
+        np.array_equal(a, b) for a, b in zip(one.traces(), traces))
 
 
 def test_batch_c2_shape_properties():
@@ -333,6 +339,27 @@ def test_batch_c2_shape_properties():
         t, s = oracle.align_optimal(codes1[off1[k]:off1[k + 1]], codes2[off2[k]:off2[k + 1]],
                                     matrix, (-10, -1), True, False, False, 1)
         assert s == res.scores[k] and np.array_equal(t[0], res.trace(k))
+
+
+def test_pipelined_windows_match_resident_batch():
+    """Several windows through both slots of the pipelined path (bt_align_batch)."""
+    rng = np.random.default_rng(9)
+    n_pairs = 700_000
+    codes1, off1, codes2, off2 = _random_batch(rng, n_pairs, 20, 60)
+    matrix = BLOSUM().score_matrix()
+    one = bt.align_batch_arrays(codes1, off1, codes2, off2, matrix, (-10, -1), True, False)
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, (-10, -1), True, False) as batch:
+        assert batch.kernel == "interseq_s16x2"
+        batch.run()
+        res = batch.fetch()
+    assert np.array_equal(one.scores, res.scores)
+    assert np.array_equal(one.trace_len, res.trace_len)
+    assert np.array_equal(one.first, res.first)
+    idx = rng.choice(n_pairs, 200, replace=False)
+    for k in idx:
+        t, sc = oracle.align_optimal(codes1[off1[k]:off1[k + 1]], codes2[off2[k]:off2[k + 1]],
+                                     matrix, (-10, -1), True, False, False, 1)
+        assert sc == one.scores[k] and np.array_equal(t[0], one.trace(k)) and np.array_equal(t[0], res.trace(k))
 
 
 def test_banded_batch_matches_oracle():
