@@ -7,6 +7,8 @@
 //                    range; full direction sets (general_kernel.cuh)
 // There is no CPU path: without a device every compute call fails.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -411,7 +413,7 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
 
     if (b->route == ROUTE_INTERSEQ) {
         st = interseq_prepare(b->interseq, *params, b->h_off1, b->h_off2, n_pairs, b->score_only, mn, mx,
-                              &b->cells, 1, s);
+                              &b->cells, 1, 3, s);
         if (st == BT_ERR_OOM) return fail(st, "out of device memory (inter-sequence plan)");
         if (st) return fail(st, "inter-sequence plan failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
@@ -550,6 +552,9 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
                                  int32_t *scores_out, int64_t *trace_len_out, int32_t *first_out,
                                  uint8_t *ops_out) {
     const int64_t total1 = h_off1[n_pairs], total2 = h_off2[n_pairs];
+    const bool trace = getenv("B200ALIGN_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     DevBuf d_codes1, d_codes2, d_off1, d_off2, d_matrix, d_score, d_len, d_first, d_ops, d_flag;
     CUDA_TRY(d_codes1.alloc((size_t)total1));
     CUDA_TRY(d_codes2.alloc((size_t)total2));
@@ -576,15 +581,24 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     CUDA_TRY(cudaStreamCreateWithFlags(&st.s[1], cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&st.ready, cudaEventDisableTiming));
 
-    InterseqPlan plan;
-    int64_t cells = 0;
-    int rc = interseq_prepare(plan, *params, h_off1, h_off2, n_pairs, score_only, mn, mx, &cells, 2, st.s[0]);
-    if (rc == BT_ERR_OOM) return fail(rc, "out of device memory (inter-sequence plan)");
-    if (rc) return fail(rc, "inter-sequence plan failed");
+    const double t1 = now();
+    // start moving data before the host plans the windows: offsets, matrix and the codes of
+    // the first window
     CUDA_TRY(cudaMemsetAsync(d_flag.ptr, 0, 4, st.s[0]));
     CUDA_TRY(cudaMemcpyAsync(d_off1.ptr, off1, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.s[0]));
     CUDA_TRY(cudaMemcpyAsync(d_off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.s[0]));
     CUDA_TRY(cudaMemcpyAsync(d_matrix.ptr, matrix, mb, cudaMemcpyHostToDevice, st.s[0]));
+    {
+        const int64_t first_end = std::min(n_pairs, interseq_pairs_per_window(n_pairs, 1));
+        CUDA_TRY(cudaMemcpyAsync(d_codes1.ptr, codes1, (size_t)h_off1[first_end], cudaMemcpyHostToDevice, st.s[0]));
+        CUDA_TRY(cudaMemcpyAsync(d_codes2.ptr, codes2, (size_t)h_off2[first_end], cudaMemcpyHostToDevice, st.s[0]));
+    }
+    InterseqPlan plan;
+    int64_t cells = 0;
+    int rc = interseq_prepare(plan, *params, h_off1, h_off2, n_pairs, score_only, mn, mx, &cells, 2, 1, st.s[0]);
+    const double t2 = now();
+    if (rc == BT_ERR_OOM) return fail(rc, "out of device memory (inter-sequence plan)");
+    if (rc) return fail(rc, "inter-sequence plan failed");
     CUDA_TRY(cudaEventRecord(st.ready, st.s[0]));
     CUDA_TRY(cudaStreamWaitEvent(st.s[1], st.ready, 0));
 
@@ -598,8 +612,10 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
         const int64_t a1 = h_off1[win.pair_begin], b1 = h_off1[win.pair_end];
         const int64_t a2 = h_off2[win.pair_begin], b2 = h_off2[win.pair_end];
         const int64_t np = win.pair_end - win.pair_begin;
-        CUDA_TRY(cudaMemcpyAsync((char *)d_codes1.ptr + a1, (const char *)codes1 + a1, (size_t)(b1 - a1), cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync((char *)d_codes2.ptr + a2, (const char *)codes2 + a2, (size_t)(b2 - a2), cudaMemcpyHostToDevice, s));
+        if (w > 0) {
+            CUDA_TRY(cudaMemcpyAsync((char *)d_codes1.ptr + a1, (const char *)codes1 + a1, (size_t)(b1 - a1), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync((char *)d_codes2.ptr + a2, (const char *)codes2 + a2, (size_t)(b2 - a2), cudaMemcpyHostToDevice, s));
+        }
         validate_codes_kernel<<<(int)std::min<int64_t>(592, (b1 - a1 + 255) / 256), 256, 0, s>>>(
             (const char *)d_codes1.ptr + a1, b1 - a1, 1, (uint64_t)params->n_rows, d_flag.as<int>());
         validate_codes_kernel<<<(int)std::min<int64_t>(592, (b2 - a2 + 255) / 256), 256, 0, s>>>(
@@ -619,8 +635,12 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
         }
     }
     int flag = 0;
+    const double t3 = now();
     CUDA_TRY(cudaStreamSynchronize(st.s[0]));
     CUDA_TRY(cudaStreamSynchronize(st.s[1]));
+    if (trace)
+        fprintf(stderr, "[b200align] alloc %.2f ms, plan %.2f ms, enqueue %.2f ms, drain %.2f ms, windows %zu\n",
+                t1 - t0, t2 - t1, t3 - t2, now() - t3, plan.windows.size());
     CUDA_TRY(cudaMemcpy(&flag, d_flag.ptr, 4, cudaMemcpyDeviceToHost));
     if (flag) return fail(BT_ERR_INVALID_CODE, "a sequence code is outside the substitution matrix");
     return BT_OK;

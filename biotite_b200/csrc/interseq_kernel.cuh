@@ -26,7 +26,9 @@
 // that no finite value can leave the exact range (interseq_eligible).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200align.h"
@@ -374,74 +376,110 @@ inline int64_t interseq_window_groups() {
     return (int64_t)sms * 3 * (IS_THREADS / 32) * 3;
 }
 
+// Pairs per window for a batch of n_pairs when a window should span `waves` full waves.
+inline int64_t interseq_pairs_per_window(int64_t n_pairs, int waves) {
+    const int64_t win_pairs = interseq_window_groups() / 3 * waves * 64;
+    const int64_t n_windows = std::max<int64_t>(1, (n_pairs + win_pairs - 1) / win_pairs);
+    return ((n_pairs + n_windows - 1) / n_windows + 63) / 64 * 64;  // balanced windows
+}
+
+struct WindowPlan {
+    Window win{};
+    std::vector<int32_t> order;
+    std::vector<WarpDesc> desc;
+    int64_t cells = 0;
+};
+
+// Sort one window by (len1, len2) (two stable counting passes over 16-bit keys), deal the
+// pairs to groups of 64 - longest first, because the block scheduler hands out groups in
+// index order and the tail of a window should consist of its cheapest groups - and lay out
+// the window's scratch.
+inline void interseq_plan_window(WindowPlan &wp, const std::vector<int64_t> &off1,
+                                 const std::vector<int64_t> &off2, int64_t w0, int64_t w1, int score_only) {
+    const int64_t cnt = w1 - w0;
+    std::vector<int32_t> tmp((size_t)cnt), sorted((size_t)cnt), count(IS_MAX_LEN + 2, 0);
+    for (int64_t k = w0; k < w1; k++) count[(size_t)(off2[k + 1] - off2[k]) + 1]++;
+    for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
+    for (int64_t k = w0; k < w1; k++) tmp[(size_t)count[(size_t)(off2[k + 1] - off2[k])]++] = (int32_t)k;
+    std::fill(count.begin(), count.end(), 0);
+    for (int64_t k = w0; k < w1; k++) count[(size_t)(off1[k + 1] - off1[k]) + 1]++;
+    for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
+    for (int64_t q = 0; q < cnt; q++) {
+        const int32_t k = tmp[(size_t)q];
+        sorted[(size_t)count[(size_t)(off1[k + 1] - off1[k])]++] = k;
+    }
+    Window &win = wp.win;
+    win.pair_begin = w0; win.pair_end = w1;
+    const int64_t groups = (cnt + 63) / 64;
+    wp.order.assign((size_t)groups * 64, -1);
+    std::copy(sorted.rbegin(), sorted.rend(), wp.order.begin());
+    wp.desc.resize((size_t)groups);
+    for (int64_t g = 0; g < groups; g++) {
+        int nmax = 1, mmax = 1;
+        for (int q = 0; q < 64; q++) {
+            const int32_t k = wp.order[(size_t)(g * 64 + q)];
+            if (k < 0) continue;
+            const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
+            nmax = std::max<int>(nmax, (int)n); mmax = std::max<int>(mmax, (int)m);
+            wp.cells += n * m;
+        }
+        WarpDesc &d = wp.desc[(size_t)g];
+        d.nmax = nmax; d.mmax = mmax; d.stripes = (nmax + IS_R - 1) / IS_R; d.pad = 0;
+        d.dir_off = win.dir_words; d.rowbuf_off = win.rowbuf_entries;
+        d.rowcode_off = win.rowcodes; d.colcode_off = win.colcodes;
+        if (!score_only) win.dir_words += (int64_t)d.stripes * mmax * 128;  // uint4 per lane, column, stripe
+        win.rowbuf_entries += (int64_t)mmax * 32;
+        win.rowcodes += (int64_t)d.stripes * IS_R * 32;
+        win.colcodes += (int64_t)mmax * 32;
+    }
+}
+
 inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const std::vector<int64_t> &off1,
                             const std::vector<int64_t> &off2, int64_t n_pairs, int score_only,
                             int32_t min_score, int32_t max_score, int64_t *cells_out, int n_slots,
-                            cudaStream_t stream) {
+                            int waves_per_window, cudaStream_t stream) {
     (void)max_score;
     plan.n_pairs = n_pairs;
     plan.C.gap_open = P.gap_open; plan.C.gap_ext = P.gap_ext;
     plan.C.neg = -32768 - P.gap_open - P.gap_ext - std::min(min_score, 0);
     plan.C.n_rows = P.n_rows; plan.C.n_cols = P.n_cols; plan.C.score_only = score_only;
 
-    const int64_t win_pairs = interseq_window_groups() * 64;
-    const int64_t n_windows = (n_pairs + win_pairs - 1) / win_pairs;
-    // balance the windows (all about the same number of waves)
-    const int64_t per_window = ((n_pairs + n_windows - 1) / n_windows + 63) / 64 * 64;
+    const int64_t per_window = interseq_pairs_per_window(n_pairs, waves_per_window);
+    const int64_t n_windows = (n_pairs + per_window - 1) / per_window;
+    std::vector<WindowPlan> wps((size_t)n_windows);
+    {
+        // windows are independent: plan them on a few host threads
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int n_threads = (int)std::min<int64_t>(std::min<unsigned>(hw, 8u), n_windows);
+        std::atomic<int64_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const int64_t w = next.fetch_add(1);
+                if (w >= n_windows) break;
+                const int64_t w0 = w * per_window, w1 = std::min(n_pairs, w0 + per_window);
+                interseq_plan_window(wps[(size_t)w], off1, off2, w0, w1, score_only);
+            }
+        };
+        std::vector<std::thread> threads;
+        for (int t = 1; t < n_threads; t++) threads.emplace_back(work);
+        work();
+        for (std::thread &t : threads) t.join();
+    }
     plan.windows.clear();
     plan.order.clear();
     plan.desc.clear();
-    std::vector<int32_t> tmp, sorted, count(IS_MAX_LEN + 2);
     int64_t cells = 0;
-    for (int64_t w0 = 0; w0 < n_pairs; w0 += per_window) {
-        const int64_t w1 = std::min(n_pairs, w0 + per_window), cnt = w1 - w0;
-        // counting sort of the window by (len1, len2): two stable passes over 16-bit keys
-        tmp.resize((size_t)cnt); sorted.resize((size_t)cnt);
-        std::fill(count.begin(), count.end(), 0);
-        for (int64_t k = w0; k < w1; k++) count[(size_t)(off2[k + 1] - off2[k]) + 1]++;
-        for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
-        for (int64_t k = w0; k < w1; k++) tmp[(size_t)count[(size_t)(off2[k + 1] - off2[k])]++] = (int32_t)k;
-        std::fill(count.begin(), count.end(), 0);
-        for (int64_t k = w0; k < w1; k++) count[(size_t)(off1[k + 1] - off1[k]) + 1]++;
-        for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
-        for (int64_t q = 0; q < cnt; q++) {
-            const int32_t k = tmp[(size_t)q];
-            sorted[(size_t)count[(size_t)(off1[k + 1] - off1[k])]++] = k;
-        }
-        Window win{};
-        win.pair_begin = w0; win.pair_end = w1;
-        win.group_begin = (int64_t)plan.desc.size();
-        const int64_t groups = (cnt + 63) / 64;
-        win.group_end = win.group_begin + groups;
-        const size_t base = plan.order.size();
-        plan.order.resize(base + (size_t)groups * 64, -1);
-        // longest pairs first: the block scheduler hands out groups in index order, so the
-        // tail of every window consists of its cheapest groups
-        std::copy(sorted.rbegin(), sorted.rend(), plan.order.begin() + (std::ptrdiff_t)base);
-        for (int64_t g = 0; g < groups; g++) {
-            int nmax = 1, mmax = 1;
-            for (int q = 0; q < 64; q++) {
-                const int32_t k = plan.order[base + (size_t)(g * 64 + q)];
-                if (k < 0) continue;
-                const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
-                nmax = std::max<int>(nmax, (int)n); mmax = std::max<int>(mmax, (int)m);
-                cells += n * m;
-            }
-            WarpDesc d{};
-            d.nmax = nmax; d.mmax = mmax; d.stripes = (nmax + IS_R - 1) / IS_R; d.pad = 0;
-            d.dir_off = win.dir_words; d.rowbuf_off = win.rowbuf_entries;
-            d.rowcode_off = win.rowcodes; d.colcode_off = win.colcodes;
-            if (!score_only) win.dir_words += (int64_t)d.stripes * mmax * 128;  // uint4 per lane, column, stripe
-            win.rowbuf_entries += (int64_t)mmax * 32;
-            win.rowcodes += (int64_t)d.stripes * IS_R * 32;
-            win.colcodes += (int64_t)mmax * 32;
-            plan.desc.push_back(d);
-        }
-        plan.max_dir_words = std::max(plan.max_dir_words, win.dir_words);
-        plan.max_rowbuf = std::max(plan.max_rowbuf, win.rowbuf_entries);
-        plan.max_rowcodes = std::max(plan.max_rowcodes, win.rowcodes);
-        plan.max_colcodes = std::max(plan.max_colcodes, win.colcodes);
-        plan.windows.push_back(win);
+    for (WindowPlan &wp : wps) {
+        wp.win.group_begin = (int64_t)plan.desc.size();
+        wp.win.group_end = wp.win.group_begin + (int64_t)wp.desc.size();
+        plan.order.insert(plan.order.end(), wp.order.begin(), wp.order.end());
+        plan.desc.insert(plan.desc.end(), wp.desc.begin(), wp.desc.end());
+        plan.max_dir_words = std::max(plan.max_dir_words, wp.win.dir_words);
+        plan.max_rowbuf = std::max(plan.max_rowbuf, wp.win.rowbuf_entries);
+        plan.max_rowcodes = std::max(plan.max_rowcodes, wp.win.rowcodes);
+        plan.max_colcodes = std::max(plan.max_colcodes, wp.win.colcodes);
+        plan.windows.push_back(wp.win);
+        cells += wp.cells;
     }
     plan.n_groups = (int64_t)plan.desc.size();
     if (cells_out) *cells_out = cells;
