@@ -329,8 +329,8 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total_cells * args.steps / e2e_s * 1e-9
-    h2d = int(p_codes1.nbytes + p_codes2.nbytes + off1.nbytes + off2.nbytes + matrix.nbytes)
-    d2h = int(sum(a.nbytes for a in out))
+    h2d = int(sum_over_ranks(float(p_codes1.nbytes + p_codes2.nbytes + off1.nbytes + off2.nbytes + matrix.nbytes)))
+    d2h = int(sum_over_ranks(float(sum(a.nbytes for a in out))))
 
     # ---- roofline of the dominant kernel (DP fill) ---------------------------------------------
     peak = np.zeros(3)
@@ -338,7 +338,8 @@ def main():
         v = _cabi.ctypes.c_double(0.0)
         _cabi.check(lib.bt_microbench(kind, _cabi.ctypes.byref(v)))
         peak[kind] = v.value
-    fill_s = fill_ms * 1e-3 / args.steps
+    fill_s = fill_ms * 1e-3 / args.steps          # all fill launches of one step (rank 0)
+    n_fill_launches = max(1, (launches // args.steps) // 3)  # pack + fill + traceback per window
     achieved = cells * ALGO_LANE_INSTR_PER_CELL / fill_s
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     hbm_peak, hbm_src = 6650.0, "fallback"
@@ -350,7 +351,8 @@ def main():
         "frac": achieved / peak[0],
         "peak_source": "bt_microbench kind 0 (VIADDMNMX.S16x2 + VIMNMX3.S16x2, register-only) measured in this run",
         "algorithmic_lane_instr_per_cell": ALGO_LANE_INSTR_PER_CELL,
-        "cells_per_launch": cells, "fill_ms_per_step": fill_s * 1e3,
+        "fill_launches_per_step": n_fill_launches, "cells_per_launch": cells / n_fill_launches,
+        "ms_per_launch": fill_s * 1e3 / n_fill_launches, "fill_ms_per_step": fill_s * 1e3,
         "traceback_ms_per_step": back_ms / args.steps,
         "fill_share_of_step": fill_ms / device_ms if device_ms else None,
         "peak_s32_dpx": peak[1] * 1e-12, "peak_dual_issue": peak[2] * 1e-12,

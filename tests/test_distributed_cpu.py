@@ -1,0 +1,98 @@
+"""World-size-2 ``gloo`` test of the multi-process path: sharding by DP work and the final
+gather.  The compute step is injected (CPU oracle) because there is no GPU here; on the GPU
+box the same function runs with the CUDA batch entry point (tests/test_gpu_parity.py)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import biotite_b200 as bt
+from biotite_b200.distributed import shard_bounds
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make_batch(seed=0, n_pairs=37):
+    rng = np.random.default_rng(seed)
+    len1 = rng.integers(1, 60, n_pairs)
+    len2 = rng.integers(1, 60, n_pairs)
+    off1 = np.concatenate(([0], np.cumsum(len1))).astype(np.int64)
+    off2 = np.concatenate(([0], np.cumsum(len2))).astype(np.int64)
+    codes1 = rng.integers(0, 20, off1[-1]).astype(np.uint8)
+    codes2 = rng.integers(0, 20, off2[-1]).astype(np.uint8)
+    return codes1, off1, codes2, off2
+
+
+def _oracle_compute(codes1, off1, codes2, off2, scoring, gap, term, local, bands, score_only):
+    """Stand-in for align_batch_arrays with the same result layout."""
+    from biotite_b200.batch import BatchResult
+    from oracle import oracle
+    scores, traces = oracle.batch(codes1, off1, codes2, off2, scoring, gap, term, local, score_only,
+                                  n_threads=2)
+    n = len(off1) - 1
+    ops_off = off1 + off2
+    trace_len = np.zeros(n, dtype=np.int64)
+    first = np.zeros((n, 2), dtype=np.int32)
+    ops = np.zeros(int(ops_off[-1]), dtype=np.uint8)
+    for k in range(n):
+        t = traces[k]
+        trace_len[k] = len(t)
+        if len(t) == 0:
+            continue
+        # first alignment column -> table cell; following rows -> step bytes (end-to-start)
+        i = t[0, 0] + 1 if t[0, 0] >= 0 else 0
+        j = t[0, 1] + 1 if t[0, 1] >= 0 else 0
+        first[k] = (i, j)
+        step = np.where(t[:, 0] == -1, 1, np.where(t[:, 1] == -1, 2, 0)).astype(np.uint8)
+        ops[ops_off[k]:ops_off[k] + len(t)] = step[::-1]
+    return BatchResult(scores, trace_len, first, ops, ops_off)
+
+
+def _worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from biotite_b200.distributed import align_batch_sharded
+    codes1, off1, codes2, off2 = _make_batch()
+    matrix = bt.SubstitutionMatrix.std_protein_matrix().score_matrix()
+    res = align_batch_sharded(codes1, off1, codes2, off2, matrix, (-10, -1), True, False,
+                              compute=_oracle_compute)
+    if rank == 0:
+        flat, rows_off = res.traces_flat()
+        np.savez(out_path, scores=res.scores, flat=flat, rows_off=rows_off)
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_balance_cells():
+    codes1, off1, codes2, off2 = _make_batch(n_pairs=1000)
+    for world in (1, 2, 4, 8):
+        b = shard_bounds(off1, off2, world)
+        assert b[0] == 0 and b[-1] == 1000 and np.all(np.diff(b) >= 0)
+        cells = np.diff(off1) * np.diff(off2)
+        per = np.array([cells[b[r]:b[r + 1]].sum() for r in range(world)])
+        assert per.max() <= per.mean() + cells.max()
+
+
+def test_two_rank_gloo_gather_matches_single_process(tmp_path):
+    import torch.multiprocessing as mp
+    out = tmp_path / "result.npz"
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(out)), nprocs=2, join=True)
+    got = np.load(out)
+    codes1, off1, codes2, off2 = _make_batch()
+    matrix = bt.SubstitutionMatrix.std_protein_matrix().score_matrix()
+    ref = _oracle_compute(codes1, off1, codes2, off2, matrix, (-10, -1), True, False, None, False)
+    flat, rows_off = ref.traces_flat()
+    assert np.array_equal(got["scores"], ref.scores)
+    assert np.array_equal(got["rows_off"], rows_off)
+    assert np.array_equal(got["flat"], flat)
