@@ -131,6 +131,7 @@ general_fill_kernel(const DevParams P, const BatchView V) {
         int32_t *smat = smem + (V.gscratch ? 0 : 3 * slots * NS);
         for (int k = tid; k < P.n_rows * P.n_cols; k += nthr) smat[k] = V.matrix[k];
         mat = smat;
+        __syncthreads();  // the first wavefront reads entries staged by other threads
     }
     uint8_t *dir = P.score_only ? nullptr : V.dirs + V.dir_off[p];
     int32_t *cand = (BANDED && !P.local) ? V.cand + V.cand_off[p] : nullptr;
