@@ -136,7 +136,7 @@ struct BtBatch {
     std::vector<int64_t> h_off1, h_off2, h_bands, h_dir_off, h_cand_off;
     std::vector<Chunk> chunks;
     DevBuf codes1, codes2, off1, off2, bands, matrix, dir_off, cand_off, cand, dirs, gscratch;
-    DevBuf score, start_idx, start_state, end_vals, trace_len, first, ops, flag;
+    DevBuf score, start_idx, start_state, end_vals, trace_len, first, ops, flag, is_start;
     InterseqPlan interseq;  // state of the packed 16-bit route
     bool ran = false;
     // per-phase device timing: events[3k..3k+2] bracket fill and traceback of step k
@@ -412,6 +412,7 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     }
 
     if (b->route == ROUTE_INTERSEQ) {
+        CUDA_TRY(b->is_start.alloc((size_t)n_pairs * 8));
         st = interseq_prepare(b->interseq, *params, b->h_off1, b->h_off2, n_pairs, b->score_only, mn, mx,
                               &b->cells, 1, 3, s);
         if (st == BT_ERR_OOM) return fail(st, "out of device memory (inter-sequence plan)");
@@ -472,7 +473,7 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
         if (b->route == ROUTE_INTERSEQ) {
             InterseqIO io{b->codes1.ptr, b->codes2.ptr, b->off1.as<int64_t>(), b->off2.as<int64_t>(),
                           b->matrix.as<int32_t>(), b->score.as<int32_t>(), b->trace_len.as<int64_t>(),
-                          b->first.as<int32_t>(), b->ops.as<uint8_t>()};
+                          b->first.as<int32_t>(), b->ops.as<uint8_t>(), b->is_start.as<int32_t>()};
             cudaError_t e = cudaSuccess;
             for (const Window &win : b->interseq.windows) {
                 if (e == cudaSuccess) e = b->mark_phase();
@@ -555,7 +556,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     const bool trace = getenv("B200ALIGN_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
-    DevBuf d_codes1, d_codes2, d_off1, d_off2, d_matrix, d_score, d_len, d_first, d_ops, d_flag;
+    DevBuf d_codes1, d_codes2, d_off1, d_off2, d_matrix, d_score, d_len, d_first, d_ops, d_flag, d_start;
     CUDA_TRY(d_codes1.alloc((size_t)total1));
     CUDA_TRY(d_codes2.alloc((size_t)total2));
     CUDA_TRY(d_off1.alloc((size_t)(n_pairs + 1) * 8));
@@ -564,6 +565,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     CUDA_TRY(d_matrix.alloc(mb));
     CUDA_TRY(d_score.alloc((size_t)n_pairs * 4));
     CUDA_TRY(d_flag.alloc(4));
+    CUDA_TRY(d_start.alloc((size_t)n_pairs * 8));
     if (!score_only) {
         CUDA_TRY(d_len.alloc((size_t)n_pairs * 8));
         CUDA_TRY(d_first.alloc((size_t)n_pairs * 8));
@@ -603,7 +605,8 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     CUDA_TRY(cudaStreamWaitEvent(st.s[1], st.ready, 0));
 
     InterseqIO io{d_codes1.ptr, d_codes2.ptr, d_off1.as<int64_t>(), d_off2.as<int64_t>(), d_matrix.as<int32_t>(),
-                  d_score.as<int32_t>(), d_len.as<int64_t>(), d_first.as<int32_t>(), d_ops.as<uint8_t>()};
+                  d_score.as<int32_t>(), d_len.as<int64_t>(), d_first.as<int32_t>(), d_ops.as<uint8_t>(),
+                  d_start.as<int32_t>()};
     int64_t launches = 0;
     for (size_t w = 0; w < plan.windows.size(); w++) {
         const Window &win = plan.windows[w];

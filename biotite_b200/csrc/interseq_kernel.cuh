@@ -57,6 +57,7 @@ struct InterseqConst {
     int32_t gap_open, gap_ext, neg;  // neg: the 16-bit "minus infinity"
     int32_t n_rows, n_cols;
     int32_t score_only;
+    int32_t mode;                    // IS_GLOBAL / IS_SEMI / IS_LOCAL
 };
 
 // A window is a run of consecutive pairs (in input order) that is sorted, packed, filled and
@@ -70,7 +71,7 @@ struct Window {
 
 // Scratch buffers of one in-flight window.
 struct SlotBuffers {
-    DevBuf rowcodes, colcodes, dirs, rowbuf;
+    DevBuf rowcodes, colcodes, dirs, rowbuf, lastrow, lastcol;
 };
 
 // Host-side plan of one batch.
@@ -93,6 +94,7 @@ struct InterseqIO {
     int64_t *trace_len;
     int32_t *first;
     uint8_t *ops;
+    int32_t *start;  // local: first optimum cell per pair (2 ints), scratch of the batch
 };
 
 // ---------------------------------------------------------------------------------------
@@ -101,7 +103,7 @@ struct InterseqIO {
 inline bool interseq_eligible(const BtParams &P, const std::vector<int64_t> &off1,
                               const std::vector<int64_t> &off2, int64_t n_pairs, int32_t min_score,
                               int32_t max_score) {
-    if (!P.affine || P.banded || P.local || !P.terminal_penalty || !P.use_matrix) return false;
+    if (!P.affine || P.banded || !P.use_matrix) return false;
     if (P.code_bytes != 1 || n_pairs < 64) return false;
     if ((int64_t)P.n_rows * P.n_cols * IS_ROWW > 96 * 1024 || P.n_rows > 255 || P.n_cols > 255) return false;
     int64_t nmax = 0, mmax = 0;
@@ -161,31 +163,49 @@ __global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes
         : "=&r"(out), "+r"(acc_lo), "+r"(acc_hi)                                          \
         : "r"(a), "r"(b), "r"(c))
 
-template <bool TRACED>
+enum : int { IS_GLOBAL = 0, IS_SEMI = 1, IS_LOCAL = 2 };
+
+// Per-window scratch and per-batch result pointers handed to the kernels.
+struct InterseqArgs {
+    const WarpDesc *desc;
+    const int32_t *order;
+    const int64_t *off1, *off2;
+    const int32_t *matrix;
+    const uint16_t *rowcodes, *colcodes;
+    uint32_t *rowbuf;     // 3 planes [j][lane]: M, F2, H of the stripe's last row
+    uint32_t *lastrow;    // semi-global: M of the pair's last row, 2 planes [j][lane] (low / high pair)
+    uint32_t *lastcol;    // semi-global: M of the pair's last column, 2 planes [row][lane] (low / high pair)
+    uint32_t *dirs;
+    int32_t *score;
+    int32_t *start;       // local: table cell (i, j) of the first optimum, 2 per pair
+    int64_t n_groups;
+};
+
+// MODE selects the boundary conditions of pairwise.rs: IS_GLOBAL = terminal gaps penalised
+// (:707-780), IS_SEMI = free terminal gaps (the waived last row / column is resolved by the
+// traceback kernel from the captured border M values, see there), IS_LOCAL = Smith-Waterman
+// (M clamped at 0, :659-666; clamping the gap states is not needed for scores or for the
+// first-priority trace because M >= 0 always wins a tie against a non-positive gap state).
+template <int MODE, bool TRACED>
 __global__ void __launch_bounds__(IS_THREADS, 3)
-interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
-                     const int32_t *__restrict__ order, const int64_t *__restrict__ off1,
-                     const int64_t *__restrict__ off2, const int32_t *__restrict__ matrix,
-                     const uint16_t *__restrict__ rowcodes, const uint16_t *__restrict__ colcodes,
-                     uint32_t *__restrict__ rowbuf, uint32_t *__restrict__ dirs,
-                     int32_t *__restrict__ score, int64_t n_groups) {
+interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
     extern __shared__ uint32_t table[];  // [b][a][lane]: zero-extended s16 score, one copy per lane
     const int lane = threadIdx.x & 31;
     {
         const int entries = C.n_rows * C.n_cols;
         for (int e = threadIdx.x >> 5; e < entries; e += IS_THREADS / 32) {
             const int a = e / C.n_cols, b = e % C.n_cols;
-            table[(b * C.n_rows + a) * 32 + lane] = (uint32_t)matrix[e] & 0xffffu;
+            table[(b * C.n_rows + a) * 32 + lane] = (uint32_t)A.matrix[e] & 0xffffu;
         }
     }
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * (IS_THREADS / 32) + (threadIdx.x >> 5);
-    if (g >= n_groups) return;
-    const WarpDesc d = desc[g];
-    const int32_t p_lo = order[g * 64 + 2 * lane], p_hi = order[g * 64 + 2 * lane + 1];
+    if (g >= A.n_groups) return;
+    const WarpDesc d = A.desc[g];
+    const int32_t p_lo = A.order[g * 64 + 2 * lane], p_hi = A.order[g * 64 + 2 * lane + 1];
     int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
-    if (p_lo >= 0) { n_lo = (int)(off1[p_lo + 1] - off1[p_lo]); m_lo = (int)(off2[p_lo + 1] - off2[p_lo]); }
-    if (p_hi >= 0) { n_hi = (int)(off1[p_hi + 1] - off1[p_hi]); m_hi = (int)(off2[p_hi + 1] - off2[p_hi]); }
+    if (p_lo >= 0) { n_lo = (int)(A.off1[p_lo + 1] - A.off1[p_lo]); m_lo = (int)(A.off2[p_lo + 1] - A.off2[p_lo]); }
+    if (p_hi >= 0) { n_hi = (int)(A.off1[p_hi + 1] - A.off1[p_hi]); m_hi = (int)(A.off2[p_hi + 1] - A.off2[p_hi]); }
 
     const uint32_t ext2 = ((uint32_t)C.gap_ext & 0xffffu) * 0x10001u;
     const uint32_t open2 = ((uint32_t)C.gap_open & 0xffffu) * 0x10001u;
@@ -193,19 +213,30 @@ interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
     const uint32_t col_stride = (uint32_t)C.n_rows * IS_ROWW;  // bytes between column letters
     const char *tbase = (const char *)table + lane * 4;
 
-    const uint16_t *rc = rowcodes + d.rowcode_off + lane;
-    const uint16_t *cc = colcodes + d.colcode_off + lane;
-    uint32_t *rb_m = rowbuf + d.rowbuf_off * 3 + lane;            // [j][lane] planes: M, F2, H
+    const uint16_t *rc = A.rowcodes + d.rowcode_off + lane;
+    const uint16_t *cc = A.colcodes + d.colcode_off + lane;
+    uint32_t *rb_m = A.rowbuf + d.rowbuf_off * 3 + lane;            // [j][lane] planes: M, F2, H
     uint32_t *rb_f = rb_m + (int64_t)d.mmax * 32;
     uint32_t *rb_h = rb_f + (int64_t)d.mmax * 32;
-    uint4 *dir = TRACED ? (uint4 *)(dirs + d.dir_off) + lane : nullptr;
+    uint4 *dir = TRACED ? (uint4 *)(A.dirs + d.dir_off) + lane : nullptr;
+    // two planes each (low / high pair): their last rows / columns are captured at different times
+    uint32_t *lastrow_lo = MODE == IS_SEMI ? A.lastrow + d.rowbuf_off * 2 + lane : nullptr;
+    uint32_t *lastrow_hi = MODE == IS_SEMI ? lastrow_lo + (int64_t)d.mmax * 32 : nullptr;
+    uint32_t *lastcol_lo = MODE == IS_SEMI ? A.lastcol + d.rowcode_off * 2 + lane : nullptr;
+    uint32_t *lastcol_hi = MODE == IS_SEMI ? lastcol_lo + (int64_t)d.stripes * IS_R * 32 : nullptr;
 
-    int32_t best_lo = 0, best_hi = 0;
+    int32_t best_lo = 0, best_hi = 0;          // optimum (local: running maximum of M)
+    int32_t bidx_lo = 0, bidx_hi = 0;          // local: row-major index i*(m+1)+j of the first optimum
+    uint32_t best2 = 0;                        // local score-only: packed running maximum
     for (int s = 0; s < d.stripes; s++) {
         const int r0 = s * IS_R;  // rows r0+1 .. r0+R of the DP table
         // column step at which this stripe holds the end cell (n, m) of the low / high pair
         const int j_lo = (n_lo - 1) / IS_R == s ? m_lo - 1 : -1;
         const int j_hi = (n_hi - 1) / IS_R == s ? m_hi - 1 : -1;
+        // row of this stripe that is the last row of the low / high pair (or -1)
+        const int rl_lo = (n_lo - 1) / IS_R == s ? (n_lo - 1) % IS_R : -1;
+        const int rl_hi = (n_hi - 1) / IS_R == s ? (n_hi - 1) % IS_R : -1;
+        const bool rows_valid = r0 + IS_R <= n_lo && r0 + IS_R <= n_hi;  // no padding rows in this stripe
         uint32_t rp_lo[IS_R], rp_hi[IS_R], Ml[IS_R], F1l[IS_R], Hl[IS_R];
 #pragma unroll
         for (int r = 0; r < IS_R; r++) {
@@ -213,13 +244,15 @@ interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
             rp_lo[r] = (v & 0xffu) * IS_ROWW;
             rp_hi[r] = (v >> 8) * IS_ROWW;
             // column 0 (pairwise.rs:707-745): M = G1 = -inf, H = G2 = open + (i-1)*ext
+            // (semi-global / local: H = 0)
             Ml[r] = neg2;
             F1l[r] = neg2;
-            Hl[r] = ((uint32_t)(C.gap_open + (r0 + r) * C.gap_ext) & 0xffffu) * 0x10001u;
+            Hl[r] = MODE == IS_GLOBAL ? ((uint32_t)(C.gap_open + (r0 + r) * C.gap_ext) & 0xffffu) * 0x10001u : 0u;
         }
         // H(r0, 0): the origin for the first stripe, else column 0 of the row above
-        uint32_t hu_prev = s == 0 ? 0u : ((uint32_t)(C.gap_open + (r0 - 1) * C.gap_ext) & 0xffffu) * 0x10001u;
-        uint32_t h_row0 = open2;  // H(0, j) = open + (j-1)*ext (pairwise.rs:747-780)
+        uint32_t hu_prev = (s == 0 || MODE != IS_GLOBAL)
+                               ? 0u : ((uint32_t)(C.gap_open + (r0 - 1) * C.gap_ext) & 0xffffu) * 0x10001u;
+        uint32_t h_row0 = MODE == IS_GLOBAL ? open2 : 0u;  // H(0, j) = open + (j-1)*ext (pairwise.rs:747-780) or 0
         uint32_t nxt = cc[0];
         // the row above the stripe is prefetched one column ahead: its L2/HBM latency hides
         // behind the 16 rows of the current column
@@ -236,16 +269,17 @@ interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
             }
             if (j + 1 < d.mmax) {
                 nxt = cc[(int64_t)(j + 1) * 32];
-#if !defined(BT_EXP) || BT_EXP != 1
                 if (s > 0) {
                     nx_m = rb_m[(int64_t)(j + 1) * 32]; nx_f = rb_f[(int64_t)(j + 1) * 32];
                     nx_h = rb_h[(int64_t)(j + 1) * 32];
                 }
-#endif
             }
             const char *t_lo = tbase + (v & 0xffu) * col_stride;
             const char *t_hi = tbase + (v >> 8) * col_stride;
-            if (s == 0) { hu = h_row0; h_row0 = __vadd2(h_row0, ext2); }
+            if (s == 0) {
+                hu = h_row0;
+                if (MODE == IS_GLOBAL) h_row0 = __vadd2(h_row0, ext2);
+            }
             // Rows are software-pipelined so that every state array is updated in place:
             // F1 and M of row r+1 are formed (from the previous column's M and H) before
             // H of row r overwrites Hl[r].
@@ -265,7 +299,7 @@ interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
         const uint32_t fe = __vadd2(F1l[r], ext2);                                           \
         if (TRACED) { BT_MAX_PRED(F1l[r], Ml[r], fe, BT_ACC_LO(r), BT_ACC_HI(r), BT_BIT(r, 2)); } \
         else F1l[r] = __vmaxs2(Ml[r], fe);                                                   \
-        Ml[r] = __vadd2(diag_h, sim[r]);                                                     \
+        Ml[r] = MODE == IS_LOCAL ? __viaddmax_s16x2(diag_h, sim[r], 0u) : __vadd2(diag_h, sim[r]); \
     }
             BT_ROW_F1_M(0, hu_prev);
             hu_prev = hu;
@@ -289,41 +323,116 @@ interseq_fill_kernel(const InterseqConst C, const WarpDesc *__restrict__ desc,
                 rb_m[(int64_t)j * 32] = up_m; rb_f[(int64_t)j * 32] = up_f2; rb_h[(int64_t)j * 32] = Hl[IS_R - 1];
             }
             if (TRACED) dir[((int64_t)s * d.mmax + j) * 32] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-            // optimum: H(n, m) (pairwise.rs:866-879)
-            if (j == j_lo || j == j_hi) {
+
+            if (MODE == IS_GLOBAL) {
+                // optimum: H(n, m) (pairwise.rs:866-879)
+                if (j == j_lo || j == j_hi) {
 #pragma unroll
-                for (int r = 0; r < IS_R; r++) {
-                    if (j == j_lo && r0 + r + 1 == n_lo) best_lo = (int16_t)(Hl[r] & 0xffffu);
-                    if (j == j_hi && r0 + r + 1 == n_hi) best_hi = (int16_t)(Hl[r] >> 16);
+                    for (int r = 0; r < IS_R; r++) {
+                        if (j == j_lo && r0 + r + 1 == n_lo) best_lo = (int16_t)(Hl[r] & 0xffffu);
+                        if (j == j_hi && r0 + r + 1 == n_hi) best_hi = (int16_t)(Hl[r] >> 16);
+                    }
+                }
+            } else if (MODE == IS_SEMI) {
+                // border capture: M along the pair's last row and last column
+                if (rl_lo >= 0 || rl_hi >= 0) {
+                    uint32_t w_lo = 0, w_hi = 0;
+#pragma unroll
+                    for (int r = 0; r < IS_R; r++) {
+                        if (r == rl_lo) w_lo = Ml[r];
+                        if (r == rl_hi) w_hi = Ml[r];
+                    }
+                    if (rl_lo >= 0) lastrow_lo[(int64_t)j * 32] = w_lo;
+                    if (rl_hi >= 0) lastrow_hi[(int64_t)j * 32] = w_hi;
+                }
+                if (j == m_lo - 1) {
+#pragma unroll
+                    for (int r = 0; r < IS_R; r++) lastcol_lo[(int64_t)(r0 + r) * 32] = Ml[r];
+                }
+                if (j == m_hi - 1) {
+#pragma unroll
+                    for (int r = 0; r < IS_R; r++) lastcol_hi[(int64_t)(r0 + r) * 32] = Ml[r];
+                }
+            } else {
+                // local: running maximum of M over the cells inside the table, first in row-major
+                // order (pairwise.rs:849-865).  Fast path: one packed max per row; the scalar
+                // path runs where padding must be masked or (traced) a new optimum may appear.
+                uint32_t cm = Ml[0];
+#pragma unroll
+                for (int r = 1; r < IS_R; r++) cm = __vmaxs2(cm, Ml[r]);
+                const bool inside = rows_valid && j < m_lo && j < m_hi;
+                bool slow = !inside;
+                if (inside) {
+                    if (!TRACED) best2 = __vmaxs2(best2, cm);
+                    else {
+                        const int c_lo = (int16_t)(cm & 0xffffu), c_hi = (int16_t)(cm >> 16);
+                        slow = (c_lo >= best_lo && c_lo > 0) || (c_hi >= best_hi && c_hi > 0);
+                    }
+                }
+                if (slow) {
+#pragma unroll
+                    for (int r = 0; r < IS_R; r++) {
+                        const int row = r0 + r + 1, col = j + 1;
+                        const int v_lo = (int16_t)(Ml[r] & 0xffffu), v_hi = (int16_t)(Ml[r] >> 16);
+                        if (row <= n_lo && col <= m_lo) {
+                            const int idx = row * (m_lo + 1) + col;
+                            if (v_lo > best_lo || (v_lo == best_lo && v_lo > 0 && idx < bidx_lo)) { best_lo = v_lo; bidx_lo = idx; }
+                        }
+                        if (row <= n_hi && col <= m_hi) {
+                            const int idx = row * (m_hi + 1) + col;
+                            if (v_hi > best_hi || (v_hi == best_hi && v_hi > 0 && idx < bidx_hi)) { best_hi = v_hi; bidx_hi = idx; }
+                        }
+                    }
                 }
             }
         }
     }
-    if (p_lo >= 0) score[p_lo] = best_lo;
-    if (p_hi >= 0) score[p_hi] = best_hi;
+    if (MODE == IS_LOCAL && !TRACED) {
+        best_lo = max(best_lo, (int)(int16_t)(best2 & 0xffffu));
+        best_hi = max(best_hi, (int)(int16_t)(best2 >> 16));
+    }
+    if (MODE != IS_SEMI) {  // semi-global scores come from the border pass
+        if (p_lo >= 0) A.score[p_lo] = best_lo;
+        if (p_hi >= 0) A.score[p_hi] = best_hi;
+    }
+    if (MODE == IS_LOCAL && TRACED) {
+        if (p_lo >= 0) { A.start[2 * p_lo] = bidx_lo / (m_lo + 1); A.start[2 * p_lo + 1] = bidx_lo % (m_lo + 1); }
+        if (p_hi >= 0) { A.start[2 * p_hi] = bidx_hi / (m_hi + 1); A.start[2 * p_hi + 1] = bidx_hi % (m_hi + 1); }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
 // traceback over the nibbles: one thread per pair, first-priority steps only
 // (trace.rs:59-90 with max_number = 1; step order cell.rs:219-254)
+//
+// Semi-global (terminal_penalty = false): the reference drops the gap penalties in the last
+// row and column (pairwise.rs:794-843), values that only flow along that border to the end
+// cell.  With M(n, .) and M(., m) captured by the fill kernel the border is resolved here:
+//   G1(n, m) = max_{j<m} M(n, j),   G2(n, m) = max_{i<n} M(i, m),
+// the optimum is the first of M(n,m), G1(n,m), G2(n,m) attaining the maximum, and a start in
+// G1 (G2) walks the last row (column) back to the right-most (bottom-most) maximum, because
+// the reference prefers the M -> gap transition on ties (cell.rs:370-391).
+// Local: the walk starts at the first optimum in state M and carries the running score; it
+// ends at the first M state whose value is 0 (direction bits cleared, pairwise.rs:661-666).
 // ---------------------------------------------------------------------------------------
-__global__ void interseq_traceback_kernel(const WarpDesc *__restrict__ desc,
-                                          const int32_t *__restrict__ order,
-                                          const int64_t *__restrict__ off1,
-                                          const int64_t *__restrict__ off2,
-                                          const uint32_t *__restrict__ dirs, int64_t *__restrict__ trace_len,
+template <int MODE>
+__global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqArgs A,
+                                          const uint8_t *__restrict__ codes1,
+                                          const uint8_t *__restrict__ codes2, int64_t *__restrict__ trace_len,
                                           int32_t *__restrict__ first, uint8_t *__restrict__ ops,
                                           int64_t n_slots) {
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
-    const int32_t p = order[slot];
+    const int32_t p = A.order[slot];
     if (p < 0) return;
     const int64_t g = slot >> 6;
     const int lane = (int)(slot & 63) >> 1, half = (int)(slot & 1);
-    const WarpDesc d = desc[g];
-    const int n = (int)(off1[p + 1] - off1[p]), m = (int)(off2[p + 1] - off2[p]);
-    const uint32_t *base = dirs + d.dir_off + lane * 4 + half * 2;
-    uint8_t *out = ops + off1[p] + off2[p];
+    const WarpDesc d = A.desc[g];
+    const int64_t o1 = A.off1[p], o2 = A.off2[p];
+    const int n = (int)(A.off1[p + 1] - o1), m = (int)(A.off2[p + 1] - o2);
+    const bool traced = !C.score_only;
+    const uint32_t *base = A.dirs + d.dir_off + lane * 4 + half * 2;
+    uint8_t *out = ops + o1 + o2;
     auto nibble = [&](int i, int j) -> uint32_t {  // 1-based table cell (i, j)
         const int rg = i - 1, s = rg / IS_R, r = rg % IS_R;
         const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 128 + (r >> 3)];
@@ -335,27 +444,63 @@ __global__ void interseq_traceback_kernel(const WarpDesc *__restrict__ desc,
         const uint32_t nb = nibble(i, j);
         return (nb & 1u) ? ST_MATCH : ((nb & 2u) ? ST_GAP1 : ST_GAP2);
     };
-    int i = n, j = m, len = 0;
-    int st = h_state(i, j);
+    int i = n, j = m, len = 0, st = ST_MATCH;
     int fi = 0, fj = 0;
+    int32_t value = 0;
+    if (MODE == IS_GLOBAL) {
+        st = h_state(i, j);
+    } else if (MODE == IS_SEMI) {
+        const uint32_t *lr = A.lastrow + d.rowbuf_off * 2 + lane + (half ? (int64_t)d.mmax * 32 : 0);
+        const uint32_t *lc = A.lastcol + d.rowcode_off * 2 + lane + (half ? (int64_t)d.stripes * IS_R * 32 : 0);
+        auto m_row = [&](int jj) -> int { const uint32_t w = lr[(int64_t)(jj - 1) * 32]; return (int16_t)(half ? w >> 16 : w & 0xffffu); };
+        auto m_col = [&](int ii) -> int { const uint32_t w = lc[(int64_t)(ii - 1) * 32]; return (int16_t)(half ? w >> 16 : w & 0xffffu); };
+        const int mc = m_row(m);
+        int g1 = C.neg, p1 = 0, g2 = C.neg, p2 = 0;
+        for (int jj = 1; jj < m; jj++) { const int v = m_row(jj); if (v >= g1) { g1 = v; p1 = jj; } }
+        for (int ii = 1; ii < n; ii++) { const int v = m_col(ii); if (v >= g2) { g2 = v; p2 = ii; } }
+        const int best = max(mc, max(g1, g2));
+        A.score[p] = best;
+        if (traced) {
+            fi = n; fj = m;
+            if (mc == best) { st = ST_MATCH; }
+            else if (g1 == best) { while (j > p1) { fi = i; fj = j; out[len++] = OP_TO1; j--; } st = ST_MATCH; }
+            else { while (i > p2) { fi = i; fj = j; out[len++] = OP_TO2; i--; } st = ST_MATCH; }
+        }
+    } else {
+        i = A.start[2 * p]; j = A.start[2 * p + 1];
+        value = A.score[p];
+    }
+    if (!traced) return;
+    const int32_t *mat = A.matrix;
     while (i > 0 || j > 0) {
-        fi = i; fj = j;
-        if (i == 0) { out[len++] = OP_TO1; j--; continue; }   // first row: leading gap in sequence 1
-        if (j == 0) { out[len++] = OP_TO2; i--; continue; }   // first column
+        if (MODE == IS_LOCAL && (i == 0 || j == 0)) break;         // boundary cells have no direction
+        if (i == 0) { fi = i; fj = j; out[len++] = OP_TO1; j--; continue; }   // first row: leading gap in sequence 1
+        if (j == 0) { fi = i; fj = j; out[len++] = OP_TO2; i--; continue; }   // first column
         if (st == ST_MATCH) {
+            if (MODE == IS_LOCAL) {
+                if (value <= 0) break;                              // M clamped to 0: trace ends before this cell
+                value -= mat[(int)codes1[o1 + i - 1] * C.n_cols + (int)codes2[o2 + j - 1]];
+            }
+            fi = i; fj = j;
             out[len++] = OP_DIAG;
             i--; j--;
             st = h_state(i, j);
         } else if (st == ST_GAP1) {
             const uint32_t nb = nibble(i, j);
+            fi = i; fj = j;
             out[len++] = OP_TO1;
             j--;
-            st = (nb & 4u) ? ST_MATCH : ST_GAP1;
+            const bool opened = (nb & 4u) != 0;
+            st = opened ? ST_MATCH : ST_GAP1;
+            if (MODE == IS_LOCAL) value -= opened ? C.gap_open : C.gap_ext;
         } else {
             const uint32_t nb = nibble(i, j);
+            fi = i; fj = j;
             out[len++] = OP_TO2;
             i--;
-            st = (nb & 8u) ? ST_MATCH : ST_GAP2;
+            const bool opened = (nb & 8u) != 0;
+            st = opened ? ST_MATCH : ST_GAP2;
+            if (MODE == IS_LOCAL) value -= opened ? C.gap_open : C.gap_ext;
         }
     }
     trace_len[p] = len;
@@ -443,6 +588,7 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const std::ve
     plan.C.gap_open = P.gap_open; plan.C.gap_ext = P.gap_ext;
     plan.C.neg = -32768 - P.gap_open - P.gap_ext - std::min(min_score, 0);
     plan.C.n_rows = P.n_rows; plan.C.n_cols = P.n_cols; plan.C.score_only = score_only;
+    plan.C.mode = P.local ? IS_LOCAL : (P.terminal_penalty ? IS_GLOBAL : IS_SEMI);
 
     const int64_t per_window = interseq_pairs_per_window(n_pairs, waves_per_window);
     const int64_t n_windows = (n_pairs + per_window - 1) / per_window;
@@ -493,6 +639,10 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const std::ve
         if ((e = b.colcodes.alloc((size_t)plan.max_colcodes * 2)) != cudaSuccess) goto fail;
         if ((e = b.rowbuf.alloc((size_t)plan.max_rowbuf * 12)) != cudaSuccess) goto fail;
         if ((e = b.dirs.alloc((size_t)plan.max_dir_words * 4)) != cudaSuccess) goto fail;
+        if (plan.C.mode == IS_SEMI) {
+            if ((e = b.lastrow.alloc((size_t)plan.max_rowbuf * 8)) != cudaSuccess) goto fail;
+            if ((e = b.lastcol.alloc((size_t)plan.max_rowcodes * 8)) != cudaSuccess) goto fail;
+        }
     }
     if ((e = cudaMemcpyAsync(plan.d_order.ptr, plan.order.data(), plan.order.size() * 4, cudaMemcpyHostToDevice, stream)) != cudaSuccess) goto fail;
     if ((e = cudaMemcpyAsync(plan.d_desc.ptr, plan.desc.data(), plan.desc.size() * sizeof(WarpDesc), cudaMemcpyHostToDevice, stream)) != cudaSuccess) goto fail;
@@ -502,46 +652,76 @@ fail:
     return e == cudaErrorMemoryAllocation ? BT_ERR_OOM : BT_ERR_CUDA;
 }
 
+inline InterseqArgs interseq_args(InterseqPlan &plan, const Window &win, int slot, const InterseqIO &io) {
+    SlotBuffers &b = plan.slots[slot];
+    InterseqArgs A{};
+    A.desc = plan.d_desc.as<WarpDesc>() + win.group_begin;
+    A.order = plan.d_order.as<int32_t>() + win.group_begin * 64;
+    A.off1 = io.off1; A.off2 = io.off2; A.matrix = io.matrix;
+    A.rowcodes = b.rowcodes.as<uint16_t>(); A.colcodes = b.colcodes.as<uint16_t>();
+    A.rowbuf = b.rowbuf.as<uint32_t>(); A.lastrow = b.lastrow.as<uint32_t>(); A.lastcol = b.lastcol.as<uint32_t>();
+    A.dirs = b.dirs.as<uint32_t>();
+    A.score = io.score; A.start = io.start;
+    A.n_groups = win.group_end - win.group_begin;
+    return A;
+}
+
+template <int MODE, bool TRACED>
+inline cudaError_t interseq_launch_fill(const InterseqConst &C, const InterseqArgs &A, unsigned grid, size_t smem,
+                                        cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(interseq_fill_kernel<MODE, TRACED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    interseq_fill_kernel<MODE, TRACED><<<grid, IS_THREADS, smem, stream>>>(C, A);
+    return cudaGetLastError();
+}
+
 // pack + fill of one window into the scratch of `slot`
 inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, int slot, const InterseqIO &io,
                                         cudaStream_t stream, int64_t *launches) {
-    SlotBuffers &b = plan.slots[slot];
-    const int64_t groups = win.group_end - win.group_begin;
-    const int32_t *order = plan.d_order.as<int32_t>() + win.group_begin * 64;
-    const WarpDesc *desc = plan.d_desc.as<WarpDesc>() + win.group_begin;
+    const InterseqArgs A = interseq_args(plan, win, slot, io);
+    const int64_t groups = A.n_groups;
     interseq_pack_kernel<<<(unsigned)groups, 256, 0, stream>>>(
-        (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.off1, io.off2, order, desc,
-        b.rowcodes.as<uint16_t>(), b.colcodes.as<uint16_t>(), groups);
+        (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.off1, io.off2, A.order, A.desc,
+        plan.slots[slot].rowcodes.as<uint16_t>(), plan.slots[slot].colcodes.as<uint16_t>(), groups);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     (*launches)++;
     const size_t smem = (size_t)plan.C.n_rows * plan.C.n_cols * IS_ROWW;
     const unsigned grid = (unsigned)((groups + IS_THREADS / 32 - 1) / (IS_THREADS / 32));
-    if (plan.C.score_only) {
-        e = cudaFuncSetAttribute(interseq_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        interseq_fill_kernel<false><<<grid, IS_THREADS, smem, stream>>>(
-            plan.C, desc, order, io.off1, io.off2, io.matrix, b.rowcodes.as<uint16_t>(), b.colcodes.as<uint16_t>(),
-            b.rowbuf.as<uint32_t>(), b.dirs.as<uint32_t>(), io.score, groups);
-    } else {
-        e = cudaFuncSetAttribute(interseq_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        interseq_fill_kernel<true><<<grid, IS_THREADS, smem, stream>>>(
-            plan.C, desc, order, io.off1, io.off2, io.matrix, b.rowcodes.as<uint16_t>(), b.colcodes.as<uint16_t>(),
-            b.rowbuf.as<uint32_t>(), b.dirs.as<uint32_t>(), io.score, groups);
+    const bool traced = !plan.C.score_only;
+    switch (plan.C.mode) {
+    case IS_GLOBAL:
+        e = traced ? interseq_launch_fill<IS_GLOBAL, true>(plan.C, A, grid, smem, stream)
+                   : interseq_launch_fill<IS_GLOBAL, false>(plan.C, A, grid, smem, stream);
+        break;
+    case IS_SEMI:
+        e = traced ? interseq_launch_fill<IS_SEMI, true>(plan.C, A, grid, smem, stream)
+                   : interseq_launch_fill<IS_SEMI, false>(plan.C, A, grid, smem, stream);
+        break;
+    default:
+        e = traced ? interseq_launch_fill<IS_LOCAL, true>(plan.C, A, grid, smem, stream)
+                   : interseq_launch_fill<IS_LOCAL, false>(plan.C, A, grid, smem, stream);
+        break;
     }
-    e = cudaGetLastError();
     if (e == cudaSuccess) (*launches)++;
     return e;
 }
 
 inline cudaError_t interseq_traceback_window(InterseqPlan &plan, const Window &win, int slot,
                                              const InterseqIO &io, cudaStream_t stream, int64_t *launches) {
-    if (plan.C.score_only) return cudaSuccess;
-    const int64_t slots = (win.group_end - win.group_begin) * 64;
-    interseq_traceback_kernel<<<(unsigned)((slots + 127) / 128), 128, 0, stream>>>(
-        plan.d_desc.as<WarpDesc>() + win.group_begin, plan.d_order.as<int32_t>() + win.group_begin * 64, io.off1,
-        io.off2, plan.slots[slot].dirs.as<uint32_t>(), io.trace_len, io.first, io.ops, slots);
+    // semi-global scores are produced by the border pass even when no trace is wanted
+    if (plan.C.score_only && plan.C.mode != IS_SEMI) return cudaSuccess;
+    const InterseqArgs A = interseq_args(plan, win, slot, io);
+    const int64_t slots = A.n_groups * 64;
+    const unsigned grid = (unsigned)((slots + 127) / 128);
+    const uint8_t *c1 = (const uint8_t *)io.codes1, *c2 = (const uint8_t *)io.codes2;
+    if (plan.C.mode == IS_GLOBAL)
+        interseq_traceback_kernel<IS_GLOBAL><<<grid, 128, 0, stream>>>(plan.C, A, c1, c2, io.trace_len, io.first, io.ops, slots);
+    else if (plan.C.mode == IS_SEMI)
+        interseq_traceback_kernel<IS_SEMI><<<grid, 128, 0, stream>>>(plan.C, A, c1, c2, io.trace_len, io.first, io.ops, slots);
+    else
+        interseq_traceback_kernel<IS_LOCAL><<<grid, 128, 0, stream>>>(plan.C, A, c1, c2, io.trace_len, io.first, io.ops, slots);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) (*launches)++;
     return e;

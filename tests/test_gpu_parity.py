@@ -304,6 +304,38 @@ def test_batch_matches_oracle(gap, local, term):
         np.array_equal(a, b) for a, b in zip(one.traces(), traces))
 
 
+@pytest.mark.parametrize("local,term", [(False, True), (False, False), (True, True)])
+@pytest.mark.parametrize("gap", [(-10, -1), (-12, -2), (-6, -6)])
+def test_batch_protein_300aa_all_modes(local, term, gap):
+    """Config-2/3/5 shaped pairs (200-400 aa, half homologous) through the packed kernels,
+    every score and trace against the oracle; score-only variants too."""
+    rng = np.random.default_rng(7)
+    n_pairs = 2500
+    codes1, off1, codes2, off2 = _random_batch(rng, n_pairs, 200, 400)
+    for k in range(0, n_pairs, 2):
+        n = min(off1[k + 1] - off1[k], off2[k + 1] - off2[k])
+        shift = int(rng.integers(0, 30))
+        n = n - shift
+        codes2[off2[k] + shift:off2[k] + shift + n] = codes1[off1[k]:off1[k] + n]
+        flip = rng.random(n) < 0.2
+        codes2[off2[k] + shift:off2[k] + shift + n][flip] = rng.integers(0, 20, int(flip.sum()))
+    matrix = BLOSUM().score_matrix()
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, gap, term, local) as batch:
+        assert batch.kernel == "interseq_s16x2"
+        batch.run()
+        res = batch.fetch()
+    ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, matrix, gap, term, local)
+    assert np.array_equal(res.scores, ref_scores)
+    traces = res.traces()
+    for k in range(n_pairs):
+        assert np.array_equal(traces[k], ref_traces[k]), k
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, gap, term, local, score_only=True) as batch:
+        batch.run()
+        assert np.array_equal(batch.fetch().scores, ref_scores)
+    one = bt.align_batch_arrays(codes1, off1, codes2, off2, matrix, gap, term, local, score_only=True)
+    assert np.array_equal(one.scores, ref_scores)
+
+
 def test_batch_c2_shape_properties():
     """BASELINE config 2 shape (global affine BLOSUM62, ~300 aa) at a size the
     oracle cannot check exhaustively: re-score every trace instead."""
