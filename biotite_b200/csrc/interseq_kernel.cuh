@@ -27,6 +27,8 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -111,6 +113,27 @@ inline bool interseq_eligible(const BtParams &P, const std::vector<int64_t> &off
         const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
         if (n < 1 || m < 1 || n > IS_MAX_LEN || m > IS_MAX_LEN) return false;
         nmax = std::max(nmax, n); mmax = std::max(mmax, m);
+    }
+    // Routing by a simple cost model: the packed kernel runs one group of 64 pairs per warp,
+    // so a batch with few groups leaves most of the chip idle; the general kernel runs one
+    // block per pair and is bound by ~1.2 us per anti-diagonal.  Measured rates on B200:
+    // ~1.0e9 cells/s per resident warp (1776 warps) for the packed kernel, ~9e10 cells/s for a
+    // full grid of the general kernel.
+    // B200ALIGN_ROUTE=packed|general overrides the cost model (tests exercise both routes on the
+    // same inputs); the exactness conditions below always apply.
+    const char *forced = getenv("B200ALIGN_ROUTE");
+    if (forced && strcmp(forced, "general") == 0) return false;
+    if (!(forced && strcmp(forced, "packed") == 0)) {
+        double total = 0.0, max_pair = 0.0, max_diag = 0.0;
+        for (int64_t k = 0; k < n_pairs; k++) {
+            const double n = (double)(off1[k + 1] - off1[k]), m = (double)(off2[k + 1] - off2[k]);
+            total += n * m; max_pair = std::max(max_pair, n * m); max_diag = std::max(max_diag, n + m);
+        }
+        const double groups = (double)((n_pairs + 63) / 64);
+        const double t_packed = std::max(64.0 * max_pair / 1.0e9, total / 1.8e12) * (groups > 1776.0 ? 1.0 : 1.0);
+        const double waves = std::ceil((double)n_pairs / 888.0);
+        const double t_general = std::max(total / 9.0e10, max_diag * 1.2e-6 * waves);
+        if (t_general < t_packed) return false;
     }
     const int64_t open = P.gap_open, ext = P.gap_ext;
     const int64_t mn = std::min<int64_t>(min_score, 0), mx = std::max<int64_t>(max_score, 0);

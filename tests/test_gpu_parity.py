@@ -20,6 +20,13 @@ from tests.util import (
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=["packed", "general"])
+def route(request, monkeypatch):
+    """Run a batch test once per kernel family (B200ALIGN_ROUTE overrides the cost model)."""
+    monkeypatch.setenv("B200ALIGN_ROUTE", request.param)
+    return request.param
+
 NUC = bt.SubstitutionMatrix.std_nucleotide_matrix
 BLOSUM = bt.SubstitutionMatrix.std_protein_matrix
 
@@ -275,7 +282,7 @@ def _random_batch(rng, n_pairs, lo, hi, alphabet=20):
 
 @pytest.mark.parametrize("gap", [(-10, -1), -10, (-4, -4), (-11, 0)])
 @pytest.mark.parametrize("local,term", [(False, True), (False, False), (True, True)])
-def test_batch_matches_oracle(gap, local, term):
+def test_batch_matches_oracle(gap, local, term, route):
     rng = np.random.default_rng(42)
     codes1, off1, codes2, off2 = _random_batch(rng, 300, 1, 200)
     matrix = BLOSUM().score_matrix()
@@ -306,9 +313,10 @@ def test_batch_matches_oracle(gap, local, term):
 
 @pytest.mark.parametrize("local,term", [(False, True), (False, False), (True, True)])
 @pytest.mark.parametrize("gap", [(-10, -1), (-12, -2), (-6, -6)])
-def test_batch_protein_300aa_all_modes(local, term, gap):
+def test_batch_protein_300aa_all_modes(local, term, gap, monkeypatch):
     """Config-2/3/5 shaped pairs (200-400 aa, half homologous) through the packed kernels,
     every score and trace against the oracle; score-only variants too."""
+    monkeypatch.setenv("B200ALIGN_ROUTE", "packed")
     rng = np.random.default_rng(7)
     n_pairs = 2500
     codes1, off1, codes2, off2 = _random_batch(rng, n_pairs, 200, 400)
@@ -371,6 +379,17 @@ def test_batch_c2_shape_properties():
         t, s = oracle.align_optimal(codes1[off1[k]:off1[k + 1]], codes2[off2[k]:off2[k + 1]],
                                     matrix, (-10, -1), True, False, False, 1)
         assert s == res.scores[k] and np.array_equal(t[0], res.trace(k))
+
+
+def test_cost_model_routes_small_batches_to_general():
+    rng = np.random.default_rng(5)
+    matrix = BLOSUM().score_matrix()
+    codes1, off1, codes2, off2 = _random_batch(rng, 256, 1000, 1400)
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, (-10, -1), True, False, score_only=True) as b:
+        assert b.kernel == "general_i32"
+    codes1, off1, codes2, off2 = _random_batch(rng, 40000, 200, 300)
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, (-10, -1), True, False, score_only=True) as b:
+        assert b.kernel == "interseq_s16x2"
 
 
 def test_pipelined_windows_match_resident_batch():
