@@ -60,6 +60,7 @@ struct InterseqConst {
     int32_t n_rows, n_cols;
     int32_t score_only;
     int32_t mode;                    // IS_GLOBAL / IS_SEMI / IS_LOCAL
+    int32_t affine;                  // 0: linear gap penalty (gap_open)
 };
 
 // A window is a run of consecutive pairs (in input order) that is sorted, packed, filled and
@@ -105,7 +106,8 @@ struct InterseqIO {
 inline bool interseq_eligible(const BtParams &P, const std::vector<int64_t> &off1,
                               const std::vector<int64_t> &off2, int64_t n_pairs, int32_t min_score,
                               int32_t max_score) {
-    if (!P.affine || P.banded || !P.use_matrix) return false;
+    if (P.banded || !P.use_matrix) return false;
+    if (!P.affine && !P.local && !P.terminal_penalty) return false;  // linear semi-global: general kernel
     if (P.code_bytes != 1 || n_pairs < 64) return false;
     if ((int64_t)P.n_rows * P.n_cols * IS_ROWW > 96 * 1024 || P.n_rows > 255 || P.n_cols > 255) return false;
     int64_t nmax = 0, mmax = 0;
@@ -135,7 +137,7 @@ inline bool interseq_eligible(const BtParams &P, const std::vector<int64_t> &off
         const double t_general = std::max(total / 9.0e10, max_diag * 1.2e-6 * waves);
         if (t_general < t_packed) return false;
     }
-    const int64_t open = P.gap_open, ext = P.gap_ext;
+    const int64_t open = P.gap_open, ext = P.affine ? P.gap_ext : P.gap_open;
     const int64_t mn = std::min<int64_t>(min_score, 0), mx = std::max<int64_t>(max_score, 0);
     const int64_t neg = -32768 - open - ext - mn;                         // one open/ext and one sim may be added
     const int64_t lowest = 3 * open + (nmax + mmax + 2 + IS_R) * ext + 2 * mn;  // lowest finite value
@@ -532,6 +534,197 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
 }
 
 // ---------------------------------------------------------------------------------------
+// linear gap penalty (reference: pairwise.rs:378-415): one state per cell,
+//     S = max(S(i-1,j-1) + sim, S(i,j-1) + g, S(i-1,j) + g),
+// first-priority step Diag, then To1 (left), then To2 (up) (cell.rs:125-138, :291-323).
+// Two predicates per cell: d = [diag >= max(left, up) + g], l = [left >= up].
+// IS_GLOBAL (terminal gaps penalised) and IS_LOCAL; semi-global linear batches use the
+// general kernel.  Same mapping, buffers and row software-pipelining as the affine kernel;
+// the row buffer has one plane (S of the stripe's last row) and there is no -inf state.
+// ---------------------------------------------------------------------------------------
+template <int MODE, bool TRACED>
+__global__ void __launch_bounds__(IS_THREADS, 3)
+interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
+    extern __shared__ uint32_t table[];
+    const int lane = threadIdx.x & 31;
+    {
+        const int entries = C.n_rows * C.n_cols;
+        for (int e = threadIdx.x >> 5; e < entries; e += IS_THREADS / 32) {
+            const int a = e / C.n_cols, b = e % C.n_cols;
+            table[(b * C.n_rows + a) * 32 + lane] = (uint32_t)A.matrix[e] & 0xffffu;
+        }
+    }
+    __syncthreads();
+    const int64_t g = (int64_t)blockIdx.x * (IS_THREADS / 32) + (threadIdx.x >> 5);
+    if (g >= A.n_groups) return;
+    const WarpDesc d = A.desc[g];
+    const int32_t p_lo = A.order[g * 64 + 2 * lane], p_hi = A.order[g * 64 + 2 * lane + 1];
+    int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
+    if (p_lo >= 0) { n_lo = (int)(A.off1[p_lo + 1] - A.off1[p_lo]); m_lo = (int)(A.off2[p_lo + 1] - A.off2[p_lo]); }
+    if (p_hi >= 0) { n_hi = (int)(A.off1[p_hi + 1] - A.off1[p_hi]); m_hi = (int)(A.off2[p_hi + 1] - A.off2[p_hi]); }
+
+    const uint32_t gap2 = ((uint32_t)C.gap_open & 0xffffu) * 0x10001u;
+    const uint32_t col_stride = (uint32_t)C.n_rows * IS_ROWW;
+    const char *tbase = (const char *)table + lane * 4;
+    const uint16_t *rc = A.rowcodes + d.rowcode_off + lane;
+    const uint16_t *cc = A.colcodes + d.colcode_off + lane;
+    uint32_t *rb_s = A.rowbuf + d.rowbuf_off * 3 + lane;
+    uint2 *dir = TRACED ? (uint2 *)(A.dirs + d.dir_off) + lane : nullptr;
+
+    int32_t best_lo = 0, best_hi = 0, bidx_lo = 0, bidx_hi = 0;
+    uint32_t best2 = 0;
+    for (int s = 0; s < d.stripes; s++) {
+        const int r0 = s * IS_R;
+        const int j_lo = (n_lo - 1) / IS_R == s ? m_lo - 1 : -1;
+        const int j_hi = (n_hi - 1) / IS_R == s ? m_hi - 1 : -1;
+        const bool rows_valid = r0 + IS_R <= n_lo && r0 + IS_R <= n_hi;
+        uint32_t rp_lo[IS_R], rp_hi[IS_R], Sl[IS_R];
+#pragma unroll
+        for (int r = 0; r < IS_R; r++) {
+            const uint32_t v = rc[(int64_t)(r0 + r) * 32];
+            rp_lo[r] = (v & 0xffu) * IS_ROWW;
+            rp_hi[r] = (v >> 8) * IS_ROWW;
+            // column 0 (pairwise.rs:434-450): S(i, 0) = i * g, local 0
+            Sl[r] = MODE == IS_GLOBAL ? ((uint32_t)((r0 + r + 1) * C.gap_open) & 0xffffu) * 0x10001u : 0u;
+        }
+        uint32_t hu_prev = MODE == IS_GLOBAL ? ((uint32_t)(r0 * C.gap_open) & 0xffffu) * 0x10001u : 0u;  // S(r0, 0)
+        uint32_t s_row0 = MODE == IS_GLOBAL ? gap2 : 0u;  // S(0, j) = j * g (pairwise.rs:452-467)
+        uint32_t nxt = cc[0];
+        uint32_t nx_s = 0;
+        if (s > 0) nx_s = rb_s[0];
+        for (int j = 0; j < d.mmax; j++) {
+            const uint32_t v = nxt;
+            uint32_t up = nx_s;
+            if (j + 1 < d.mmax) {
+                nxt = cc[(int64_t)(j + 1) * 32];
+                if (s > 0) nx_s = rb_s[(int64_t)(j + 1) * 32];
+            }
+            const char *t_lo = tbase + (v & 0xffu) * col_stride;
+            const char *t_hi = tbase + (v >> 8) * col_stride;
+            if (s == 0) {
+                up = s_row0;
+                if (MODE == IS_GLOBAL) s_row0 = __vadd2(s_row0, gap2);
+            }
+            uint32_t acc[2] = {0, 0};  // 2 bits per row: low pair, high pair
+            uint32_t a[IS_R];
+            // diagonal candidates first: they read the previous column's S before it is replaced
+#pragma unroll
+            for (int r = 0; r < IS_R; r++) {
+                const uint32_t s_lo = *(const uint32_t *)(t_lo + rp_lo[r]);
+                const uint32_t s_hi = *(const uint32_t *)(t_hi + rp_hi[r]);
+                a[r] = __vadd2(r == 0 ? hu_prev : Sl[r - 1], s_hi * 65536u + s_lo);
+            }
+            hu_prev = up;
+#pragma unroll
+            for (int r = 0; r < IS_R; r++) {
+                uint32_t t, sc;
+                if (TRACED) {
+                    BT_MAX_PRED(t, Sl[r], up, acc[0], acc[1], 2u << (2 * r));       // left >= up
+                    const uint32_t tg = __vadd2(t, gap2);
+                    BT_MAX_PRED(sc, a[r], tg, acc[0], acc[1], 1u << (2 * r));       // diag >= gap
+                } else {
+                    sc = __viaddmax_s16x2(__vmaxs2(Sl[r], up), gap2, a[r]);
+                }
+                if (MODE == IS_LOCAL) sc = __vmaxs2(sc, 0u);  // pairwise.rs:410-413
+                Sl[r] = sc;
+                up = sc;
+            }
+            if (s + 1 < d.stripes) rb_s[(int64_t)j * 32] = up;
+            if (TRACED) dir[((int64_t)s * d.mmax + j) * 32] = make_uint2(acc[0], acc[1]);
+            if (MODE == IS_GLOBAL) {
+                if (j == j_lo || j == j_hi) {
+#pragma unroll
+                    for (int r = 0; r < IS_R; r++) {
+                        if (j == j_lo && r0 + r + 1 == n_lo) best_lo = (int16_t)(Sl[r] & 0xffffu);
+                        if (j == j_hi && r0 + r + 1 == n_hi) best_hi = (int16_t)(Sl[r] >> 16);
+                    }
+                }
+            } else {
+                uint32_t cm = Sl[0];
+#pragma unroll
+                for (int r = 1; r < IS_R; r++) cm = __vmaxs2(cm, Sl[r]);
+                const bool inside = rows_valid && j < m_lo && j < m_hi;
+                bool slow = !inside;
+                if (inside) {
+                    if (!TRACED) best2 = __vmaxs2(best2, cm);
+                    else {
+                        const int c_lo = (int16_t)(cm & 0xffffu), c_hi = (int16_t)(cm >> 16);
+                        slow = (c_lo >= best_lo && c_lo > 0) || (c_hi >= best_hi && c_hi > 0);
+                    }
+                }
+                if (slow) {
+#pragma unroll
+                    for (int r = 0; r < IS_R; r++) {
+                        const int row = r0 + r + 1, col = j + 1;
+                        const int v_lo = (int16_t)(Sl[r] & 0xffffu), v_hi = (int16_t)(Sl[r] >> 16);
+                        if (row <= n_lo && col <= m_lo) {
+                            const int idx = row * (m_lo + 1) + col;
+                            if (v_lo > best_lo || (v_lo == best_lo && v_lo > 0 && idx < bidx_lo)) { best_lo = v_lo; bidx_lo = idx; }
+                        }
+                        if (row <= n_hi && col <= m_hi) {
+                            const int idx = row * (m_hi + 1) + col;
+                            if (v_hi > best_hi || (v_hi == best_hi && v_hi > 0 && idx < bidx_hi)) { best_hi = v_hi; bidx_hi = idx; }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == IS_LOCAL && !TRACED) {
+        best_lo = max(best_lo, (int)(int16_t)(best2 & 0xffffu));
+        best_hi = max(best_hi, (int)(int16_t)(best2 >> 16));
+    }
+    if (p_lo >= 0) A.score[p_lo] = best_lo;
+    if (p_hi >= 0) A.score[p_hi] = best_hi;
+    if (MODE == IS_LOCAL && TRACED) {
+        if (p_lo >= 0) { A.start[2 * p_lo] = bidx_lo / (m_lo + 1); A.start[2 * p_lo + 1] = bidx_lo % (m_lo + 1); }
+        if (p_hi >= 0) { A.start[2 * p_hi] = bidx_hi / (m_hi + 1); A.start[2 * p_hi + 1] = bidx_hi % (m_hi + 1); }
+    }
+}
+
+template <int MODE>
+__global__ void interseq_linear_traceback_kernel(const InterseqConst C, const InterseqArgs A,
+                                                 const uint8_t *__restrict__ codes1,
+                                                 const uint8_t *__restrict__ codes2,
+                                                 int64_t *__restrict__ trace_len, int32_t *__restrict__ first,
+                                                 uint8_t *__restrict__ ops, int64_t n_slots) {
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const int32_t p = A.order[slot];
+    if (p < 0) return;
+    const int64_t g = slot >> 6;
+    const int lane = (int)(slot & 63) >> 1, half = (int)(slot & 1);
+    const WarpDesc d = A.desc[g];
+    const int64_t o1 = A.off1[p], o2 = A.off2[p];
+    const int n = (int)(A.off1[p + 1] - o1), m = (int)(A.off2[p + 1] - o2);
+    const uint32_t *base = A.dirs + d.dir_off + lane * 2 + half;
+    uint8_t *out = ops + o1 + o2;
+    int i = n, j = m, len = 0, fi = 0, fj = 0;
+    int32_t value = 0;
+    if (MODE == IS_LOCAL) { i = A.start[2 * p]; j = A.start[2 * p + 1]; value = A.score[p]; }
+    while (i > 0 || j > 0) {
+        if (MODE == IS_LOCAL && (i == 0 || j == 0 || value <= 0)) break;  // score <= 0: direction cleared
+        fi = i; fj = j;
+        if (i == 0) { out[len++] = OP_TO1; j--; continue; }
+        if (j == 0) { out[len++] = OP_TO2; i--; continue; }
+        const int rg = i - 1, s = rg / IS_R, r = rg % IS_R;
+        const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 64];
+        const uint32_t bits = (w >> (2 * r)) & 3u;
+        if (bits & 1u) {
+            if (MODE == IS_LOCAL) value -= A.matrix[(int)codes1[o1 + i - 1] * C.n_cols + (int)codes2[o2 + j - 1]];
+            out[len++] = OP_DIAG; i--; j--;
+        } else {
+            if (MODE == IS_LOCAL) value -= C.gap_open;
+            if (bits & 2u) { out[len++] = OP_TO1; j--; }
+            else { out[len++] = OP_TO2; i--; }
+        }
+    }
+    trace_len[p] = len;
+    first[2 * p] = fi;
+    first[2 * p + 1] = fj;
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 
@@ -563,7 +756,8 @@ struct WindowPlan {
 // index order and the tail of a window should consist of its cheapest groups - and lay out
 // the window's scratch.
 inline void interseq_plan_window(WindowPlan &wp, const std::vector<int64_t> &off1,
-                                 const std::vector<int64_t> &off2, int64_t w0, int64_t w1, int score_only) {
+                                 const std::vector<int64_t> &off2, int64_t w0, int64_t w1, int score_only,
+                                 int dir_words_per_lane) {
     const int64_t cnt = w1 - w0;
     std::vector<int32_t> tmp((size_t)cnt), sorted((size_t)cnt), count(IS_MAX_LEN + 2, 0);
     for (int64_t k = w0; k < w1; k++) count[(size_t)(off2[k + 1] - off2[k]) + 1]++;
@@ -595,7 +789,8 @@ inline void interseq_plan_window(WindowPlan &wp, const std::vector<int64_t> &off
         d.nmax = nmax; d.mmax = mmax; d.stripes = (nmax + IS_R - 1) / IS_R; d.pad = 0;
         d.dir_off = win.dir_words; d.rowbuf_off = win.rowbuf_entries;
         d.rowcode_off = win.rowcodes; d.colcode_off = win.colcodes;
-        if (!score_only) win.dir_words += (int64_t)d.stripes * mmax * 128;  // uint4 per lane, column, stripe
+        // affine: uint4 (4 bits x 16 rows x 2 pairs), linear: uint2, per lane, column and stripe
+        if (!score_only) win.dir_words += (int64_t)d.stripes * mmax * 32 * dir_words_per_lane;
         win.rowbuf_entries += (int64_t)mmax * 32;
         win.rowcodes += (int64_t)d.stripes * IS_R * 32;
         win.colcodes += (int64_t)mmax * 32;
@@ -608,8 +803,9 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const std::ve
                             int waves_per_window, cudaStream_t stream) {
     (void)max_score;
     plan.n_pairs = n_pairs;
-    plan.C.gap_open = P.gap_open; plan.C.gap_ext = P.gap_ext;
-    plan.C.neg = -32768 - P.gap_open - P.gap_ext - std::min(min_score, 0);
+    plan.C.gap_open = P.gap_open; plan.C.gap_ext = P.affine ? P.gap_ext : P.gap_open;
+    plan.C.affine = P.affine;
+    plan.C.neg = -32768 - plan.C.gap_open - plan.C.gap_ext - std::min(min_score, 0);
     plan.C.n_rows = P.n_rows; plan.C.n_cols = P.n_cols; plan.C.score_only = score_only;
     plan.C.mode = P.local ? IS_LOCAL : (P.terminal_penalty ? IS_GLOBAL : IS_SEMI);
 
@@ -626,7 +822,7 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const std::ve
                 const int64_t w = next.fetch_add(1);
                 if (w >= n_windows) break;
                 const int64_t w0 = w * per_window, w1 = std::min(n_pairs, w0 + per_window);
-                interseq_plan_window(wps[(size_t)w], off1, off2, w0, w1, score_only);
+                interseq_plan_window(wps[(size_t)w], off1, off2, w0, w1, score_only, P.affine ? 4 : 2);
             }
         };
         std::vector<std::thread> threads;
@@ -690,6 +886,16 @@ inline InterseqArgs interseq_args(InterseqPlan &plan, const Window &win, int slo
 }
 
 template <int MODE, bool TRACED>
+inline cudaError_t interseq_launch_linear_fill(const InterseqConst &C, const InterseqArgs &A, unsigned grid,
+                                               size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(interseq_linear_fill_kernel<MODE, TRACED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    interseq_linear_fill_kernel<MODE, TRACED><<<grid, IS_THREADS, smem, stream>>>(C, A);
+    return cudaGetLastError();
+}
+
+template <int MODE, bool TRACED>
 inline cudaError_t interseq_launch_fill(const InterseqConst &C, const InterseqArgs &A, unsigned grid, size_t smem,
                                         cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(interseq_fill_kernel<MODE, TRACED>,
@@ -713,6 +919,16 @@ inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, i
     const size_t smem = (size_t)plan.C.n_rows * plan.C.n_cols * IS_ROWW;
     const unsigned grid = (unsigned)((groups + IS_THREADS / 32 - 1) / (IS_THREADS / 32));
     const bool traced = !plan.C.score_only;
+    if (!plan.C.affine) {
+        if (plan.C.mode == IS_GLOBAL)
+            e = traced ? interseq_launch_linear_fill<IS_GLOBAL, true>(plan.C, A, grid, smem, stream)
+                       : interseq_launch_linear_fill<IS_GLOBAL, false>(plan.C, A, grid, smem, stream);
+        else
+            e = traced ? interseq_launch_linear_fill<IS_LOCAL, true>(plan.C, A, grid, smem, stream)
+                       : interseq_launch_linear_fill<IS_LOCAL, false>(plan.C, A, grid, smem, stream);
+        if (e == cudaSuccess) (*launches)++;
+        return e;
+    }
     switch (plan.C.mode) {
     case IS_GLOBAL:
         e = traced ? interseq_launch_fill<IS_GLOBAL, true>(plan.C, A, grid, smem, stream)
@@ -739,7 +955,12 @@ inline cudaError_t interseq_traceback_window(InterseqPlan &plan, const Window &w
     const int64_t slots = A.n_groups * 64;
     const unsigned grid = (unsigned)((slots + 127) / 128);
     const uint8_t *c1 = (const uint8_t *)io.codes1, *c2 = (const uint8_t *)io.codes2;
-    if (plan.C.mode == IS_GLOBAL)
+    if (!plan.C.affine) {
+        if (plan.C.mode == IS_GLOBAL)
+            interseq_linear_traceback_kernel<IS_GLOBAL><<<grid, 128, 0, stream>>>(plan.C, A, c1, c2, io.trace_len, io.first, io.ops, slots);
+        else
+            interseq_linear_traceback_kernel<IS_LOCAL><<<grid, 128, 0, stream>>>(plan.C, A, c1, c2, io.trace_len, io.first, io.ops, slots);
+    } else if (plan.C.mode == IS_GLOBAL)
         interseq_traceback_kernel<IS_GLOBAL><<<grid, 128, 0, stream>>>(plan.C, A, c1, c2, io.trace_len, io.first, io.ops, slots);
     else if (plan.C.mode == IS_SEMI)
         interseq_traceback_kernel<IS_SEMI><<<grid, 128, 0, stream>>>(plan.C, A, c1, c2, io.trace_len, io.first, io.ops, slots);

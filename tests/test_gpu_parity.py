@@ -312,7 +312,7 @@ def test_batch_matches_oracle(gap, local, term, route):
 
 
 @pytest.mark.parametrize("local,term", [(False, True), (False, False), (True, True)])
-@pytest.mark.parametrize("gap", [(-10, -1), (-12, -2), (-6, -6)])
+@pytest.mark.parametrize("gap", [(-10, -1), (-12, -2), (-6, -6), -10, -3])
 def test_batch_protein_300aa_all_modes(local, term, gap, monkeypatch):
     """Config-2/3/5 shaped pairs (200-400 aa, half homologous) through the packed kernels,
     every score and trace against the oracle; score-only variants too."""
@@ -328,8 +328,9 @@ def test_batch_protein_300aa_all_modes(local, term, gap, monkeypatch):
         flip = rng.random(n) < 0.2
         codes2[off2[k] + shift:off2[k] + shift + n][flip] = rng.integers(0, 20, int(flip.sum()))
     matrix = BLOSUM().score_matrix()
+    linear_semi = isinstance(gap, int) and not local and not term  # no packed kernel for this one
     with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, gap, term, local) as batch:
-        assert batch.kernel == "interseq_s16x2"
+        assert batch.kernel == ("general_i32" if linear_semi else "interseq_s16x2")
         batch.run()
         res = batch.fetch()
     ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, matrix, gap, term, local)

@@ -14,7 +14,11 @@ n_pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 500_000
 codes1, off1, codes2, off2 = bench.make_c2(n_pairs, 0)
 matrix = bt.SubstitutionMatrix.std_protein_matrix().score_matrix()
 rows = []
+GAPS = {"affine": (-10, -1), "linear": -10}
 for name, term, local, score_only in [
+    ("global linear, score+trace", True, False, False),
+    ("global linear, score only", True, False, True),
+    ("local linear, score only", True, True, True),
     ("global affine, score+trace (C2)", True, False, False),
     ("global affine, score only", True, False, True),
     ("semi-global affine, score+trace (C5 shape)", False, False, False),
@@ -22,7 +26,7 @@ for name, term, local, score_only in [
     ("local affine, score only (C3 shape)", True, True, True),
     ("local affine, score+trace", True, True, False),
 ]:
-    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, (-10, -1), term, local, None, score_only) as b:
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, GAPS[name.split()[1].rstrip(',')], term, local, None, score_only) as b:
         for _ in range(2):
             b.run()
         ms = [b.run() for _ in range(3)]
