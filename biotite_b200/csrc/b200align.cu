@@ -22,6 +22,7 @@
 #include "general_kernel.cuh"
 #include "host_trace.hpp"
 #include "interseq_kernel.cuh"
+#include "banded_kernel.cuh"
 #include "microbench.cuh"
 
 using namespace bt;
@@ -113,7 +114,7 @@ static int32_t reference_neg_inf(const BtParams &P, int32_t min_score) {
 // ---------------------------------------------------------------------------------------
 // batch object
 // ---------------------------------------------------------------------------------------
-enum Route { ROUTE_GENERAL = 0, ROUTE_INTERSEQ = 1 };
+enum Route { ROUTE_GENERAL = 0, ROUTE_INTERSEQ = 1, ROUTE_BANDED = 2 };
 
 struct Chunk {
     int64_t begin, end;   // pair range
@@ -138,6 +139,7 @@ struct BtBatch {
     DevBuf codes1, codes2, off1, off2, bands, matrix, dir_off, cand_off, cand, dirs, gscratch;
     DevBuf score, start_idx, start_state, end_vals, trace_len, first, ops, flag, is_start;
     InterseqPlan interseq;  // state of the packed 16-bit route
+    BandedPlan banded;      // state of the banded inter-sequence route
     bool ran = false;
     // per-phase device timing: events[3k..3k+2] bracket fill and traceback of step k
     std::vector<cudaEvent_t> phase_events;
@@ -386,6 +388,8 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     b->route = ROUTE_GENERAL;
     if (!force_general && interseq_eligible(*params, b->h_off1, b->h_off2, n_pairs, mn, mx))
         b->route = ROUTE_INTERSEQ;
+    else if (!force_general && banded_eligible(*params, b->h_off1, b->h_off2, b->h_bands, n_pairs, mn, mx))
+        b->route = ROUTE_BANDED;
 
     const size_t cb = (size_t)params->code_bytes;
     CUDA_TRY(b->codes1.alloc((size_t)b->total1 * cb));
@@ -417,6 +421,13 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
                               &b->cells, 1, 3, s);
         if (st == BT_ERR_OOM) return fail(st, "out of device memory (inter-sequence plan)");
         if (st) return fail(st, "inter-sequence plan failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } else if (b->route == ROUTE_BANDED) {
+        CUDA_TRY(b->bands.alloc((size_t)n_pairs * 16));
+        CUDA_TRY(cudaMemcpyAsync(b->bands.ptr, bands, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, s));
+        st = banded_prepare(b->banded, *params, b->h_off1, b->h_off2, b->h_bands, n_pairs, b->score_only,
+                            &b->cells, s);
+        if (st == BT_ERR_OOM) return fail(st, "out of device memory (banded plan)");
+        if (st) return fail(st, "banded plan failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
         st = build_chunks(b.get());
         if (st) return st;
@@ -483,6 +494,19 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
                 if (e == cudaSuccess) e = b->mark_phase();
             }
             if (e != cudaSuccess) st = fail(BT_ERR_CUDA, "inter-sequence kernels: %s", cudaGetErrorString(e));
+        } else if (b->route == ROUTE_BANDED) {
+            BandedIO io{b->codes1.ptr, b->codes2.ptr, b->off1.as<int64_t>(), b->off2.as<int64_t>(),
+                        b->bands.as<int64_t>(), b->matrix.as<int32_t>(), b->score.as<int32_t>(),
+                        b->trace_len.as<int64_t>(), b->first.as<int32_t>(), b->ops.as<uint8_t>()};
+            cudaError_t e = cudaSuccess;
+            for (const BandWindow &win : b->banded.windows) {
+                if (e == cudaSuccess) e = b->mark_phase();
+                if (e == cudaSuccess) e = banded_fill_window(b->banded, win, io, b->stream, &b->launches);
+                if (e == cudaSuccess) e = b->mark_phase();
+                if (e == cudaSuccess) e = banded_traceback_window(b->banded, win, io, b->stream, &b->launches);
+                if (e == cudaSuccess) e = b->mark_phase();
+            }
+            if (e != cudaSuccess) st = fail(BT_ERR_CUDA, "banded kernels: %s", cudaGetErrorString(e));
         } else {
             st = run_general(b, true);
         }
@@ -539,7 +563,7 @@ extern "C" int64_t bt_batch_cells(const BtBatch *b) { return b ? b->cells : 0; }
 extern "C" int64_t bt_batch_launches(const BtBatch *b) { return b ? b->launches : 0; }
 extern "C" const char *bt_batch_kernel(const BtBatch *b) {
     if (!b) return "";
-    return b->route == ROUTE_INTERSEQ ? "interseq_s16x2" : "general_i32";
+    return b->route == ROUTE_INTERSEQ ? "interseq_s16x2" : (b->route == ROUTE_BANDED ? "banded_i32" : "general_i32");
 }
 extern "C" void bt_batch_destroy(BtBatch *b) { delete b; }
 

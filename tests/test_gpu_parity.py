@@ -414,7 +414,85 @@ def test_pipelined_windows_match_resident_batch():
         assert sc == one.scores[k] and np.array_equal(t[0], one.trace(k)) and np.array_equal(t[0], res.trace(k))
 
 
-def test_banded_batch_matches_oracle():
+@pytest.mark.parametrize("gap", [(-10, -1), (-3, -3), (-7, 0)])
+def test_banded_interseq_random_bands(gap, monkeypatch):
+    """The banded inter-sequence kernels on ragged inputs: tiny and unequal lengths, bands that
+    start left of / end right of the sequences, width-1 bands; every score and trace vs the
+    oracle (align_banded, semi-global, max_number=1)."""
+    monkeypatch.setenv("B200ALIGN_ROUTE", "packed")
+    from biotite_b200.banded import crop_band
+    rng = np.random.default_rng(17)
+    c1, c2, o1, o2, bands = [], [], [0], [0], []
+    while len(bands) < 300:
+        n = int(rng.integers(1, 130))
+        m = n + int(rng.integers(0, 90))
+        a = rng.integers(0, 4, n).astype(np.uint8)
+        b = rng.integers(0, 4, m).astype(np.uint8)
+        if rng.random() < 0.6:   # plant a shifted copy so that real alignments exist
+            shift = int(rng.integers(0, m - n + 1))
+            b[shift:shift + n] = a
+            flip = rng.random(m) < 0.1
+            b[flip] = rng.integers(0, 4, int(flip.sum()))
+        lo = int(rng.integers(-n - 5, m + 5))
+        hi = lo + int(rng.integers(0, 70))
+        try:
+            band = crop_band(n, m, (lo, hi))
+        except ValueError:
+            continue
+        c1.append(a); c2.append(b); o1.append(o1[-1] + n); o2.append(o2[-1] + m); bands.append(band)
+    codes1, codes2 = np.concatenate(c1), np.concatenate(c2)
+    off1, off2 = np.array(o1, dtype=np.int64), np.array(o2, dtype=np.int64)
+    bands = np.array(bands, dtype=np.int64)
+    matrix = NUC().score_matrix()
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, gap, True, False, bands) as batch:
+        assert batch.kernel == "banded_i32"
+        batch.run()
+        res = batch.fetch()
+    ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, matrix, gap, bands=bands)
+    assert np.array_equal(res.scores, ref_scores)
+    traces = res.traces()
+    for k in range(len(bands)):
+        assert np.array_equal(traces[k], ref_traces[k]), (k, bands[k], off1[k + 1] - off1[k], off2[k + 1] - off2[k])
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, gap, True, False, bands, score_only=True) as batch:
+        batch.run()
+        assert np.array_equal(batch.fetch().scores, ref_scores)
+
+
+def test_banded_interseq_c4_shape(monkeypatch):
+    """Config-4 shaped pairs (3 kb here, band +-64, NUC, affine) against the oracle."""
+    monkeypatch.setenv("B200ALIGN_ROUTE", "packed")
+    rng = np.random.default_rng(23)
+    c1, c2, o1, o2 = [], [], [0], [0]
+    for k in range(96):
+        L = int(rng.integers(2500, 3200))
+        a = rng.integers(0, 4, L).astype(np.uint8)
+        b = a.copy()
+        sub = rng.random(L) < 0.05
+        b[sub] = rng.integers(0, 4, int(sub.sum()))
+        b = b[rng.random(L) >= 0.006]
+        ins = np.sort(rng.choice(len(b), 15, replace=False))
+        b = np.insert(b, ins, rng.integers(0, 4, 15).astype(np.uint8))
+        if len(b) < len(a):
+            a, b = b, a
+        c1.append(a); c2.append(b); o1.append(o1[-1] + len(a)); o2.append(o2[-1] + len(b))
+    codes1, codes2 = np.concatenate(c1), np.concatenate(c2)
+    off1, off2 = np.array(o1, dtype=np.int64), np.array(o2, dtype=np.int64)
+    bands = np.array([bt.banded.crop_band(off1[k + 1] - off1[k], off2[k + 1] - off2[k], (-64, 64))
+                      for k in range(96)], dtype=np.int64)
+    matrix = NUC().score_matrix()
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, (-10, -1), True, False, bands) as batch:
+        assert batch.kernel == "banded_i32"
+        batch.run()
+        res = batch.fetch()
+    ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, matrix, (-10, -1), bands=bands)
+    assert np.array_equal(res.scores, ref_scores)
+    assert res.scores.max() > 10000   # beyond the packed 16-bit kernels' comfort zone
+    traces = res.traces()
+    for k in range(96):
+        assert np.array_equal(traces[k], ref_traces[k]), k
+
+
+def test_banded_batch_matches_oracle(route):
     rng = np.random.default_rng(3)
     n_pairs = 40
     seqs1, seqs2, bands = [], [], []
