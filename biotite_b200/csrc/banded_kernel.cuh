@@ -172,13 +172,18 @@ banded_fill_kernel(const BandConst C, const BandArgs A) {
         int32_t hu_prev, nx_m, nx_f, nx_h;
         { int32_t t0, t1; above(c_first - 1, t0, t1, hu_prev); }
         above(c_first, nx_m, nx_f, nx_h);
+        auto col_code = [&](int c) -> uint32_t {
+            const int sjc = min(max(base_j + c, 0), d.mmax - 1);
+            return cc[(int64_t)sjc * 32];
+        };
+        uint32_t nx_code = col_code(c_first);
         for (int c = c_first; c <= c_last; c++) {
             int32_t up_m = nx_m, up_f2 = nx_f;
             const int32_t hu = nx_h;
-            if (c < c_last) above(c + 1, nx_m, nx_f, nx_h);
+            const uint32_t code = nx_code;
+            if (c < c_last) { above(c + 1, nx_m, nx_f, nx_h); nx_code = col_code(c + 1); }   // one column ahead
             const int sj = base_j + c;
-            const int sjc = min(max(sj, 0), d.mmax - 1);
-            const char *t_col = tbase + (uint32_t)cc[(int64_t)sjc * 32] * col_stride;
+            const char *t_col = tbase + code * col_stride;
             uint32_t acc0 = 0, acc1 = 0;   // nibbles of rows 0-7 and 8-15
             int32_t sim[BD_R];
 #pragma unroll
