@@ -94,7 +94,7 @@ __global__ void banded_pack_kernel(const uint8_t *codes1, const uint8_t *codes2,
         : "r"(a), "r"(b), "r"(c))
 
 template <bool TRACED>
-__global__ void __launch_bounds__(BD_THREADS, 3)
+__global__ void __launch_bounds__(BD_THREADS, 4)
 banded_fill_kernel(const BandConst C, const BandArgs A) {
     extern __shared__ int32_t btable[];  // [b][a][lane], one private copy per lane (no bank conflicts)
     const int lane = threadIdx.x & 31;
