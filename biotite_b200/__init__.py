@@ -35,6 +35,8 @@ from .batch import (
     DeviceBatch,
     PackedSequences,
     align_batch_arrays,
+    align_indexed_batch,
+    all_vs_all_scores,
     align_banded_batch,
     align_optimal_batch,
     pack_sequences,

@@ -28,6 +28,8 @@ __all__ = [
     "DeviceBatch",
     "BatchResult",
     "align_batch_arrays",
+    "align_indexed_batch",
+    "all_vs_all_scores",
     "align_optimal_batch",
     "align_banded_batch",
 ]
@@ -81,7 +83,13 @@ class DeviceBatch:
     """
 
     def __init__(self, codes1, off1, codes2, off2, scoring, gap_penalty,
-                 terminal_penalty=True, local=False, bands=None, score_only=False):
+                 terminal_penalty=True, local=False, bands=None, score_only=False,
+                 idx1=None, idx2=None):
+        """
+        Without `idx1` / `idx2` pair ``k`` aligns sequence ``k`` of either side.  With them
+        the two sides are sequence *pools* and pair ``k`` aligns ``pool1[idx1[k]]`` with
+        ``pool2[idx2[k]]`` (one-vs-many searches, all-vs-all matrices).
+        """
         self._lib = _cabi.load()
         self._handle = None
         dtype = np.promote_types(codes1.dtype, codes2.dtype)
@@ -89,20 +97,41 @@ class DeviceBatch:
         self.codes2 = np.ascontiguousarray(codes2, dtype)
         self.off1 = np.ascontiguousarray(off1, dtype=np.int64)
         self.off2 = np.ascontiguousarray(off2, dtype=np.int64)
-        if len(self.off1) != len(self.off2):
-            raise ValueError("Both sides of the batch must hold the same number of sequences")
-        self.n_pairs = len(self.off1) - 1
+        self.idx1 = None if idx1 is None else np.ascontiguousarray(idx1, dtype=np.int32)
+        self.idx2 = None if idx2 is None else np.ascontiguousarray(idx2, dtype=np.int32)
+        if self.idx1 is None:
+            if len(self.off1) != len(self.off2):
+                raise ValueError("Both sides of the batch must hold the same number of sequences")
+            self.n_pairs = len(self.off1) - 1
+        else:
+            if self.idx2 is None or len(self.idx1) != len(self.idx2):
+                raise ValueError("idx1 and idx2 must have the same length")
+            self.n_pairs = len(self.idx1)
         self.bands = None if bands is None else np.ascontiguousarray(bands, dtype=np.int64)
         self.score_only = bool(score_only)
         self._params, self._matrix = _cabi.make_params(
             scoring, gap_penalty, terminal_penalty, local, bands is not None, dtype)
         handle = ctypes.c_void_p(None)
-        _cabi.check(self._lib.bt_batch_create(
-            ctypes.byref(self._params), _cabi.ptr(self.codes1), _cabi.ptr(self.off1),
-            _cabi.ptr(self.codes2), _cabi.ptr(self.off2), self.n_pairs,
-            _cabi.ptr(self._matrix), _cabi.ptr(self.bands), int(self.score_only),
-            ctypes.byref(handle)))
+        if self.idx1 is None:
+            _cabi.check(self._lib.bt_batch_create(
+                ctypes.byref(self._params), _cabi.ptr(self.codes1), _cabi.ptr(self.off1),
+                _cabi.ptr(self.codes2), _cabi.ptr(self.off2), self.n_pairs,
+                _cabi.ptr(self._matrix), _cabi.ptr(self.bands), int(self.score_only),
+                ctypes.byref(handle)))
+        else:
+            _cabi.check(self._lib.bt_batch_create_indexed(
+                ctypes.byref(self._params), _cabi.ptr(self.codes1), _cabi.ptr(self.off1),
+                len(self.off1) - 1, _cabi.ptr(self.codes2), _cabi.ptr(self.off2),
+                len(self.off2) - 1, _cabi.ptr(self.idx1), _cabi.ptr(self.idx2), self.n_pairs,
+                _cabi.ptr(self._matrix), _cabi.ptr(self.bands), int(self.score_only),
+                ctypes.byref(handle)))
         self._handle = handle
+
+    def _ops_offsets(self):
+        if self.idx1 is None:
+            return self.off1 + self.off2
+        lens = np.diff(self.off1)[self.idx1] + np.diff(self.off2)[self.idx2]
+        return np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.int64)
 
     @property
     def cells(self):
@@ -137,14 +166,14 @@ class DeviceBatch:
             if not self.score_only:
                 trace_len = np.empty(n, dtype=np.int64)
                 first = np.empty((n, 2), dtype=np.int32)
-                ops = np.empty(int(self.off1[-1] + self.off2[-1]), dtype=np.uint8)
+                ops = np.empty(int(self._lib.bt_batch_ops_bytes(self._handle)), dtype=np.uint8)
         else:
             scores, trace_len, first, ops = out
         _cabi.check(self._lib.bt_batch_fetch_scores(self._handle, _cabi.ptr(scores)))
         if not self.score_only:
             _cabi.check(self._lib.bt_batch_fetch_traces(
                 self._handle, _cabi.ptr(trace_len), _cabi.ptr(first), _cabi.ptr(ops)))
-        return BatchResult(scores, trace_len, first, ops, self.off1 + self.off2, self.bands)
+        return BatchResult(scores, trace_len, first, ops, self._ops_offsets(), self.bands)
 
     def close(self):
         if self._handle is not None:
@@ -284,6 +313,70 @@ class BatchResult:
             Alignment([self.seqs1[k], self.seqs2[k]], traces[k], int(self.scores[k]))
             for k in range(len(self.scores))
         ]
+
+
+def align_indexed_batch(pool1, pool2, idx1, idx2, matrix, gap_penalty=-10, terminal_penalty=True,
+                        local=False, score_only=False):
+    """
+    ``align_optimal(pool1[idx1[k]], pool2[idx2[k]], ..., max_number=1)`` for every ``k``
+    without materialising the pairs: the pools (lists of ``Sequence`` or
+    :class:`PackedSequences`) are uploaded once.  Returns a :class:`BatchResult`.
+    """
+    _check_gap_penalty(gap_penalty)
+    p1, p2 = pack_sequences(pool1), pack_sequences(pool2)
+    scoring = _resolve_scoring(matrix, p1, p2)
+    with DeviceBatch(p1.codes, p1.offsets, p2.codes, p2.offsets, scoring, gap_penalty,
+                     terminal_penalty, local, None, score_only, idx1=idx1, idx2=idx2) as batch:
+        batch.run()
+        result = batch.fetch()
+    if p1.sequences is not None and p2.sequences is not None:
+        result.seqs1 = _IndexedView(p1.sequences, batch.idx1)
+        result.seqs2 = _IndexedView(p2.sequences, batch.idx2)
+    return result
+
+
+class _IndexedView:
+    def __init__(self, items, index):
+        self._items, self._index = items, index
+
+    def __getitem__(self, k):
+        return self._items[int(self._index[k])]
+
+    def __len__(self):
+        return len(self._index)
+
+
+def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True, local=False,
+                      chunk_pairs=1 << 24):
+    """
+    Symmetric ``(N, N)`` int32 matrix of optimal alignment scores of every pair ``i <= j``
+    (the quantity the reference's ``align_multiple`` computes pair by pair for its guide
+    tree, ``multiple.pyx:322-333``).  The triangle is enumerated in chunks of `chunk_pairs`
+    index pairs; the sequences are uploaded once per chunk call, never the pairs.
+    """
+    _check_gap_penalty(gap_penalty)
+    pool = pack_sequences(sequences)
+    scoring = _resolve_scoring(matrix, pool, pool)
+    if not isinstance(scoring, tuple) and not np.array_equal(scoring, scoring.T):
+        raise ValueError("all_vs_all_scores needs a symmetric substitution matrix")
+    n = len(pool)
+    out = np.zeros((n, n), dtype=np.int32)
+    rows_done = 0
+    while rows_done < n:
+        # rows i = rows_done .. stop-1 of the upper triangle (j >= i)
+        counts = n - np.arange(rows_done, n)
+        stop = rows_done + max(1, int(np.searchsorted(np.cumsum(counts), chunk_pairs, side="right")))
+        stop = min(stop, n)
+        i_idx = np.repeat(np.arange(rows_done, stop, dtype=np.int32), n - np.arange(rows_done, stop))
+        j_idx = np.concatenate([np.arange(i, n, dtype=np.int32) for i in range(rows_done, stop)])
+        with DeviceBatch(pool.codes, pool.offsets, pool.codes, pool.offsets, scoring, gap_penalty,
+                         terminal_penalty, local, None, True, idx1=i_idx, idx2=j_idx) as batch:
+            batch.run()
+            scores = batch.fetch().scores
+        out[i_idx, j_idx] = scores
+        out[j_idx, i_idx] = scores
+        rows_done = stop
+    return out
 
 
 def _resolve_scoring(matrix, packed1, packed2):

@@ -134,9 +134,27 @@ struct BtBatch {
     int min_score = 0, max_score = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<int64_t> h_off1, h_off2, h_bands, h_dir_off, h_cand_off;
+    std::vector<int64_t> h_off1, h_off2, h_bands, h_dir_off, h_cand_off, h_ops_off;
+    std::vector<int32_t> h_idx1, h_idx2;   // pair -> sequence of pool 1 / 2 (empty: identity)
+    int64_t n_seq1 = 0, n_seq2 = 0, ops_total = 0;
+    PairMap host_map() const {
+        PairMap m;
+        m.off1 = h_off1.data(); m.off2 = h_off2.data();
+        m.idx1 = h_idx1.empty() ? nullptr : h_idx1.data();
+        m.idx2 = h_idx2.empty() ? nullptr : h_idx2.data();
+        m.ops_off = h_ops_off.empty() ? nullptr : h_ops_off.data();
+        return m;
+    }
+    PairMap dev_map() const {
+        PairMap m;
+        m.off1 = off1.as<int64_t>(); m.off2 = off2.as<int64_t>();
+        m.idx1 = h_idx1.empty() ? nullptr : idx1.as<int32_t>();
+        m.idx2 = h_idx2.empty() ? nullptr : idx2.as<int32_t>();
+        m.ops_off = h_ops_off.empty() ? nullptr : ops_off.as<int64_t>();
+        return m;
+    }
     std::vector<Chunk> chunks;
-    DevBuf codes1, codes2, off1, off2, bands, matrix, dir_off, cand_off, cand, dirs, gscratch;
+    DevBuf codes1, codes2, off1, off2, idx1, idx2, ops_off, bands, matrix, dir_off, cand_off, cand, dirs, gscratch;
     DevBuf score, start_idx, start_state, end_vals, trace_len, first, ops, flag, is_start;
     InterseqPlan interseq;  // state of the packed 16-bit route
     BandedPlan banded;      // state of the banded inter-sequence route
@@ -177,7 +195,7 @@ __global__ void validate_codes_kernel(const void *codes, int64_t n, int bytes, u
 static BatchView make_view(BtBatch *b) {
     BatchView V{};
     V.codes1 = b->codes1.ptr; V.codes2 = b->codes2.ptr;
-    V.off1 = b->off1.as<int64_t>(); V.off2 = b->off2.as<int64_t>();
+    V.map = b->dev_map();
     V.bands = b->P.banded ? b->bands.as<int64_t>() : nullptr;
     V.matrix = b->P.use_matrix ? b->matrix.as<int32_t>() : nullptr;
     V.dirs = b->dirs.as<uint8_t>();
@@ -288,8 +306,9 @@ static int build_chunks(BtBatch *b) {
     Chunk cur{0, 0, 0, 0, 0, 0};
     int64_t cand_total = 0;
     b->cells = 0;
+    const PairMap hm = b->host_map();
     for (int64_t k = 0; k < n; k++) {
-        const int64_t l1 = b->h_off1[k + 1] - b->h_off1[k], l2 = b->h_off2[k + 1] - b->h_off2[k];
+        const int64_t l1 = hm.len1(k), l2 = hm.len2(k);
         if (l1 < 0 || l2 < 0) return fail(BT_ERR_INVALID_ARG, "offsets must be non-decreasing");
         if (l1 > INT32_MAX / 2 - 2 || l2 > INT32_MAX / 2 - 2)
             return fail(BT_ERR_INVALID_ARG, "sequence too long");
@@ -332,15 +351,19 @@ static int build_chunks(BtBatch *b) {
     return BT_OK;
 }
 
-static int batch_create_impl(const BtParams *params, const void *codes1, const int64_t *off1,
-                             const void *codes2, const int64_t *off2, int64_t n_pairs,
-                             const int32_t *matrix, const int64_t *bands, int32_t score_only,
-                             bool force_general, BtBatch **batch_out) {
+static int batch_create_impl(const BtParams *params, const void *codes1, const int64_t *off1, int64_t n_seq1,
+                             const void *codes2, const int64_t *off2, int64_t n_seq2, const int32_t *idx1,
+                             const int32_t *idx2, int64_t n_pairs, const int32_t *matrix, const int64_t *bands,
+                             int32_t score_only, bool force_general, BtBatch **batch_out) {
     if (!batch_out) return fail(BT_ERR_INVALID_ARG, "batch_out is NULL");
     *batch_out = nullptr;
     int st = check_params(params);
     if (st) return st;
-    if (n_pairs < 0 || !off1 || !off2) return fail(BT_ERR_INVALID_ARG, "bad pair offsets");
+    if (n_pairs < 0 || n_seq1 < 0 || n_seq2 < 0 || !off1 || !off2) return fail(BT_ERR_INVALID_ARG, "bad pair offsets");
+    if ((idx1 == nullptr) != (idx2 == nullptr)) return fail(BT_ERR_INVALID_ARG, "give both index arrays or none");
+    if (!idx1 && (n_seq1 != n_pairs || n_seq2 != n_pairs))
+        return fail(BT_ERR_INVALID_ARG, "without index arrays both pools must hold n_pairs sequences");
+    if (n_pairs > INT32_MAX) return fail(BT_ERR_INVALID_ARG, "too many pairs for one batch (split it)");
     if (params->use_matrix && !matrix) return fail(BT_ERR_INVALID_ARG, "matrix is NULL");
     if (params->banded && !bands) return fail(BT_ERR_INVALID_ARG, "bands is NULL");
     if (bt_device_count() <= 0)
@@ -351,11 +374,36 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     b->n_pairs = n_pairs;
     b->score_only = score_only ? 1 : 0;
     b->device = bt_get_device();
-    b->h_off1.assign(off1, off1 + n_pairs + 1);
-    b->h_off2.assign(off2, off2 + n_pairs + 1);
+    b->n_seq1 = n_seq1; b->n_seq2 = n_seq2;
+    b->h_off1.assign(off1, off1 + n_seq1 + 1);
+    b->h_off2.assign(off2, off2 + n_seq2 + 1);
     if (params->banded) b->h_bands.assign(bands, bands + 2 * n_pairs);
-    b->total1 = b->h_off1[n_pairs] - b->h_off1[0];
-    b->total2 = b->h_off2[n_pairs] - b->h_off2[0];
+    b->total1 = b->h_off1[n_seq1] - b->h_off1[0];
+    b->total2 = b->h_off2[n_seq2] - b->h_off2[0];
+    for (int64_t k = 0; k < n_seq1; k++)
+        if (off1[k + 1] < off1[k]) return fail(BT_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    for (int64_t k = 0; k < n_seq2; k++)
+        if (off2[k + 1] < off2[k]) return fail(BT_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    if (idx1) {
+        b->h_idx1.assign(idx1, idx1 + n_pairs);
+        b->h_idx2.assign(idx2, idx2 + n_pairs);
+        for (int64_t k = 0; k < n_pairs; k++)
+            if (idx1[k] < 0 || idx1[k] >= n_seq1 || idx2[k] < 0 || idx2[k] >= n_seq2)
+                return fail(BT_ERR_INVALID_ARG, "pair index out of range");
+        if (!score_only) {   // step bytes of pair k start at the prefix sum of len1 + len2
+            b->h_ops_off.resize((size_t)n_pairs);
+            int64_t acc = 0;
+            const PairMap hm0 = b->host_map();
+            for (int64_t k = 0; k < n_pairs; k++) {
+                b->h_ops_off[(size_t)k] = acc;
+                acc += (b->h_off1[idx1[k] + 1] - b->h_off1[idx1[k]]) + (b->h_off2[idx2[k] + 1] - b->h_off2[idx2[k]]);
+            }
+            (void)hm0;
+            b->ops_total = acc;
+        }
+    } else {
+        b->ops_total = b->total1 + b->total2;
+    }
     if (b->h_off1[0] != 0 || b->h_off2[0] != 0)
         return fail(BT_ERR_INVALID_ARG, "offsets must start at 0");
 
@@ -386,24 +434,35 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
 
     // route: packed 16-bit inter-sequence kernels when they are provably exact
     b->route = ROUTE_GENERAL;
-    if (!force_general && interseq_eligible(*params, b->h_off1, b->h_off2, n_pairs, mn, mx))
+    const PairMap hm = b->host_map();
+    if (!force_general && interseq_eligible(*params, hm, n_pairs, mn, mx))
         b->route = ROUTE_INTERSEQ;
-    else if (!force_general && banded_eligible(*params, b->h_off1, b->h_off2, b->h_bands, n_pairs, mn, mx))
+    else if (!force_general && banded_eligible(*params, hm, b->h_bands, n_pairs, mn, mx))
         b->route = ROUTE_BANDED;
 
     const size_t cb = (size_t)params->code_bytes;
     CUDA_TRY(b->codes1.alloc((size_t)b->total1 * cb));
     CUDA_TRY(b->codes2.alloc((size_t)b->total2 * cb));
-    CUDA_TRY(b->off1.alloc((size_t)(n_pairs + 1) * 8));
-    CUDA_TRY(b->off2.alloc((size_t)(n_pairs + 1) * 8));
+    CUDA_TRY(b->off1.alloc((size_t)(n_seq1 + 1) * 8));
+    CUDA_TRY(b->off2.alloc((size_t)(n_seq2 + 1) * 8));
     CUDA_TRY(b->score.alloc((size_t)n_pairs * 4));
     CUDA_TRY(b->flag.alloc(4));
     CUDA_TRY(cudaMemsetAsync(b->flag.ptr, 0, 4, b->stream));
     cudaStream_t s = b->stream;
     CUDA_TRY(cudaMemcpyAsync(b->codes1.ptr, codes1, (size_t)b->total1 * cb, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(b->codes2.ptr, codes2, (size_t)b->total2 * cb, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(b->off1.ptr, off1, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(b->off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->off1.ptr, off1, (size_t)(n_seq1 + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->off2.ptr, off2, (size_t)(n_seq2 + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (idx1) {
+        CUDA_TRY(b->idx1.alloc((size_t)n_pairs * 4));
+        CUDA_TRY(b->idx2.alloc((size_t)n_pairs * 4));
+        CUDA_TRY(cudaMemcpyAsync(b->idx1.ptr, idx1, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(b->idx2.ptr, idx2, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s));
+        if (!b->h_ops_off.empty()) {
+            CUDA_TRY(b->ops_off.alloc((size_t)n_pairs * 8));
+            CUDA_TRY(cudaMemcpyAsync(b->ops_off.ptr, b->h_ops_off.data(), (size_t)n_pairs * 8, cudaMemcpyHostToDevice, s));
+        }
+    }
     if (params->use_matrix) {
         const size_t mb = (size_t)params->n_rows * params->n_cols * 4;
         CUDA_TRY(b->matrix.alloc(mb));
@@ -412,19 +471,19 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     if (!b->score_only) {
         CUDA_TRY(b->trace_len.alloc((size_t)n_pairs * 8));
         CUDA_TRY(b->first.alloc((size_t)n_pairs * 8));
-        CUDA_TRY(b->ops.alloc((size_t)(b->total1 + b->total2)));
+        CUDA_TRY(b->ops.alloc((size_t)b->ops_total));
     }
 
     if (b->route == ROUTE_INTERSEQ) {
         CUDA_TRY(b->is_start.alloc((size_t)n_pairs * 8));
-        st = interseq_prepare(b->interseq, *params, b->h_off1, b->h_off2, n_pairs, b->score_only, mn, mx,
+        st = interseq_prepare(b->interseq, *params, hm, n_pairs, b->score_only, mn, mx,
                               &b->cells, 1, 3, s);
         if (st == BT_ERR_OOM) return fail(st, "out of device memory (inter-sequence plan)");
         if (st) return fail(st, "inter-sequence plan failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else if (b->route == ROUTE_BANDED) {
         CUDA_TRY(b->bands.alloc((size_t)n_pairs * 16));
         CUDA_TRY(cudaMemcpyAsync(b->bands.ptr, bands, (size_t)n_pairs * 16, cudaMemcpyHostToDevice, s));
-        st = banded_prepare(b->banded, *params, b->h_off1, b->h_off2, b->h_bands, n_pairs, b->score_only,
+        st = banded_prepare(b->banded, *params, hm, b->h_bands, n_pairs, b->score_only,
                             &b->cells, s);
         if (st == BT_ERR_OOM) return fail(st, "out of device memory (banded plan)");
         if (st) return fail(st, "banded plan failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -469,9 +528,21 @@ extern "C" int bt_batch_create(const BtParams *params, const void *codes1, const
                                const void *codes2, const int64_t *off2, int64_t n_pairs,
                                const int32_t *matrix, const int64_t *bands, int32_t score_only,
                                BtBatch **batch_out) {
-    return batch_create_impl(params, codes1, off1, codes2, off2, n_pairs, matrix, bands, score_only,
-                             false, batch_out);
+    return batch_create_impl(params, codes1, off1, n_pairs, codes2, off2, n_pairs, nullptr, nullptr, n_pairs, matrix,
+                             bands, score_only, false, batch_out);
 }
+
+extern "C" int bt_batch_create_indexed(const BtParams *params, const void *codes1, const int64_t *off1,
+                                       int64_t n_seq1, const void *codes2, const int64_t *off2, int64_t n_seq2,
+                                       const int32_t *idx1, const int32_t *idx2, int64_t n_pairs,
+                                       const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                                       BtBatch **batch_out) {
+    if (!idx1 || !idx2) return fail(BT_ERR_INVALID_ARG, "index arrays are NULL");
+    return batch_create_impl(params, codes1, off1, n_seq1, codes2, off2, n_seq2, idx1, idx2, n_pairs, matrix, bands,
+                             score_only, false, batch_out);
+}
+
+extern "C" int64_t bt_batch_ops_bytes(const BtBatch *b) { return b ? b->ops_total : 0; }
 
 extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
     if (!b) return fail(BT_ERR_INVALID_ARG, "batch is NULL");
@@ -482,7 +553,7 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
     int st = BT_OK;
     if (b->n_pairs > 0) {
         if (b->route == ROUTE_INTERSEQ) {
-            InterseqIO io{b->codes1.ptr, b->codes2.ptr, b->off1.as<int64_t>(), b->off2.as<int64_t>(),
+            InterseqIO io{b->codes1.ptr, b->codes2.ptr, b->dev_map(),
                           b->matrix.as<int32_t>(), b->score.as<int32_t>(), b->trace_len.as<int64_t>(),
                           b->first.as<int32_t>(), b->ops.as<uint8_t>(), b->is_start.as<int32_t>()};
             cudaError_t e = cudaSuccess;
@@ -495,7 +566,7 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
             }
             if (e != cudaSuccess) st = fail(BT_ERR_CUDA, "inter-sequence kernels: %s", cudaGetErrorString(e));
         } else if (b->route == ROUTE_BANDED) {
-            BandedIO io{b->codes1.ptr, b->codes2.ptr, b->off1.as<int64_t>(), b->off2.as<int64_t>(),
+            BandedIO io{b->codes1.ptr, b->codes2.ptr, b->dev_map(),
                         b->bands.as<int64_t>(), b->matrix.as<int32_t>(), b->score.as<int32_t>(),
                         b->trace_len.as<int64_t>(), b->first.as<int32_t>(), b->ops.as<uint8_t>()};
             cudaError_t e = cudaSuccess;
@@ -554,7 +625,7 @@ extern "C" int bt_batch_fetch_traces(BtBatch *b, int64_t *trace_len_out, int32_t
     if (first_out)
         CUDA_TRY(cudaMemcpyAsync(first_out, b->first.ptr, (size_t)b->n_pairs * 8, cudaMemcpyDeviceToHost, s));
     if (ops_out)
-        CUDA_TRY(cudaMemcpyAsync(ops_out, b->ops.ptr, (size_t)(b->total1 + b->total2), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(ops_out, b->ops.ptr, (size_t)b->ops_total, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return BT_OK;
 }
@@ -621,14 +692,18 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     }
     InterseqPlan plan;
     int64_t cells = 0;
-    int rc = interseq_prepare(plan, *params, h_off1, h_off2, n_pairs, score_only, mn, mx, &cells, 2, 1, st.s[0]);
+    PairMap hm;
+    hm.off1 = h_off1.data(); hm.off2 = h_off2.data();
+    int rc = interseq_prepare(plan, *params, hm, n_pairs, score_only, mn, mx, &cells, 2, 1, st.s[0]);
     const double t2 = now();
     if (rc == BT_ERR_OOM) return fail(rc, "out of device memory (inter-sequence plan)");
     if (rc) return fail(rc, "inter-sequence plan failed");
     CUDA_TRY(cudaEventRecord(st.ready, st.s[0]));
     CUDA_TRY(cudaStreamWaitEvent(st.s[1], st.ready, 0));
 
-    InterseqIO io{d_codes1.ptr, d_codes2.ptr, d_off1.as<int64_t>(), d_off2.as<int64_t>(), d_matrix.as<int32_t>(),
+    PairMap dm;
+    dm.off1 = d_off1.as<int64_t>(); dm.off2 = d_off2.as<int64_t>();
+    InterseqIO io{d_codes1.ptr, d_codes2.ptr, dm, d_matrix.as<int32_t>(),
                   d_score.as<int32_t>(), d_len.as<int64_t>(), d_first.as<int32_t>(), d_ops.as<uint8_t>(),
                   d_start.as<int32_t>()};
     int64_t launches = 0;
@@ -686,7 +761,9 @@ extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const 
         const int64_t cnt = (int64_t)params->n_rows * params->n_cols;
         int32_t mn = matrix[0], mx = matrix[0];
         for (int64_t k = 1; k < cnt; k++) { mn = std::min(mn, matrix[k]); mx = std::max(mx, matrix[k]); }
-        if (h1[0] == 0 && h2[0] == 0 && interseq_eligible(*params, h1, h2, n_pairs, mn, mx))
+        PairMap hm;
+        hm.off1 = h1.data(); hm.off2 = h2.data();
+        if (h1[0] == 0 && h2[0] == 0 && interseq_eligible(*params, hm, n_pairs, mn, mx))
             return align_batch_pipelined(params, codes1, off1, codes2, off2, n_pairs, matrix, score_only, mn, mx,
                                          h1, h2, scores_out, trace_len_out, first_out, ops_out);
     }
@@ -748,8 +825,8 @@ extern "C" int bt_align_pair(const BtParams *params, const void *code1, int64_t 
     // the single-pair path always uses full direction sets (general route)
     BtParams P = *params;
     BtBatch *raw = nullptr;
-    int st = batch_create_impl(&P, code1, off1, code2, off2, 1, matrix, P.banded ? band : nullptr,
-                               score_only, true, &raw);
+    int st = batch_create_impl(&P, code1, off1, 1, code2, off2, 1, nullptr, nullptr, 1, matrix,
+                               P.banded ? band : nullptr, score_only, true, &raw);
     if (st) return st;
     std::unique_ptr<BtBatch> b(raw);
     const bool first_only = (max_number == 1);

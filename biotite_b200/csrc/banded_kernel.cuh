@@ -58,7 +58,8 @@ struct BandConst {
 struct BandArgs {
     const BandDesc *desc;
     const int32_t *order;
-    const int64_t *off1, *off2, *bands;
+    PairMap map;
+    const int64_t *bands;
     const int32_t *matrix;
     const uint8_t *rowcodes, *colcodes;
     int32_t *ring, *lastrow, *lastcol;
@@ -70,8 +71,8 @@ struct BandArgs {
 // ---------------------------------------------------------------------------------------
 // packer: lane-interleaved byte codes of each group
 // ---------------------------------------------------------------------------------------
-__global__ void banded_pack_kernel(const uint8_t *codes1, const uint8_t *codes2, const int64_t *off1,
-                                   const int64_t *off2, const int32_t *order, const BandDesc *desc,
+__global__ void banded_pack_kernel(const uint8_t *codes1, const uint8_t *codes2, const PairMap map,
+                                   const int32_t *order, const BandDesc *desc,
                                    uint8_t *rowcodes, uint8_t *colcodes, int64_t n_groups) {
     const int64_t g = blockIdx.x;
     if (g >= n_groups) return;
@@ -80,7 +81,7 @@ __global__ void banded_pack_kernel(const uint8_t *codes1, const uint8_t *codes2,
     const int32_t p = order[g * 32 + lane];
     int64_t a = 0, b = 0;
     int n = 0, m = 0;
-    if (p >= 0) { a = off1[p]; n = (int)(off1[p + 1] - a); b = off2[p]; m = (int)(off2[p + 1] - b); }
+    if (p >= 0) { a = map.beg1(p); n = (int)map.len1(p); b = map.beg2(p); m = (int)map.len2(p); }
     const int rows = d.stripes * BD_R;
     for (int i = sub; i < rows; i += nsub) rowcodes[d.rowcode_off + (int64_t)i * 32 + lane] = i < n ? codes1[a + i] : 0;
     for (int j = sub; j < d.mmax; j += nsub) colcodes[d.colcode_off + (int64_t)j * 32 + lane] = j < m ? codes2[b + j] : 0;
@@ -113,7 +114,7 @@ banded_fill_kernel(const BandConst C, const BandArgs A) {
     // a padding lane behaves like a 1 x 1 pair with band (0, 0)
     int n = 1, m = 1, lower = 0, W = 1;
     if (p >= 0) {
-        n = (int)(A.off1[p + 1] - A.off1[p]); m = (int)(A.off2[p + 1] - A.off2[p]);
+        n = (int)A.map.len1(p); m = (int)A.map.len2(p);
         lower = (int)A.bands[2 * p]; W = (int)(A.bands[2 * p + 1] - A.bands[2 * p]) + 1;
     }
     const int32_t NEG = BD_NEG, open = C.gap_open, ext = C.gap_ext;
@@ -285,8 +286,7 @@ __global__ void banded_traceback_kernel(const BandConst C, const BandArgs A, int
     const int64_t g = slot >> 5;
     const int lane = (int)(slot & 31);
     const BandDesc d = A.desc[g];
-    const int64_t o1 = A.off1[p], o2 = A.off2[p];
-    const int n = (int)(A.off1[p + 1] - o1), m = (int)(A.off2[p + 1] - o2);
+    const int n = (int)A.map.len1(p), m = (int)A.map.len2(p);
     const int lower = (int)A.bands[2 * p], W = (int)(A.bands[2 * p + 1] - A.bands[2 * p]) + 1;
     const bool traced = !C.score_only;
     const uint32_t *base = A.dirs + d.dir_off + lane * 2;
@@ -324,7 +324,7 @@ __global__ void banded_traceback_kernel(const BandConst C, const BandArgs A, int
             if (hit) { si = i; ssj = sj; st = want; break; }
         }
     }
-    uint8_t *out = ops + o1 + o2;
+    uint8_t *out = ops + A.map.ops(p);
     int i = si, sj = ssj, len = 0, fi = 0, fsj = 0;
     while (i >= 1 && sj >= 0) {
         const int jb = sj - (i - 1) - lower + 1;
@@ -369,7 +369,8 @@ struct BandedPlan {
 
 struct BandedIO {
     const void *codes1, *codes2;
-    const int64_t *off1, *off2, *bands;
+    PairMap map;
+    const int64_t *bands;
     const int32_t *matrix;
     int32_t *score;
     int64_t *trace_len;
@@ -377,7 +378,7 @@ struct BandedIO {
     uint8_t *ops;
 };
 
-inline bool banded_eligible(const BtParams &P, const std::vector<int64_t> &off1, const std::vector<int64_t> &off2,
+inline bool banded_eligible(const BtParams &P, const PairMap &hm,
                             const std::vector<int64_t> &bands, int64_t n_pairs, int32_t min_score,
                             int32_t max_score) {
     if (!P.banded || !P.affine || P.local || !P.use_matrix || P.code_bytes != 1) return false;
@@ -387,7 +388,7 @@ inline bool banded_eligible(const BtParams &P, const std::vector<int64_t> &off1,
     double total = 0.0, max_pair = 0.0, max_waves = 0.0;
     int64_t span = 0;
     for (int64_t k = 0; k < n_pairs; k++) {
-        const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
+        const int64_t n = hm.len1(k), m = hm.len2(k);
         const int64_t w = bands[2 * k + 1] - bands[2 * k] + 1;
         if (n < 1 || m < 1 || n > BD_MAX_LEN || m > BD_MAX_LEN || w < 1 || w > BD_MAX_W) return false;
         if (bands[2 * k] < -(n - 1) || bands[2 * k + 1] > m - 1) return false;  // must be cropped
@@ -410,8 +411,8 @@ inline bool banded_eligible(const BtParams &P, const std::vector<int64_t> &off1,
     return true;
 }
 
-inline int banded_prepare(BandedPlan &plan, const BtParams &P, const std::vector<int64_t> &off1,
-                          const std::vector<int64_t> &off2, const std::vector<int64_t> &bands, int64_t n_pairs,
+inline int banded_prepare(BandedPlan &plan, const BtParams &P, const PairMap &hm,
+                          const std::vector<int64_t> &bands, int64_t n_pairs,
                           int score_only, int64_t *cells_out, cudaStream_t stream) {
     plan.n_pairs = n_pairs;
     plan.C.gap_open = P.gap_open; plan.C.gap_ext = P.gap_ext;
@@ -419,7 +420,7 @@ inline int banded_prepare(BandedPlan &plan, const BtParams &P, const std::vector
     // sort by length of the first sequence (rows), then of the second: std::sort on packed keys
     std::vector<uint64_t> keys((size_t)n_pairs);
     for (int64_t k = 0; k < n_pairs; k++)
-        keys[(size_t)k] = ((uint64_t)(off1[k + 1] - off1[k]) << 48) | ((uint64_t)(off2[k + 1] - off2[k]) << 32) | (uint64_t)k;
+        keys[(size_t)k] = ((uint64_t)hm.len1(k) << 48) | ((uint64_t)hm.len2(k) << 32) | (uint64_t)k;
     std::sort(keys.begin(), keys.end(), std::greater<uint64_t>());   // longest first
     plan.n_groups = (n_pairs + 31) / 32;
     plan.order.assign((size_t)plan.n_groups * 32, -1);
@@ -443,7 +444,7 @@ inline int banded_prepare(BandedPlan &plan, const BtParams &P, const std::vector
         for (int q = 0; q < 32; q++) {
             const int32_t k = plan.order[(size_t)(g * 32 + q)];
             if (k < 0) continue;
-            const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
+            const int64_t n = hm.len1(k), m = hm.len2(k);
             const int64_t lo = bands[2 * k], up = bands[2 * k + 1];
             nmax = std::max<int>(nmax, (int)n); mmax = std::max<int>(mmax, (int)m);
             wmax = std::max<int>(wmax, (int)(up - lo + 1));
@@ -494,7 +495,7 @@ inline BandArgs banded_args(BandedPlan &plan, const BandWindow &win, const Bande
     BandArgs A{};
     A.desc = plan.d_desc.as<BandDesc>() + win.group_begin;
     A.order = plan.d_order.as<int32_t>() + win.group_begin * 32;
-    A.off1 = io.off1; A.off2 = io.off2; A.bands = io.bands; A.matrix = io.matrix;
+    A.map = io.map; A.bands = io.bands; A.matrix = io.matrix;
     A.rowcodes = plan.rowcodes.as<uint8_t>(); A.colcodes = plan.colcodes.as<uint8_t>();
     A.ring = plan.ring.as<int32_t>(); A.lastrow = plan.lastrow.as<int32_t>(); A.lastcol = plan.lastcol.as<int32_t>();
     A.dirs = plan.dirs.as<uint32_t>();
@@ -507,7 +508,7 @@ inline cudaError_t banded_fill_window(BandedPlan &plan, const BandWindow &win, c
                                       cudaStream_t stream, int64_t *launches) {
     const BandArgs A = banded_args(plan, win, io);
     banded_pack_kernel<<<(unsigned)A.n_groups, 256, 0, stream>>>(
-        (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.off1, io.off2, A.order, A.desc,
+        (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.map, A.order, A.desc,
         plan.rowcodes.as<uint8_t>(), plan.colcodes.as<uint8_t>(), A.n_groups);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -26,10 +26,30 @@ struct DevParams {
     int matrix_in_smem;  // matrix staged in shared memory
 };
 
+// Which sequences pair p aligns.  off1/off2 are the offsets of two sequence pools; idx1/idx2
+// map a pair to its sequences (nullptr = identity: pair p aligns sequence p of either pool,
+// the plain many-pairs batch).  Usable with host or device pointers.
+struct PairMap {
+    const int64_t *off1 = nullptr, *off2 = nullptr;
+    const int32_t *idx1 = nullptr, *idx2 = nullptr;
+    const int64_t *ops_off = nullptr;   // pair -> first step byte (nullptr: off1[p] + off2[p])
+    __host__ __device__ __forceinline__ int64_t beg1(int64_t p) const { return off1[idx1 ? idx1[p] : p]; }
+    __host__ __device__ __forceinline__ int64_t beg2(int64_t p) const { return off2[idx2 ? idx2[p] : p]; }
+    __host__ __device__ __forceinline__ int64_t len1(int64_t p) const {
+        const int64_t q = idx1 ? idx1[p] : p;
+        return off1[q + 1] - off1[q];
+    }
+    __host__ __device__ __forceinline__ int64_t len2(int64_t p) const {
+        const int64_t q = idx2 ? idx2[p] : p;
+        return off2[q + 1] - off2[q];
+    }
+    __host__ __device__ __forceinline__ int64_t ops(int64_t p) const { return ops_off ? ops_off[p] : off1[p] + off2[p]; }
+};
+
 // Device views of one batch (or one chunk of it).
 struct BatchView {
     const void *codes1, *codes2;
-    const int64_t *off1, *off2;   // n_pairs+1 element offsets
+    PairMap map;                  // pair -> sequences
     const int64_t *bands;         // 2*n_pairs (lower, upper) or nullptr
     const int32_t *matrix;        // n_rows*n_cols or nullptr
     uint8_t *dirs;                // direction table storage of this chunk

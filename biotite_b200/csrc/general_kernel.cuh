@@ -110,8 +110,8 @@ general_fill_kernel(const DevParams P, const BatchView V) {
 
     const int64_t p = V.pair_begin + blockIdx.x;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int64_t o1 = V.off1[p], o2 = V.off2[p];
-    const int n = (int)(V.off1[p + 1] - o1), m = (int)(V.off2[p + 1] - o2);
+    const int64_t o1 = V.map.beg1(p), o2 = V.map.beg2(p);
+    const int n = (int)V.map.len1(p), m = (int)V.map.len2(p);
     constexpr int NS = AFFINE ? 3 : 1;
     const int32_t NI = P.neg_inf;
 
@@ -323,13 +323,12 @@ template <bool AFFINE, bool BANDED>
 __global__ void general_traceback_kernel(const BatchView V) {
     const int64_t p = V.pair_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= V.pair_end) return;
-    const int64_t o1 = V.off1[p], o2 = V.off2[p];
-    const int64_t n = V.off1[p + 1] - o1, m = V.off2[p + 1] - o2;
+    const int64_t n = V.map.len1(p), m = V.map.len2(p);
     int64_t rs = m + 1;
     if (BANDED) rs = V.bands[2 * p + 1] - V.bands[2 * p] + 3;
     const int64_t step[3] = {BANDED ? -rs : -(rs + 1), -1, BANDED ? -rs + 1 : -rs};
     const uint8_t *dir = V.dirs + V.dir_off[p];
-    uint8_t *ops = V.ops + (o1 + o2);
+    uint8_t *ops = V.ops + V.map.ops(p);
     const int64_t cap = n + m;
     int64_t idx = V.start_idx[p], last = 0, len = 0;
     int st = V.start_state[p];

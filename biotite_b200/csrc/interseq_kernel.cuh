@@ -91,7 +91,7 @@ struct InterseqPlan {
 
 struct InterseqIO {
     const void *codes1, *codes2;
-    const int64_t *off1, *off2;
+    PairMap map;
     const int32_t *matrix;
     int32_t *score;
     int64_t *trace_len;
@@ -103,8 +103,7 @@ struct InterseqIO {
 // ---------------------------------------------------------------------------------------
 // eligibility: proven-exact 16-bit range (see DESIGN.md "16-bit safety")
 // ---------------------------------------------------------------------------------------
-inline bool interseq_eligible(const BtParams &P, const std::vector<int64_t> &off1,
-                              const std::vector<int64_t> &off2, int64_t n_pairs, int32_t min_score,
+inline bool interseq_eligible(const BtParams &P, const PairMap &hm, int64_t n_pairs, int32_t min_score,
                               int32_t max_score) {
     if (P.banded || !P.use_matrix) return false;
     if (!P.affine && !P.local && !P.terminal_penalty) return false;  // linear semi-global: general kernel
@@ -112,7 +111,7 @@ inline bool interseq_eligible(const BtParams &P, const std::vector<int64_t> &off
     if ((int64_t)P.n_rows * P.n_cols * IS_ROWW > 96 * 1024 || P.n_rows > 255 || P.n_cols > 255) return false;
     int64_t nmax = 0, mmax = 0;
     for (int64_t k = 0; k < n_pairs; k++) {
-        const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
+        const int64_t n = hm.len1(k), m = hm.len2(k);
         if (n < 1 || m < 1 || n > IS_MAX_LEN || m > IS_MAX_LEN) return false;
         nmax = std::max(nmax, n); mmax = std::max(mmax, m);
     }
@@ -128,7 +127,7 @@ inline bool interseq_eligible(const BtParams &P, const std::vector<int64_t> &off
     if (!(forced && strcmp(forced, "packed") == 0)) {
         double total = 0.0, max_pair = 0.0, max_diag = 0.0;
         for (int64_t k = 0; k < n_pairs; k++) {
-            const double n = (double)(off1[k + 1] - off1[k]), m = (double)(off2[k + 1] - off2[k]);
+            const double n = (double)hm.len1(k), m = (double)hm.len2(k);
             total += n * m; max_pair = std::max(max_pair, n * m); max_diag = std::max(max_diag, n + m);
         }
         const double groups = (double)((n_pairs + 63) / 64);
@@ -148,8 +147,8 @@ inline bool interseq_eligible(const BtParams &P, const std::vector<int64_t> &off
 // ---------------------------------------------------------------------------------------
 // batch packer: lane-interleaved codes of each group
 // ---------------------------------------------------------------------------------------
-__global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes2, const int64_t *off1,
-                                     const int64_t *off2, const int32_t *order, const WarpDesc *desc,
+__global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes2, const PairMap map,
+                                     const int32_t *order, const WarpDesc *desc,
                                      uint16_t *rowcodes, uint16_t *colcodes, int64_t n_groups) {
     const int64_t g = blockIdx.x;
     if (g >= n_groups) return;
@@ -160,8 +159,8 @@ __global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes
     const int32_t p_lo = order[g * 64 + 2 * lane], p_hi = order[g * 64 + 2 * lane + 1];
     int64_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
     int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
-    if (p_lo >= 0) { a_lo = off1[p_lo]; n_lo = (int)(off1[p_lo + 1] - a_lo); b_lo = off2[p_lo]; m_lo = (int)(off2[p_lo + 1] - b_lo); }
-    if (p_hi >= 0) { a_hi = off1[p_hi]; n_hi = (int)(off1[p_hi + 1] - a_hi); b_hi = off2[p_hi]; m_hi = (int)(off2[p_hi + 1] - b_hi); }
+    if (p_lo >= 0) { a_lo = map.beg1(p_lo); n_lo = (int)map.len1(p_lo); b_lo = map.beg2(p_lo); m_lo = (int)map.len2(p_lo); }
+    if (p_hi >= 0) { a_hi = map.beg1(p_hi); n_hi = (int)map.len1(p_hi); b_hi = map.beg2(p_hi); m_hi = (int)map.len2(p_hi); }
     for (int i = sub; i < rows; i += nsub) {
         const uint32_t lo = i < n_lo ? codes1[a_lo + i] : 0, hi = i < n_hi ? codes1[a_hi + i] : 0;
         rowcodes[d.rowcode_off + (int64_t)i * 32 + lane] = (uint16_t)(lo | (hi << 8));
@@ -194,7 +193,7 @@ enum : int { IS_GLOBAL = 0, IS_SEMI = 1, IS_LOCAL = 2 };
 struct InterseqArgs {
     const WarpDesc *desc;
     const int32_t *order;
-    const int64_t *off1, *off2;
+    PairMap map;
     const int32_t *matrix;
     const uint16_t *rowcodes, *colcodes;
     uint32_t *rowbuf;     // 3 planes [j][lane]: M, F2, H of the stripe's last row
@@ -229,8 +228,8 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
     const WarpDesc d = A.desc[g];
     const int32_t p_lo = A.order[g * 64 + 2 * lane], p_hi = A.order[g * 64 + 2 * lane + 1];
     int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
-    if (p_lo >= 0) { n_lo = (int)(A.off1[p_lo + 1] - A.off1[p_lo]); m_lo = (int)(A.off2[p_lo + 1] - A.off2[p_lo]); }
-    if (p_hi >= 0) { n_hi = (int)(A.off1[p_hi + 1] - A.off1[p_hi]); m_hi = (int)(A.off2[p_hi + 1] - A.off2[p_hi]); }
+    if (p_lo >= 0) { n_lo = (int)A.map.len1(p_lo); m_lo = (int)A.map.len2(p_lo); }
+    if (p_hi >= 0) { n_hi = (int)A.map.len1(p_hi); m_hi = (int)A.map.len2(p_hi); }
 
     const uint32_t ext2 = ((uint32_t)C.gap_ext & 0xffffu) * 0x10001u;
     const uint32_t open2 = ((uint32_t)C.gap_open & 0xffffu) * 0x10001u;
@@ -453,11 +452,11 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
     const int64_t g = slot >> 6;
     const int lane = (int)(slot & 63) >> 1, half = (int)(slot & 1);
     const WarpDesc d = A.desc[g];
-    const int64_t o1 = A.off1[p], o2 = A.off2[p];
-    const int n = (int)(A.off1[p + 1] - o1), m = (int)(A.off2[p + 1] - o2);
+    const int64_t o1 = A.map.beg1(p), o2 = A.map.beg2(p);
+    const int n = (int)A.map.len1(p), m = (int)A.map.len2(p);
     const bool traced = !C.score_only;
     const uint32_t *base = A.dirs + d.dir_off + lane * 4 + half * 2;
-    uint8_t *out = ops + o1 + o2;
+    uint8_t *out = ops + A.map.ops(p);
     auto nibble = [&](int i, int j) -> uint32_t {  // 1-based table cell (i, j)
         const int rg = i - 1, s = rg / IS_R, r = rg % IS_R;
         const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 128 + (r >> 3)];
@@ -560,8 +559,8 @@ interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
     const WarpDesc d = A.desc[g];
     const int32_t p_lo = A.order[g * 64 + 2 * lane], p_hi = A.order[g * 64 + 2 * lane + 1];
     int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
-    if (p_lo >= 0) { n_lo = (int)(A.off1[p_lo + 1] - A.off1[p_lo]); m_lo = (int)(A.off2[p_lo + 1] - A.off2[p_lo]); }
-    if (p_hi >= 0) { n_hi = (int)(A.off1[p_hi + 1] - A.off1[p_hi]); m_hi = (int)(A.off2[p_hi + 1] - A.off2[p_hi]); }
+    if (p_lo >= 0) { n_lo = (int)A.map.len1(p_lo); m_lo = (int)A.map.len2(p_lo); }
+    if (p_hi >= 0) { n_hi = (int)A.map.len1(p_hi); m_hi = (int)A.map.len2(p_hi); }
 
     const uint32_t gap2 = ((uint32_t)C.gap_open & 0xffffu) * 0x10001u;
     const uint32_t col_stride = (uint32_t)C.n_rows * IS_ROWW;
@@ -695,10 +694,10 @@ __global__ void interseq_linear_traceback_kernel(const InterseqConst C, const In
     const int64_t g = slot >> 6;
     const int lane = (int)(slot & 63) >> 1, half = (int)(slot & 1);
     const WarpDesc d = A.desc[g];
-    const int64_t o1 = A.off1[p], o2 = A.off2[p];
-    const int n = (int)(A.off1[p + 1] - o1), m = (int)(A.off2[p + 1] - o2);
+    const int64_t o1 = A.map.beg1(p), o2 = A.map.beg2(p);
+    const int n = (int)A.map.len1(p), m = (int)A.map.len2(p);
     const uint32_t *base = A.dirs + d.dir_off + lane * 2 + half;
-    uint8_t *out = ops + o1 + o2;
+    uint8_t *out = ops + A.map.ops(p);
     int i = n, j = m, len = 0, fi = 0, fj = 0;
     int32_t value = 0;
     if (MODE == IS_LOCAL) { i = A.start[2 * p]; j = A.start[2 * p + 1]; value = A.score[p]; }
@@ -755,20 +754,19 @@ struct WindowPlan {
 // pairs to groups of 64 - longest first, because the block scheduler hands out groups in
 // index order and the tail of a window should consist of its cheapest groups - and lay out
 // the window's scratch.
-inline void interseq_plan_window(WindowPlan &wp, const std::vector<int64_t> &off1,
-                                 const std::vector<int64_t> &off2, int64_t w0, int64_t w1, int score_only,
+inline void interseq_plan_window(WindowPlan &wp, const PairMap &hm, int64_t w0, int64_t w1, int score_only,
                                  int dir_words_per_lane) {
     const int64_t cnt = w1 - w0;
     std::vector<int32_t> tmp((size_t)cnt), sorted((size_t)cnt), count(IS_MAX_LEN + 2, 0);
-    for (int64_t k = w0; k < w1; k++) count[(size_t)(off2[k + 1] - off2[k]) + 1]++;
+    for (int64_t k = w0; k < w1; k++) count[(size_t)hm.len2(k) + 1]++;
     for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
-    for (int64_t k = w0; k < w1; k++) tmp[(size_t)count[(size_t)(off2[k + 1] - off2[k])]++] = (int32_t)k;
+    for (int64_t k = w0; k < w1; k++) tmp[(size_t)count[(size_t)hm.len2(k)]++] = (int32_t)k;
     std::fill(count.begin(), count.end(), 0);
-    for (int64_t k = w0; k < w1; k++) count[(size_t)(off1[k + 1] - off1[k]) + 1]++;
+    for (int64_t k = w0; k < w1; k++) count[(size_t)hm.len1(k) + 1]++;
     for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
     for (int64_t q = 0; q < cnt; q++) {
         const int32_t k = tmp[(size_t)q];
-        sorted[(size_t)count[(size_t)(off1[k + 1] - off1[k])]++] = k;
+        sorted[(size_t)count[(size_t)hm.len1(k)]++] = k;
     }
     Window &win = wp.win;
     win.pair_begin = w0; win.pair_end = w1;
@@ -781,7 +779,7 @@ inline void interseq_plan_window(WindowPlan &wp, const std::vector<int64_t> &off
         for (int q = 0; q < 64; q++) {
             const int32_t k = wp.order[(size_t)(g * 64 + q)];
             if (k < 0) continue;
-            const int64_t n = off1[k + 1] - off1[k], m = off2[k + 1] - off2[k];
+            const int64_t n = hm.len1(k), m = hm.len2(k);
             nmax = std::max<int>(nmax, (int)n); mmax = std::max<int>(mmax, (int)m);
             wp.cells += n * m;
         }
@@ -797,8 +795,7 @@ inline void interseq_plan_window(WindowPlan &wp, const std::vector<int64_t> &off
     }
 }
 
-inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const std::vector<int64_t> &off1,
-                            const std::vector<int64_t> &off2, int64_t n_pairs, int score_only,
+inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap &hm, int64_t n_pairs, int score_only,
                             int32_t min_score, int32_t max_score, int64_t *cells_out, int n_slots,
                             int waves_per_window, cudaStream_t stream) {
     (void)max_score;
@@ -822,7 +819,7 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const std::ve
                 const int64_t w = next.fetch_add(1);
                 if (w >= n_windows) break;
                 const int64_t w0 = w * per_window, w1 = std::min(n_pairs, w0 + per_window);
-                interseq_plan_window(wps[(size_t)w], off1, off2, w0, w1, score_only, P.affine ? 4 : 2);
+                interseq_plan_window(wps[(size_t)w], hm, w0, w1, score_only, P.affine ? 4 : 2);
             }
         };
         std::vector<std::thread> threads;
@@ -876,7 +873,7 @@ inline InterseqArgs interseq_args(InterseqPlan &plan, const Window &win, int slo
     InterseqArgs A{};
     A.desc = plan.d_desc.as<WarpDesc>() + win.group_begin;
     A.order = plan.d_order.as<int32_t>() + win.group_begin * 64;
-    A.off1 = io.off1; A.off2 = io.off2; A.matrix = io.matrix;
+    A.map = io.map; A.matrix = io.matrix;
     A.rowcodes = b.rowcodes.as<uint16_t>(); A.colcodes = b.colcodes.as<uint16_t>();
     A.rowbuf = b.rowbuf.as<uint32_t>(); A.lastrow = b.lastrow.as<uint32_t>(); A.lastcol = b.lastcol.as<uint32_t>();
     A.dirs = b.dirs.as<uint32_t>();
@@ -911,7 +908,7 @@ inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, i
     const InterseqArgs A = interseq_args(plan, win, slot, io);
     const int64_t groups = A.n_groups;
     interseq_pack_kernel<<<(unsigned)groups, 256, 0, stream>>>(
-        (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.off1, io.off2, A.order, A.desc,
+        (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.map, A.order, A.desc,
         plan.slots[slot].rowcodes.as<uint16_t>(), plan.slots[slot].colcodes.as<uint16_t>(), groups);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

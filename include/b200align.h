@@ -119,6 +119,20 @@ int bt_batch_create(const BtParams *params, const void *codes1, const int64_t *o
                     const void *codes2, const int64_t *off2, int64_t n_pairs,
                     const int32_t *matrix, const int64_t *bands, int32_t score_only,
                     BtBatch **batch_out);
+/*
+ * Indexed batch: the sequences live in two pools (pool k: n_seqk sequences, offk has
+ * n_seqk + 1 entries) and pair p aligns sequence idx1[p] of pool 1 with sequence idx2[p] of
+ * pool 2.  This is how one-vs-many searches (BASELINE config 3) and all-vs-all score
+ * matrices (config 5; the guide-tree loop of the reference, multiple.pyx:322-333) are run
+ * without materialising the pairs.  The step bytes of pair p start at the prefix sum of
+ * len1 + len2 over the pairs before it (bt_batch_ops_bytes() bytes in total).
+ */
+int bt_batch_create_indexed(const BtParams *params, const void *codes1, const int64_t *off1,
+                            int64_t n_seq1, const void *codes2, const int64_t *off2, int64_t n_seq2,
+                            const int32_t *idx1, const int32_t *idx2, int64_t n_pairs,
+                            const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                            BtBatch **batch_out);
+int64_t bt_batch_ops_bytes(const BtBatch *batch);
 int bt_batch_run(BtBatch *batch, float *device_ms);
 int bt_batch_fetch_scores(BtBatch *batch, int32_t *scores_out);
 int bt_batch_fetch_traces(BtBatch *batch, int64_t *trace_len_out, int32_t *first_out,

@@ -516,3 +516,46 @@ def test_banded_batch_matches_oracle(route):
                                           local=local, max_number=1)[0]
                 assert res.scores[k] == ref.score
                 assert np.array_equal(res.trace(k), ref.trace)
+
+
+# ---- indexed batches: one-vs-many (config 3) and all-vs-all (config 5) without materialised pairs ----
+
+def _random_proteins(rng, count, lo, hi):
+    seqs = []
+    for _ in range(count):
+        s = bt.ProteinSequence()
+        s.code = rng.integers(0, 20, int(rng.integers(lo, hi)))
+        seqs.append(s)
+    return seqs
+
+
+def test_indexed_batch_matches_plain_batch(route):
+    rng = np.random.default_rng(31)
+    pool1 = _random_proteins(rng, 40, 30, 200)
+    pool2 = _random_proteins(rng, 70, 30, 200)
+    idx1 = rng.integers(0, 40, 1500).astype(np.int32)
+    idx2 = rng.integers(0, 70, 1500).astype(np.int32)
+    for gap, term, local in (((-10, -1), True, False), ((-10, -1), False, False), ((-11, -1), True, True), (-9, True, False)):
+        res = bt.align_indexed_batch(pool1, pool2, idx1, idx2, BLOSUM(), gap, term, local)
+        plain = bt.align_optimal_batch([pool1[i] for i in idx1], [pool2[j] for j in idx2], BLOSUM(), gap, term, local)
+        assert np.array_equal(res.scores, plain.scores)
+        a, b = res.traces(), plain.traces()
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        k = 17
+        assert res.alignment(k) == plain.alignment(k)
+        only = bt.align_indexed_batch(pool1, pool2, idx1, idx2, BLOSUM(), gap, term, local, score_only=True)
+        assert np.array_equal(only.scores, plain.scores)
+
+
+def test_all_vs_all_scores_semi_global():
+    """Config 5 shape at test size: every pair i <= j, terminal_penalty=False, vs the oracle."""
+    rng = np.random.default_rng(37)
+    seqs = _random_proteins(rng, 60, 40, 260)
+    matrix = BLOSUM()
+    got = bt.all_vs_all_scores(seqs, matrix, (-10, -1), terminal_penalty=False, chunk_pairs=500)
+    assert got.shape == (60, 60) and np.array_equal(got, got.T)
+    for i in range(0, 60, 7):
+        for j in range(i, 60, 5):
+            ref = oracle_align_optimal(seqs[i], seqs[j], matrix, (-10, -1), terminal_penalty=False,
+                                       score_only=True)
+            assert got[i, j] == ref
