@@ -361,6 +361,7 @@ def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True,
         raise ValueError("all_vs_all_scores needs a symmetric substitution matrix")
     n = len(pool)
     out = np.zeros((n, n), dtype=np.int32)
+    lengths = pool.lengths
     rows_done = 0
     while rows_done < n:
         # rows i = rows_done .. stop-1 of the upper triangle (j >= i)
@@ -369,14 +370,24 @@ def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True,
         stop = min(stop, n)
         i_idx = np.repeat(np.arange(rows_done, stop, dtype=np.int32), n - np.arange(rows_done, stop))
         j_idx = np.concatenate([np.arange(i, n, dtype=np.int32) for i in range(rows_done, stop)])
-        with DeviceBatch(pool.codes, pool.offsets, pool.codes, pool.offsets, scoring, gap_penalty,
-                         terminal_penalty, local, None, True, idx1=i_idx, idx2=j_idx) as batch:
-            batch.run()
-            scores = batch.fetch().scores
-        out[i_idx, j_idx] = scores
-        out[j_idx, i_idx] = scores
+        # one very long sequence would send the whole chunk to the general kernel: pairs whose
+        # sequences fit the packed kernels are run separately from the rest
+        short = (lengths[i_idx] <= _PACKED_MAX_LEN) & (lengths[j_idx] <= _PACKED_MAX_LEN)
+        for mask in (short, ~short):
+            if not mask.any():
+                continue
+            a, b = i_idx[mask], j_idx[mask]
+            with DeviceBatch(pool.codes, pool.offsets, pool.codes, pool.offsets, scoring, gap_penalty,
+                             terminal_penalty, local, None, True, idx1=a, idx2=b) as batch:
+                batch.run()
+                scores = batch.fetch().scores
+            out[a, b] = scores
+            out[b, a] = scores
         rows_done = stop
     return out
+
+
+_PACKED_MAX_LEN = 2000   # IS_MAX_LEN of csrc/interseq_kernel.cuh
 
 
 def _resolve_scoring(matrix, packed1, packed2):

@@ -456,7 +456,7 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
     const int n = (int)A.map.len1(p), m = (int)A.map.len2(p);
     const bool traced = !C.score_only;
     const uint32_t *base = A.dirs + d.dir_off + lane * 4 + half * 2;
-    uint8_t *out = ops + A.map.ops(p);
+    uint8_t *out = traced ? ops + A.map.ops(p) : nullptr;   // score-only batches carry no step offsets
     auto nibble = [&](int i, int j) -> uint32_t {  // 1-based table cell (i, j)
         const int rg = i - 1, s = rg / IS_R, r = rg % IS_R;
         const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 128 + (r >> 3)];
