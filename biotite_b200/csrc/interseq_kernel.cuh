@@ -381,14 +381,30 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                 // local: running maximum of M over the cells inside the table, first in row-major
                 // order (pairwise.rs:849-865).  Fast path: one packed max per row; the scalar
                 // path runs where padding must be masked or (traced) a new optimum may appear.
-                uint32_t cm = Ml[0];
+                bool slow = false;
+                if (!TRACED) {
+                    // score only: packed running maximum; padding rows (last stripe) and padding
+                    // columns are masked to 0, which never beats the running maximum (>= 0)
+                    uint32_t cm = 0;
+                    if (rows_valid) {
 #pragma unroll
-                for (int r = 1; r < IS_R; r++) cm = __vmaxs2(cm, Ml[r]);
-                const bool inside = rows_valid && j < m_lo && j < m_hi;
-                bool slow = !inside;
-                if (inside) {
-                    if (!TRACED) best2 = __vmaxs2(best2, cm);
-                    else {
+                        for (int r = 0; r < IS_R; r += 2) cm = __vimax3_s16x2(cm, Ml[r], Ml[r + 1]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < IS_R; r++) {
+                            const uint32_t rmask = (r0 + r < n_lo ? 0xffffu : 0u) | (r0 + r < n_hi ? 0xffff0000u : 0u);
+                            cm = __vmaxs2(cm, Ml[r] & rmask);
+                        }
+                    }
+                    const uint32_t cmask = (j < m_lo ? 0xffffu : 0u) | (j < m_hi ? 0xffff0000u : 0u);
+                    best2 = __vmaxs2(best2, cm & cmask);
+                } else {
+                    uint32_t cm = Ml[0];
+#pragma unroll
+                    for (int r = 1; r < IS_R; r++) cm = __vmaxs2(cm, Ml[r]);
+                    const bool inside = rows_valid && j < m_lo && j < m_hi;
+                    slow = !inside;
+                    if (inside) {
                         const int c_lo = (int16_t)(cm & 0xffffu), c_hi = (int16_t)(cm >> 16);
                         slow = (c_lo >= best_lo && c_lo > 0) || (c_hi >= best_hi && c_hi > 0);
                     }
@@ -639,14 +655,29 @@ interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                     }
                 }
             } else {
-                uint32_t cm = Sl[0];
+                bool slow = false;
+                if (!TRACED) {
+                    // score only: packed running maximum, padding rows / columns masked to 0
+                    uint32_t cm = 0;
+                    if (rows_valid) {
 #pragma unroll
-                for (int r = 1; r < IS_R; r++) cm = __vmaxs2(cm, Sl[r]);
-                const bool inside = rows_valid && j < m_lo && j < m_hi;
-                bool slow = !inside;
-                if (inside) {
-                    if (!TRACED) best2 = __vmaxs2(best2, cm);
-                    else {
+                        for (int r = 0; r < IS_R; r += 2) cm = __vimax3_s16x2(cm, Sl[r], Sl[r + 1]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < IS_R; r++) {
+                            const uint32_t rmask = (r0 + r < n_lo ? 0xffffu : 0u) | (r0 + r < n_hi ? 0xffff0000u : 0u);
+                            cm = __vmaxs2(cm, Sl[r] & rmask);
+                        }
+                    }
+                    const uint32_t cmask = (j < m_lo ? 0xffffu : 0u) | (j < m_hi ? 0xffff0000u : 0u);
+                    best2 = __vmaxs2(best2, cm & cmask);
+                } else {
+                    uint32_t cm = Sl[0];
+#pragma unroll
+                    for (int r = 1; r < IS_R; r++) cm = __vmaxs2(cm, Sl[r]);
+                    const bool inside = rows_valid && j < m_lo && j < m_hi;
+                    slow = !inside;
+                    if (inside) {
                         const int c_lo = (int16_t)(cm & 0xffffu), c_hi = (int16_t)(cm >> 16);
                         slow = (c_lo >= best_lo && c_lo > 0) || (c_hi >= best_hi && c_hi > 0);
                     }
