@@ -37,6 +37,7 @@ from .batch import (
     align_batch_arrays,
     align_indexed_batch,
     all_vs_all_scores,
+    feng_doolittle_distances,
     align_banded_batch,
     align_optimal_batch,
     pack_sequences,

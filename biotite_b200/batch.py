@@ -30,6 +30,7 @@ __all__ = [
     "align_batch_arrays",
     "align_indexed_batch",
     "all_vs_all_scores",
+    "feng_doolittle_distances",
     "align_optimal_batch",
     "align_banded_batch",
 ]
@@ -84,7 +85,7 @@ class DeviceBatch:
 
     def __init__(self, codes1, off1, codes2, off2, scoring, gap_penalty,
                  terminal_penalty=True, local=False, bands=None, score_only=False,
-                 idx1=None, idx2=None):
+                 idx1=None, idx2=None, stats=False):
         """
         Without `idx1` / `idx2` pair ``k`` aligns sequence ``k`` of either side.  With them
         the two sides are sequence *pools* and pair ``k`` aligns ``pool1[idx1[k]]`` with
@@ -109,6 +110,8 @@ class DeviceBatch:
             self.n_pairs = len(self.idx1)
         self.bands = None if bands is None else np.ascontiguousarray(bands, dtype=np.int64)
         self.score_only = bool(score_only)
+        self.stats = bool(stats) and not self.score_only
+        mode = 1 if self.score_only else (2 if self.stats else 0)
         self._params, self._matrix = _cabi.make_params(
             scoring, gap_penalty, terminal_penalty, local, bands is not None, dtype)
         handle = ctypes.c_void_p(None)
@@ -116,14 +119,14 @@ class DeviceBatch:
             _cabi.check(self._lib.bt_batch_create(
                 ctypes.byref(self._params), _cabi.ptr(self.codes1), _cabi.ptr(self.off1),
                 _cabi.ptr(self.codes2), _cabi.ptr(self.off2), self.n_pairs,
-                _cabi.ptr(self._matrix), _cabi.ptr(self.bands), int(self.score_only),
+                _cabi.ptr(self._matrix), _cabi.ptr(self.bands), mode,
                 ctypes.byref(handle)))
         else:
             _cabi.check(self._lib.bt_batch_create_indexed(
                 ctypes.byref(self._params), _cabi.ptr(self.codes1), _cabi.ptr(self.off1),
                 len(self.off1) - 1, _cabi.ptr(self.codes2), _cabi.ptr(self.off2),
                 len(self.off2) - 1, _cabi.ptr(self.idx1), _cabi.ptr(self.idx2), self.n_pairs,
-                _cabi.ptr(self._matrix), _cabi.ptr(self.bands), int(self.score_only),
+                _cabi.ptr(self._matrix), _cabi.ptr(self.bands), mode,
                 ctypes.byref(handle)))
         self._handle = handle
 
@@ -166,13 +169,19 @@ class DeviceBatch:
             if not self.score_only:
                 trace_len = np.empty(n, dtype=np.int64)
                 first = np.empty((n, 2), dtype=np.int32)
-                ops = np.empty(int(self._lib.bt_batch_ops_bytes(self._handle)), dtype=np.uint8)
+                if not self.stats:
+                    ops = np.empty(int(self._lib.bt_batch_ops_bytes(self._handle)), dtype=np.uint8)
         else:
             scores, trace_len, first, ops = out
         _cabi.check(self._lib.bt_batch_fetch_scores(self._handle, _cabi.ptr(scores)))
         if not self.score_only:
             _cabi.check(self._lib.bt_batch_fetch_traces(
                 self._handle, _cabi.ptr(trace_len), _cabi.ptr(first), _cabi.ptr(ops)))
+        if self.stats:
+            # statistics mode: `first` carries (gap opening, gap extending) column counts
+            result = BatchResult(scores, trace_len, None, None, np.zeros(0, dtype=np.int64), self.bands)
+            result.gap_counts = first
+            return result
         return BatchResult(scores, trace_len, first, ops, self._ops_offsets(), self.bands)
 
     def close(self):
@@ -256,6 +265,7 @@ class BatchResult:
         self.swapped = swapped
         self.seqs1 = seqs1
         self.seqs2 = seqs2
+        self.gap_counts = None   # (n, 2) gap-open / gap-extension column counts (statistics batches)
 
     def __len__(self):
         return len(self.scores)
@@ -388,6 +398,62 @@ def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True,
 
 
 _PACKED_MAX_LEN = 2000   # IS_MAX_LEN of csrc/interseq_kernel.cuh
+
+
+def feng_doolittle_distances(sequences, matrix, gap_penalty=-10, terminal_penalty=True):
+    """
+    Pairwise distance matrix of the progressive-alignment guide tree (Feng & Doolittle), as
+    the reference's ``align_multiple`` computes it (``multiple.pyx:286-400``): every pair
+    ``i >= j`` is aligned with ``max_number=1``; with the alignment score ``S``, its length
+    ``L`` and its gap-opening / gap-extension column counts,
+
+        S_max  = (S_ii + S_jj) / 2
+        S_rand = sum_ab matrix[a, b] * count_i[a] * count_j[b] / L + n_open * open + n_ext * ext
+        D_ij   = -log((S_ij - S_rand) / (S_max - S_rand))
+
+    Scores, lengths and gap counts come from one GPU batch in statistics mode, so no trace
+    leaves the device.  Returns a symmetric float32 ``(N, N)`` matrix with a zero diagonal;
+    raises ``ValueError`` like the reference if a randomised alignment scores better.
+    """
+    _check_gap_penalty(gap_penalty)
+    pool = pack_sequences(sequences)
+    scoring = _resolve_scoring(matrix, pool, pool)
+    if isinstance(scoring, tuple):
+        raise TypeError("A substitution matrix is required")
+    n = len(pool)
+    i_idx, j_idx = np.tril_indices(n)          # i >= j, including the diagonal
+    i_idx, j_idx = i_idx.astype(np.int32), j_idx.astype(np.int32)
+    with DeviceBatch(pool.codes, pool.offsets, pool.codes, pool.offsets, scoring, gap_penalty,
+                     terminal_penalty, False, None, False, idx1=i_idx, idx2=j_idx, stats=True) as batch:
+        batch.run()
+        res = batch.fetch()
+    scores = np.zeros((n, n), dtype=np.int32)
+    scores[i_idx, j_idx] = res.scores
+    gap_open, gap_ext = (gap_penalty if isinstance(gap_penalty, tuple) else (gap_penalty, gap_penalty))
+    alphabet_size = scoring.shape[0]
+    counts = np.zeros((n, alphabet_size), dtype=np.float64)
+    for k in range(n):
+        counts[k] = np.bincount(pool.codes[pool.offsets[k]:pool.offsets[k + 1]], minlength=alphabet_size)
+    expected = counts @ scoring.astype(np.float64) @ counts.T     # sum_ab M[a,b] c_i[a] c_j[b]
+    off = i_idx != j_idx
+    a, b = i_idx[off], j_idx[off]
+    length = res.trace_len[off].astype(np.float64)
+    s_rand = (expected[a, b] / length + res.gap_counts[off, 0] * gap_open
+              + res.gap_counts[off, 1] * gap_ext).astype(np.float32)
+    s_max = ((scores[a, a].astype(np.float64) + scores[b, b]) / 2.0).astype(np.float32)
+    s_ij = scores[a, b].astype(np.float32)
+    bad = np.nonzero(s_ij < s_rand)[0]
+    if bad.size:
+        raise ValueError(
+            f"The randomized alignment of sequences {b[bad[0]]} and {a[bad[0]]} "
+            f"scores better than the real pairwise alignment, "
+            f"cannot calculate proper pairwise distance")
+    dist = np.zeros((n, n), dtype=np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = -np.log((s_ij - s_rand) / (s_max - s_rand)).astype(np.float32)
+    dist[a, b] = d
+    dist[b, a] = d
+    return dist
 
 
 def _resolve_scoring(matrix, packed1, packed2):

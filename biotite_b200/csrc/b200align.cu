@@ -126,7 +126,8 @@ struct BtBatch {
     BtParams P{};
     DevParams D{};
     int64_t n_pairs = 0;
-    int score_only = 0;
+    int score_only = 0;   // no directions, no traceback
+    int stats = 0;        // traceback emits gap statistics, no step bytes
     int device = 0;
     Route route = ROUTE_GENERAL;
     int64_t cells = 0, launches = 0;
@@ -241,11 +242,11 @@ static cudaError_t dispatch_general_traceback(const DevParams &D, const BatchVie
     const int threads = 128;
     const int grid = (int)((count + threads - 1) / threads);
     if (D.affine) {
-        if (D.banded) general_traceback_kernel<true, true><<<grid, threads, 0, s>>>(V);
-        else general_traceback_kernel<true, false><<<grid, threads, 0, s>>>(V);
+        if (D.banded) general_traceback_kernel<true, true><<<grid, threads, 0, s>>>(D, V);
+        else general_traceback_kernel<true, false><<<grid, threads, 0, s>>>(D, V);
     } else {
-        if (D.banded) general_traceback_kernel<false, true><<<grid, threads, 0, s>>>(V);
-        else general_traceback_kernel<false, false><<<grid, threads, 0, s>>>(V);
+        if (D.banded) general_traceback_kernel<false, true><<<grid, threads, 0, s>>>(D, V);
+        else general_traceback_kernel<false, false><<<grid, threads, 0, s>>>(D, V);
     }
     return cudaGetLastError();
 }
@@ -372,7 +373,9 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     std::unique_ptr<BtBatch> b(new BtBatch());
     b->P = *params;
     b->n_pairs = n_pairs;
-    b->score_only = score_only ? 1 : 0;
+    if (score_only < 0 || score_only > 2) return fail(BT_ERR_INVALID_ARG, "score_only must be 0, 1 or 2");
+    b->score_only = score_only == 1 ? 1 : 0;
+    b->stats = score_only == 2 ? 1 : 0;
     b->device = bt_get_device();
     b->n_seq1 = n_seq1; b->n_seq2 = n_seq2;
     b->h_off1.assign(off1, off1 + n_seq1 + 1);
@@ -390,7 +393,7 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
         for (int64_t k = 0; k < n_pairs; k++)
             if (idx1[k] < 0 || idx1[k] >= n_seq1 || idx2[k] < 0 || idx2[k] >= n_seq2)
                 return fail(BT_ERR_INVALID_ARG, "pair index out of range");
-        if (!score_only) {   // step bytes of pair k start at the prefix sum of len1 + len2
+        if (score_only == 0) {   // step bytes of pair k start at the prefix sum of len1 + len2
             b->h_ops_off.resize((size_t)n_pairs);
             int64_t acc = 0;
             const PairMap hm0 = b->host_map();
@@ -426,7 +429,7 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     D.match = params->match_score; D.mismatch = params->mismatch_score;
     D.neg_inf = reference_neg_inf(*params, mn);
     D.n_rows = params->n_rows; D.n_cols = params->n_cols; D.code_bytes = params->code_bytes;
-    D.mark = 0; D.mark_value = 0; D.matrix_in_smem = 0;
+    D.mark = 0; D.mark_value = 0; D.matrix_in_smem = 0; D.stats = b->stats;
 
     CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&b->ev0));
@@ -437,7 +440,7 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     const PairMap hm = b->host_map();
     if (!force_general && interseq_eligible(*params, hm, n_pairs, mn, mx))
         b->route = ROUTE_INTERSEQ;
-    else if (!force_general && banded_eligible(*params, hm, b->h_bands, n_pairs, mn, mx))
+    else if (!force_general && !b->stats && banded_eligible(*params, hm, b->h_bands, n_pairs, mn, mx))
         b->route = ROUTE_BANDED;
 
     const size_t cb = (size_t)params->code_bytes;
@@ -471,12 +474,12 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     if (!b->score_only) {
         CUDA_TRY(b->trace_len.alloc((size_t)n_pairs * 8));
         CUDA_TRY(b->first.alloc((size_t)n_pairs * 8));
-        CUDA_TRY(b->ops.alloc((size_t)b->ops_total));
+        if (!b->stats) CUDA_TRY(b->ops.alloc((size_t)b->ops_total));
     }
 
     if (b->route == ROUTE_INTERSEQ) {
         CUDA_TRY(b->is_start.alloc((size_t)n_pairs * 8));
-        st = interseq_prepare(b->interseq, *params, hm, n_pairs, b->score_only, mn, mx,
+        st = interseq_prepare(b->interseq, *params, hm, n_pairs, b->stats ? 2 : b->score_only, mn, mx,
                               &b->cells, 1, 3, s);
         if (st == BT_ERR_OOM) return fail(st, "out of device memory (inter-sequence plan)");
         if (st) return fail(st, "inter-sequence plan failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -624,8 +627,10 @@ extern "C" int bt_batch_fetch_traces(BtBatch *b, int64_t *trace_len_out, int32_t
         CUDA_TRY(cudaMemcpyAsync(trace_len_out, b->trace_len.ptr, (size_t)b->n_pairs * 8, cudaMemcpyDeviceToHost, s));
     if (first_out)
         CUDA_TRY(cudaMemcpyAsync(first_out, b->first.ptr, (size_t)b->n_pairs * 8, cudaMemcpyDeviceToHost, s));
-    if (ops_out)
+    if (ops_out) {
+        if (b->stats) return fail(BT_ERR_INVALID_ARG, "a statistics batch has no step bytes");
         CUDA_TRY(cudaMemcpyAsync(ops_out, b->ops.ptr, (size_t)b->ops_total, cudaMemcpyDeviceToHost, s));
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
     return BT_OK;
 }
@@ -755,7 +760,7 @@ extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const 
                               uint8_t *ops_out) {
     int st = check_params(params);
     if (st) return st;
-    if (n_pairs >= 64 && off1 && off2 && params->use_matrix && matrix && !params->banded &&
+    if (n_pairs >= 64 && off1 && off2 && params->use_matrix && matrix && !params->banded && score_only != 2 &&
         bt_device_count() > 0) {
         std::vector<int64_t> h1(off1, off1 + n_pairs + 1), h2(off2, off2 + n_pairs + 1);
         const int64_t cnt = (int64_t)params->n_rows * params->n_cols;
@@ -774,8 +779,8 @@ extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const 
     st = bt_batch_run(b.get(), nullptr);
     if (st) return st;
     if (scores_out) { st = bt_batch_fetch_scores(b.get(), scores_out); if (st) return st; }
-    if (!score_only && (trace_len_out || first_out || ops_out))
-        st = bt_batch_fetch_traces(b.get(), trace_len_out, first_out, ops_out);
+    if (score_only != 1 && (trace_len_out || first_out || ops_out))
+        st = bt_batch_fetch_traces(b.get(), trace_len_out, first_out, score_only == 2 ? nullptr : ops_out);
     return st;
 }
 
@@ -818,6 +823,7 @@ extern "C" int bt_align_pair(const BtParams *params, const void *code1, int64_t 
                              BtTraceList **traces_out) {
     if (!score_out) return fail(BT_ERR_INVALID_ARG, "score_out is NULL");
     if (traces_out) *traces_out = nullptr;
+    score_only = score_only ? 1 : 0;
     if (!score_only && !traces_out) return fail(BT_ERR_INVALID_ARG, "traces_out is NULL");
     if (max_number < 1) return fail(BT_ERR_INVALID_ARG, "Maximum number of returned alignments must be at least 1");
     const int64_t off1[2] = {0, len1}, off2[2] = {0, len2};

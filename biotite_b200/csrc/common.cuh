@@ -24,6 +24,7 @@ struct DevParams {
     int mark;            // second pass of local enumeration: tag cells whose M == mark_value
     int32_t mark_value;
     int matrix_in_smem;  // matrix staged in shared memory
+    int stats;           // traceback emits GapStats (in `first`) instead of step bytes
 };
 
 // Which sequences pair p aligns.  off1/off2 are the offsets of two sequence pools; idx1/idx2
@@ -67,6 +68,35 @@ struct BatchView {
     int32_t *first;               // 2 per pair
     uint8_t *ops;                 // compact traces, pair k at off1[k]+off2[k]
     int64_t pair_begin, pair_end; // pairs handled by this launch
+};
+
+// Alignment statistics accumulated during a traceback instead of storing the step bytes:
+// number of columns and of gap-opening / gap-extending columns as counted by the
+// reference's guide-tree code (src/biotite/sequence/align/multiple.pyx:403-455 `_count_gaps`):
+// a gap column opens a gap if the previous column had no gap in that sequence, else it
+// extends one; without terminal penalty the columns before the first and after the last
+// gap-free column are ignored.  The counts do not depend on the direction of the walk.
+struct GapStats {
+    int len = 0, opens = 0, exts = 0;
+    int pend_opens = 0, pend_exts = 0;
+    int prev = -1;
+    bool inner = false;       // a gap-free column has been seen
+    bool count_terminal;
+    __host__ __device__ explicit GapStats(bool terminal) : count_terminal(terminal) {}
+    __host__ __device__ __forceinline__ void push(int op) {
+        len++;
+        if (op == OP_DIAG) {
+            opens += pend_opens; exts += pend_exts;
+            pend_opens = pend_exts = 0;
+            inner = true;
+        } else if (count_terminal || inner) {
+            if (op == prev) pend_exts++; else pend_opens++;
+        }
+        prev = op;
+    }
+    __host__ __device__ __forceinline__ void finish() {
+        if (count_terminal) { opens += pend_opens; exts += pend_exts; }
+    }
 };
 
 __host__ __device__ inline int32_t wadd(int32_t a, int32_t b) {

@@ -320,7 +320,7 @@ general_fill_kernel(const DevParams P, const BatchView V) {
 // the highest-priority step of every cell (cell.rs:125-138, :219-254; trace.rs:59-90
 // with max_number = 1) and emits one step byte per path cell, end to start.
 template <bool AFFINE, bool BANDED>
-__global__ void general_traceback_kernel(const BatchView V) {
+__global__ void general_traceback_kernel(const DevParams P, const BatchView V) {
     const int64_t p = V.pair_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= V.pair_end) return;
     const int64_t n = V.map.len1(p), m = V.map.len2(p);
@@ -328,7 +328,8 @@ __global__ void general_traceback_kernel(const BatchView V) {
     if (BANDED) rs = V.bands[2 * p + 1] - V.bands[2 * p] + 3;
     const int64_t step[3] = {BANDED ? -rs : -(rs + 1), -1, BANDED ? -rs + 1 : -rs};
     const uint8_t *dir = V.dirs + V.dir_off[p];
-    uint8_t *ops = V.ops + V.map.ops(p);
+    uint8_t *ops = P.stats ? nullptr : V.ops + V.map.ops(p);
+    GapStats gs(P.terminal != 0);
     const int64_t cap = n + m;
     int64_t idx = V.start_idx[p], last = 0, len = 0;
     int st = V.start_state[p];
@@ -356,14 +357,20 @@ __global__ void general_traceback_kernel(const BatchView V) {
             else if (d & L_GAP2) op = OP_TO2;
             else break;
         }
-        ops[len++] = (uint8_t)op;
+        if (P.stats) gs.push(op); else ops[len] = (uint8_t)op;
+        len++;
         last = idx;
         idx += step[op];
         st = ns;
     }
     V.trace_len[p] = len;
-    V.first[2 * p] = (int32_t)(last / rs);
-    V.first[2 * p + 1] = (int32_t)(last % rs);
+    if (P.stats) {
+        gs.finish();
+        V.first[2 * p] = gs.opens; V.first[2 * p + 1] = gs.exts;
+    } else {
+        V.first[2 * p] = (int32_t)(last / rs);
+        V.first[2 * p + 1] = (int32_t)(last % rs);
+    }
 }
 
 }  // namespace bt

@@ -61,6 +61,8 @@ struct InterseqConst {
     int32_t score_only;
     int32_t mode;                    // IS_GLOBAL / IS_SEMI / IS_LOCAL
     int32_t affine;                  // 0: linear gap penalty (gap_open)
+    int32_t stats;                   // traceback emits GapStats instead of step bytes
+    int32_t terminal;                // terminal gap columns count in the statistics
 };
 
 // A window is a run of consecutive pairs (in input order) that is sorted, packed, filled and
@@ -472,7 +474,10 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
     const int n = (int)A.map.len1(p), m = (int)A.map.len2(p);
     const bool traced = !C.score_only;
     const uint32_t *base = A.dirs + d.dir_off + lane * 4 + half * 2;
-    uint8_t *out = traced ? ops + A.map.ops(p) : nullptr;   // score-only batches carry no step offsets
+    // score-only and statistics batches carry no step bytes
+    uint8_t *out = (traced && !C.stats) ? ops + A.map.ops(p) : nullptr;
+    GapStats gs(C.terminal != 0);
+    auto emit = [&](int op, int &len) { if (C.stats) gs.push(op); else out[len] = (uint8_t)op; len++; };
     auto nibble = [&](int i, int j) -> uint32_t {  // 1-based table cell (i, j)
         const int rg = i - 1, s = rg / IS_R, r = rg % IS_R;
         const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 128 + (r >> 3)];
@@ -503,8 +508,8 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
         if (traced) {
             fi = n; fj = m;
             if (mc == best) { st = ST_MATCH; }
-            else if (g1 == best) { while (j > p1) { fi = i; fj = j; out[len++] = OP_TO1; j--; } st = ST_MATCH; }
-            else { while (i > p2) { fi = i; fj = j; out[len++] = OP_TO2; i--; } st = ST_MATCH; }
+            else if (g1 == best) { while (j > p1) { fi = i; fj = j; emit(OP_TO1, len); j--; } st = ST_MATCH; }
+            else { while (i > p2) { fi = i; fj = j; emit(OP_TO2, len); i--; } st = ST_MATCH; }
         }
     } else {
         i = A.start[2 * p]; j = A.start[2 * p + 1];
@@ -514,21 +519,21 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
     const int32_t *mat = A.matrix;
     while (i > 0 || j > 0) {
         if (MODE == IS_LOCAL && (i == 0 || j == 0)) break;         // boundary cells have no direction
-        if (i == 0) { fi = i; fj = j; out[len++] = OP_TO1; j--; continue; }   // first row: leading gap in sequence 1
-        if (j == 0) { fi = i; fj = j; out[len++] = OP_TO2; i--; continue; }   // first column
+        if (i == 0) { fi = i; fj = j; emit(OP_TO1, len); j--; continue; }   // first row: leading gap in sequence 1
+        if (j == 0) { fi = i; fj = j; emit(OP_TO2, len); i--; continue; }   // first column
         if (st == ST_MATCH) {
             if (MODE == IS_LOCAL) {
                 if (value <= 0) break;                              // M clamped to 0: trace ends before this cell
                 value -= mat[(int)codes1[o1 + i - 1] * C.n_cols + (int)codes2[o2 + j - 1]];
             }
             fi = i; fj = j;
-            out[len++] = OP_DIAG;
+            emit(OP_DIAG, len);
             i--; j--;
             st = h_state(i, j);
         } else if (st == ST_GAP1) {
             const uint32_t nb = nibble(i, j);
             fi = i; fj = j;
-            out[len++] = OP_TO1;
+            emit(OP_TO1, len);
             j--;
             const bool opened = (nb & 4u) != 0;
             st = opened ? ST_MATCH : ST_GAP1;
@@ -536,7 +541,7 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
         } else {
             const uint32_t nb = nibble(i, j);
             fi = i; fj = j;
-            out[len++] = OP_TO2;
+            emit(OP_TO2, len);
             i--;
             const bool opened = (nb & 8u) != 0;
             st = opened ? ST_MATCH : ST_GAP2;
@@ -544,6 +549,7 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
         }
     }
     trace_len[p] = len;
+    if (C.stats) { gs.finish(); fi = gs.opens; fj = gs.exts; }   // statistics travel in `first`
     first[2 * p] = fi;
     first[2 * p + 1] = fj;
 }
@@ -728,28 +734,31 @@ __global__ void interseq_linear_traceback_kernel(const InterseqConst C, const In
     const int64_t o1 = A.map.beg1(p), o2 = A.map.beg2(p);
     const int n = (int)A.map.len1(p), m = (int)A.map.len2(p);
     const uint32_t *base = A.dirs + d.dir_off + lane * 2 + half;
-    uint8_t *out = ops + A.map.ops(p);
+    uint8_t *out = C.stats ? nullptr : ops + A.map.ops(p);
+    GapStats gs(C.terminal != 0);
+    auto emit = [&](int op, int &len) { if (C.stats) gs.push(op); else out[len] = (uint8_t)op; len++; };
     int i = n, j = m, len = 0, fi = 0, fj = 0;
     int32_t value = 0;
     if (MODE == IS_LOCAL) { i = A.start[2 * p]; j = A.start[2 * p + 1]; value = A.score[p]; }
     while (i > 0 || j > 0) {
         if (MODE == IS_LOCAL && (i == 0 || j == 0 || value <= 0)) break;  // score <= 0: direction cleared
         fi = i; fj = j;
-        if (i == 0) { out[len++] = OP_TO1; j--; continue; }
-        if (j == 0) { out[len++] = OP_TO2; i--; continue; }
+        if (i == 0) { emit(OP_TO1, len); j--; continue; }
+        if (j == 0) { emit(OP_TO2, len); i--; continue; }
         const int rg = i - 1, s = rg / IS_R, r = rg % IS_R;
         const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 64];
         const uint32_t bits = (w >> (2 * r)) & 3u;
         if (bits & 1u) {
             if (MODE == IS_LOCAL) value -= A.matrix[(int)codes1[o1 + i - 1] * C.n_cols + (int)codes2[o2 + j - 1]];
-            out[len++] = OP_DIAG; i--; j--;
+            emit(OP_DIAG, len); i--; j--;
         } else {
             if (MODE == IS_LOCAL) value -= C.gap_open;
-            if (bits & 2u) { out[len++] = OP_TO1; j--; }
-            else { out[len++] = OP_TO2; i--; }
+            if (bits & 2u) { emit(OP_TO1, len); j--; }
+            else { emit(OP_TO2, len); i--; }
         }
     }
     trace_len[p] = len;
+    if (C.stats) { gs.finish(); fi = gs.opens; fj = gs.exts; }
     first[2 * p] = fi;
     first[2 * p + 1] = fj;
 }
@@ -834,7 +843,11 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     plan.C.gap_open = P.gap_open; plan.C.gap_ext = P.affine ? P.gap_ext : P.gap_open;
     plan.C.affine = P.affine;
     plan.C.neg = -32768 - plan.C.gap_open - plan.C.gap_ext - std::min(min_score, 0);
-    plan.C.n_rows = P.n_rows; plan.C.n_cols = P.n_cols; plan.C.score_only = score_only;
+    plan.C.n_rows = P.n_rows; plan.C.n_cols = P.n_cols;
+    plan.C.stats = score_only == 2;               // trace mode 2: statistics instead of step bytes
+    plan.C.terminal = P.terminal_penalty;
+    score_only = score_only == 1;                 // from here on: "no direction nibbles"
+    plan.C.score_only = score_only;
     plan.C.mode = P.local ? IS_LOCAL : (P.terminal_penalty ? IS_GLOBAL : IS_SEMI);
 
     const int64_t per_window = interseq_pairs_per_window(n_pairs, waves_per_window);

@@ -106,6 +106,11 @@ void bt_tracelist_free(BtTraceList *list);
  *   run     : fill + traceback kernels; *device_ms (may be NULL) receives the
  *             CUDA-event time of exactly those kernels on the batch's stream
  *   fetch_* : D2H of results
+ * score_only: 0 = scores + traces, 1 = scores only, 2 = scores + trace statistics: the
+ * traceback runs on the GPU but emits, instead of step bytes, trace_len = number of alignment
+ * columns and first[2k], first[2k+1] = number of gap-opening / gap-extending columns as the
+ * reference's guide-tree code counts them (multiple.pyx:403-455; terminal gap columns are
+ * skipped when !terminal_penalty).  Not available for banded batches.
  * Results: scores (int32 per pair) and, unless score_only, one first-optimal
  * trace per pair in compact form: trace_len[k] = L, first[2k..2k+1] = table
  * coordinates of the first alignment column's cell, ops = L step bytes

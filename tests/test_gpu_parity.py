@@ -559,3 +559,70 @@ def test_all_vs_all_scores_semi_global():
             ref = oracle_align_optimal(seqs[i], seqs[j], matrix, (-10, -1), terminal_penalty=False,
                                        score_only=True)
             assert got[i, j] == ref
+
+
+# ---- next row (f): guide-tree distances, statistics fused into the GPU traceback ----------------
+
+def _count_gaps(trace, terminal_penalty):
+    """Restatement of the reference's _count_gaps (multiple.pyx:403-455) on an (L,2) trace."""
+    if not terminal_penalty:
+        full = np.nonzero((trace != -1).all(axis=1))[0]
+        if full.size == 0:
+            return 0, 0
+        trace = trace[full[0]:full[-1] + 1]
+    opens = exts = 0
+    for col in (0, 1):
+        gap = trace[:, col] == -1
+        prev = np.concatenate(([False], gap[:-1]))
+        opens += int(np.count_nonzero(gap & ~prev))
+        exts += int(np.count_nonzero(gap & prev))
+    return opens, exts
+
+
+@pytest.mark.parametrize("term", [True, False])
+@pytest.mark.parametrize("gap", [(-10, -1), -6])
+def test_trace_statistics_mode(term, gap, route):
+    rng = np.random.default_rng(41)
+    codes1, off1, codes2, off2 = _random_batch(rng, 400, 20, 160)
+    matrix = BLOSUM().score_matrix()
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, gap, term, False, stats=True) as batch:
+        batch.run()
+        res = batch.fetch()
+    ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, matrix, gap, term, False)
+    assert np.array_equal(res.scores, ref_scores)
+    for k in range(400):
+        assert res.trace_len[k] == len(ref_traces[k])
+        assert tuple(res.gap_counts[k]) == _count_gaps(ref_traces[k], term), k
+
+
+def test_feng_doolittle_distances():
+    rng = np.random.default_rng(43)
+    base = rng.integers(0, 20, 180)
+    seqs = []
+    for k in range(12):     # a family of related sequences, as align_multiple expects
+        code = base.copy()
+        flip = rng.random(len(code)) < 0.25
+        code[flip] = rng.integers(0, 20, int(flip.sum()))
+        code = code[rng.random(len(code)) > 0.05]
+        s = bt.ProteinSequence(); s.code = code
+        seqs.append(s)
+    matrix = BLOSUM()
+    for gap, term in (((-10, -1), True), (-8, False)):
+        got = bt.feng_doolittle_distances(seqs, matrix, gap, term)
+        go, ge = gap if isinstance(gap, tuple) else (gap, gap)
+        sm = matrix.score_matrix().astype(np.float64)
+        n = len(seqs)
+        ali = {(i, j): oracle_align_optimal(seqs[i], seqs[j], matrix, gap, term, max_number=1)[0]
+               for i in range(n) for j in range(i + 1)}
+        ref = np.zeros((n, n), dtype=np.float32)
+        for i in range(n):
+            for j in range(i):
+                ci = np.bincount(seqs[i].code, minlength=24)
+                cj = np.bincount(seqs[j].code, minlength=24)
+                s_rand = (ci @ sm @ cj) / ali[i, j].trace.shape[0]
+                o, e = _count_gaps(ali[i, j].trace, term)
+                s_rand += o * go + e * ge
+                s_max = (ali[i, i].score + ali[j, j].score) / 2.0
+                ref[i, j] = ref[j, i] = -np.log((ali[i, j].score - s_rand) / (s_max - s_rand))
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-6)   # float32 path, reference tolerance
+        assert np.array_equal(got, got.T) and np.all(np.diag(got) == 0)
