@@ -42,3 +42,4 @@ from .batch import (
     align_optimal_batch,
     pack_sequences,
 )
+from .statistics import EValueEstimator

@@ -626,3 +626,47 @@ def test_feng_doolittle_distances():
                 ref[i, j] = ref[j, i] = -np.log((ali[i, j].score - s_rand) / (s_max - s_rand))
         assert np.allclose(got, ref, rtol=1e-5, atol=1e-6)   # float32 path, reference tolerance
         assert np.array_equal(got, got.T) and np.all(np.diag(got) == 0)
+
+
+# ---- next row (f) rank 2: E-value estimation from one batch of random local alignments ------------
+
+BACKGROUND = np.array([35155, 8669, 24161, 28354, 17367, 33229, 9906, 23161, 25872, 40625, 10101, 20212,
+                       23435, 19208, 23105, 32070, 26311, 29012, 5990, 14488, 0, 0, 0, 0]) / 450431
+
+
+@pytest.mark.parametrize("matrix_name,gap,ref_lam,ref_k", [
+    ("BLOSUM62", (-10000, -10000), 0.318, 0.130),
+    ("BLOSUM62", (-12, -2), 0.300, 0.090),
+    ("BLOSUM62", (-5, -5), 0.131, 0.009),
+    ("PAM250", (-16, -1), 0.172, 0.018),
+])
+def test_evalue_distribution_parameters(matrix_name, gap, ref_lam, ref_k):
+    """tests/sequence/align/test_statistics.py:46-74: parameters of Altschul et al."""
+    alphabet = bt.ProteinSequence.alphabet
+    matrix = bt.SubstitutionMatrix(alphabet, alphabet, matrix_name)
+    np.random.seed(0)
+    est = bt.EValueEstimator.from_samples(alphabet, matrix, gap, BACKGROUND, 500, 1000)
+    assert est.lam == pytest.approx(ref_lam, rel=0.1)
+    assert est.k == pytest.approx(ref_k, rel=0.6)
+    # the sampled scores are bit-exact, so the oracle estimates the very same parameters
+    np.random.seed(0)
+    code = np.random.choice(24, size=(1000, 2, 500), p=BACKGROUND / BACKGROUND.sum())
+    off = np.arange(1001, dtype=np.int64) * 500
+    ref_scores, _ = oracle.batch(code[:, 0, :].reshape(-1), off, code[:, 1, :].reshape(-1), off,
+                                 matrix.score_matrix(), gap, True, True, score_only=True)
+    lam = np.pi / np.sqrt(6 * np.var(ref_scores.astype(np.int64)))
+    assert est.lam == pytest.approx(lam, rel=1e-12)
+
+
+def test_evalue_score_scaling():
+    """test_statistics.py:118-177: scaling scores and penalties by 1000 scales lambda by 1/1000."""
+    alphabet = bt.ProteinSequence.alphabet
+    matrix = BLOSUM()
+    scaled = bt.SubstitutionMatrix(alphabet, alphabet, matrix.score_matrix() * 1000)
+    np.random.seed(0)
+    a = bt.EValueEstimator.from_samples(alphabet, matrix, (-12, -1), BACKGROUND, 300, 400)
+    np.random.seed(0)
+    b = bt.EValueEstimator.from_samples(alphabet, scaled, (-12000, -1000), BACKGROUND, 300, 400)
+    assert b.lam == pytest.approx(a.lam / 1000, rel=1e-9)
+    assert b.k == pytest.approx(a.k, rel=1e-6)
+    assert a.log_evalue(50, 300, 300 * 10000) == pytest.approx(b.log_evalue(50000, 300, 300 * 10000), rel=1e-6)
