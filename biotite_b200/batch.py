@@ -235,7 +235,7 @@ def align_batch_arrays(codes1, off1, codes2, off2, scoring, gap_penalty, termina
         ctypes.byref(params), _cabi.ptr(codes1), _cabi.ptr(off1), _cabi.ptr(codes2),
         _cabi.ptr(off2), n, _cabi.ptr(matrix), _cabi.ptr(bands), int(bool(score_only)),
         _cabi.ptr(scores), _cabi.ptr(trace_len), _cabi.ptr(first), _cabi.ptr(ops)))
-    return BatchResult(scores, trace_len, first, ops, off1 + off2, bands)
+    return BatchResult(scores, trace_len, first, ops, (off1, off2), bands)
 
 
 class BatchResult:
@@ -260,7 +260,8 @@ class BatchResult:
         self.trace_len = trace_len
         self.first = first
         self.ops = ops
-        self.ops_off = np.ascontiguousarray(ops_off, dtype=np.int64)
+        # offsets of the step bytes; may be given lazily as a (off1, off2) pair of offset arrays
+        self._ops_off = ops_off
         self.bands = bands
         self.swapped = swapped
         self.seqs1 = seqs1
@@ -269,6 +270,13 @@ class BatchResult:
 
     def __len__(self):
         return len(self.scores)
+
+    @property
+    def ops_off(self):
+        if isinstance(self._ops_off, tuple):
+            self._ops_off = self._ops_off[0] + self._ops_off[1]
+        self._ops_off = np.ascontiguousarray(self._ops_off, dtype=np.int64)
+        return self._ops_off
 
     def traces_flat(self):
         """

@@ -649,9 +649,9 @@ extern "C" void bt_batch_destroy(BtBatch *b) { delete b; }
 static int align_batch_pipelined(const BtParams *params, const void *codes1, const int64_t *off1,
                                  const void *codes2, const int64_t *off2, int64_t n_pairs,
                                  const int32_t *matrix, int32_t score_only, int32_t mn, int32_t mx,
-                                 const std::vector<int64_t> &h_off1, const std::vector<int64_t> &h_off2,
                                  int32_t *scores_out, int64_t *trace_len_out, int32_t *first_out,
                                  uint8_t *ops_out) {
+    const int64_t *h_off1 = off1, *h_off2 = off2;   // the caller's host arrays stay valid during the call
     const int64_t total1 = h_off1[n_pairs], total2 = h_off2[n_pairs];
     const bool trace = getenv("B200ALIGN_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -695,14 +695,17 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
         CUDA_TRY(cudaMemcpyAsync(d_codes1.ptr, codes1, (size_t)h_off1[first_end], cudaMemcpyHostToDevice, st.s[0]));
         CUDA_TRY(cudaMemcpyAsync(d_codes2.ptr, codes2, (size_t)h_off2[first_end], cudaMemcpyHostToDevice, st.s[0]));
     }
+    // plan the windows on worker threads while the first copies are in flight; windows are
+    // launched as soon as they are planned
     InterseqPlan plan;
-    int64_t cells = 0;
     PairMap hm;
-    hm.off1 = h_off1.data(); hm.off2 = h_off2.data();
-    int rc = interseq_prepare(plan, *params, hm, n_pairs, score_only, mn, mx, &cells, 2, 1, st.s[0]);
+    hm.off1 = h_off1; hm.off2 = h_off2;
+    interseq_setup(plan, *params, n_pairs, score_only, mn);
+    (void)mx;
+    StreamingPlanner planner(plan, hm, n_pairs, 1, params->affine != 0);
+    CUDA_TRY(planner.allocate(2));
+    planner.start();
     const double t2 = now();
-    if (rc == BT_ERR_OOM) return fail(rc, "out of device memory (inter-sequence plan)");
-    if (rc) return fail(rc, "inter-sequence plan failed");
     CUDA_TRY(cudaEventRecord(st.ready, st.s[0]));
     CUDA_TRY(cudaStreamWaitEvent(st.s[1], st.ready, 0));
 
@@ -713,9 +716,10 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
                   d_start.as<int32_t>()};
     int64_t launches = 0;
     for (size_t w = 0; w < plan.windows.size(); w++) {
-        const Window &win = plan.windows[w];
         const int slot = (int)(w & 1);
         cudaStream_t s = st.s[slot];
+        CUDA_TRY(planner.take((int64_t)w, s));
+        const Window &win = plan.windows[w];
         const int64_t a1 = h_off1[win.pair_begin], b1 = h_off1[win.pair_end];
         const int64_t a2 = h_off2[win.pair_begin], b2 = h_off2[win.pair_end];
         const int64_t np = win.pair_end - win.pair_begin;
@@ -762,15 +766,16 @@ extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const 
     if (st) return st;
     if (n_pairs >= 64 && off1 && off2 && params->use_matrix && matrix && !params->banded && score_only != 2 &&
         bt_device_count() > 0) {
-        std::vector<int64_t> h1(off1, off1 + n_pairs + 1), h2(off2, off2 + n_pairs + 1);
         const int64_t cnt = (int64_t)params->n_rows * params->n_cols;
         int32_t mn = matrix[0], mx = matrix[0];
         for (int64_t k = 1; k < cnt; k++) { mn = std::min(mn, matrix[k]); mx = std::max(mx, matrix[k]); }
         PairMap hm;
-        hm.off1 = h1.data(); hm.off2 = h2.data();
-        if (h1[0] == 0 && h2[0] == 0 && interseq_eligible(*params, hm, n_pairs, mn, mx))
+        hm.off1 = off1; hm.off2 = off2;
+        bool monotone = off1[0] == 0 && off2[0] == 0;
+        for (int64_t k = 0; k < n_pairs && monotone; k++) monotone = off1[k + 1] >= off1[k] && off2[k + 1] >= off2[k];
+        if (monotone && interseq_eligible(*params, hm, n_pairs, mn, mx))
             return align_batch_pipelined(params, codes1, off1, codes2, off2, n_pairs, matrix, score_only, mn, mx,
-                                         h1, h2, scores_out, trace_len_out, first_out, ops_out);
+                                         scores_out, trace_len_out, first_out, ops_out);
     }
     BtBatch *raw = nullptr;
     st = bt_batch_create(params, codes1, off1, codes2, off2, n_pairs, matrix, bands, score_only, &raw);

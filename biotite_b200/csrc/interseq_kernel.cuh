@@ -30,6 +30,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -835,20 +836,26 @@ inline void interseq_plan_window(WindowPlan &wp, const PairMap &hm, int64_t w0, 
     }
 }
 
-inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap &hm, int64_t n_pairs, int score_only,
-                            int32_t min_score, int32_t max_score, int64_t *cells_out, int n_slots,
-                            int waves_per_window, cudaStream_t stream) {
-    (void)max_score;
+// Kernel constants of a plan; returns the "no direction nibbles" flag of the trace mode
+// (0 = traces, 1 = score only, 2 = statistics).
+inline int interseq_setup(InterseqPlan &plan, const BtParams &P, int64_t n_pairs, int trace_mode, int32_t min_score) {
     plan.n_pairs = n_pairs;
     plan.C.gap_open = P.gap_open; plan.C.gap_ext = P.affine ? P.gap_ext : P.gap_open;
     plan.C.affine = P.affine;
     plan.C.neg = -32768 - plan.C.gap_open - plan.C.gap_ext - std::min(min_score, 0);
     plan.C.n_rows = P.n_rows; plan.C.n_cols = P.n_cols;
-    plan.C.stats = score_only == 2;               // trace mode 2: statistics instead of step bytes
+    plan.C.stats = trace_mode == 2;
     plan.C.terminal = P.terminal_penalty;
-    score_only = score_only == 1;                 // from here on: "no direction nibbles"
-    plan.C.score_only = score_only;
+    plan.C.score_only = trace_mode == 1;
     plan.C.mode = P.local ? IS_LOCAL : (P.terminal_penalty ? IS_GLOBAL : IS_SEMI);
+    return plan.C.score_only;
+}
+
+inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap &hm, int64_t n_pairs, int score_only,
+                            int32_t min_score, int32_t max_score, int64_t *cells_out, int n_slots,
+                            int waves_per_window, cudaStream_t stream) {
+    (void)max_score;
+    score_only = interseq_setup(plan, P, n_pairs, score_only, min_score);
 
     const int64_t per_window = interseq_pairs_per_window(n_pairs, waves_per_window);
     const int64_t n_windows = (n_pairs + per_window - 1) / per_window;
@@ -1011,5 +1018,105 @@ inline cudaError_t interseq_traceback_window(InterseqPlan &plan, const Window &w
     if (e == cudaSuccess) (*launches)++;
     return e;
 }
+
+// ---------------------------------------------------------------------------------------
+// Streaming plan for the pipelined one-shot path: worker threads plan the windows in order
+// while the caller already copies and launches the windows that are ready.  Scratch is sized
+// from the batch-wide longest sequences, because the exact per-window sizes are not known
+// when the first window starts.
+// ---------------------------------------------------------------------------------------
+struct StreamingPlanner {
+    InterseqPlan &plan;
+    PairMap hm;
+    int64_t n_pairs, per_window, n_windows;
+    int no_dirs, dir_words_per_lane;
+    std::vector<WindowPlan> wps;
+    std::vector<int64_t> group_begin;           // n_windows + 1
+    std::unique_ptr<std::atomic<int>[]> ready;
+    PinnedBuf staging;                          // page-locked copies of order / descriptors (async H2D)
+    std::vector<std::thread> threads;
+    std::atomic<int64_t> next{0};
+
+    StreamingPlanner(InterseqPlan &p, const PairMap &map, int64_t n, int waves, bool affine)
+        : plan(p), hm(map), n_pairs(n), no_dirs(p.C.score_only), dir_words_per_lane(affine ? 4 : 2) {
+        per_window = interseq_pairs_per_window(n_pairs, waves);
+        n_windows = (n_pairs + per_window - 1) / per_window;
+        wps.resize((size_t)n_windows);
+        ready.reset(new std::atomic<int>[(size_t)n_windows]);
+        group_begin.assign((size_t)n_windows + 1, 0);
+        for (int64_t w = 0; w < n_windows; w++) {
+            ready[(size_t)w].store(0);
+            const int64_t cnt = std::min(n_pairs, (w + 1) * per_window) - w * per_window;
+            group_begin[(size_t)w + 1] = group_begin[(size_t)w] + (cnt + 63) / 64;
+        }
+        plan.windows.assign((size_t)n_windows, Window{});
+        plan.n_groups = group_begin[(size_t)n_windows];
+    }
+    ~StreamingPlanner() {
+        for (std::thread &t : threads) t.join();
+    }
+    // device allocations: order / descriptors of all windows, `n_slots` scratch sets sized by bounds
+    cudaError_t allocate(int n_slots) {
+        int64_t nmax = 1, mmax = 1;
+        for (int64_t k = 0; k < n_pairs; k++) { nmax = std::max(nmax, hm.len1(k)); mmax = std::max(mmax, hm.len2(k)); }
+        int64_t gmax = 0;
+        for (int64_t w = 0; w < n_windows; w++) gmax = std::max(gmax, group_begin[(size_t)w + 1] - group_begin[(size_t)w]);
+        const int64_t stripes = (nmax + IS_R - 1) / IS_R;
+        plan.max_dir_words = no_dirs ? 0 : gmax * stripes * mmax * 32 * dir_words_per_lane;
+        plan.max_rowbuf = gmax * mmax * 32;
+        plan.max_rowcodes = gmax * stripes * IS_R * 32;
+        plan.max_colcodes = gmax * mmax * 32;
+        cudaError_t e;
+        if ((e = plan.d_order.alloc((size_t)plan.n_groups * 64 * 4)) != cudaSuccess) return e;
+        if ((e = plan.d_desc.alloc((size_t)plan.n_groups * sizeof(WarpDesc))) != cudaSuccess) return e;
+        if ((e = staging.alloc((size_t)plan.n_groups * (64 * 4 + sizeof(WarpDesc)))) != cudaSuccess) return e;
+        for (int sl = 0; sl < n_slots; sl++) {
+            SlotBuffers &b = plan.slots[sl];
+            if ((e = b.rowcodes.alloc((size_t)plan.max_rowcodes * 2)) != cudaSuccess) return e;
+            if ((e = b.colcodes.alloc((size_t)plan.max_colcodes * 2)) != cudaSuccess) return e;
+            if ((e = b.rowbuf.alloc((size_t)plan.max_rowbuf * 12)) != cudaSuccess) return e;
+            if ((e = b.dirs.alloc((size_t)plan.max_dir_words * 4)) != cudaSuccess) return e;
+            if (plan.C.mode == IS_SEMI) {
+                if ((e = b.lastrow.alloc((size_t)plan.max_rowbuf * 8)) != cudaSuccess) return e;
+                if ((e = b.lastcol.alloc((size_t)plan.max_rowcodes * 8)) != cudaSuccess) return e;
+            }
+        }
+        return cudaSuccess;
+    }
+    void start() {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int n_threads = (int)std::min<int64_t>(std::min<unsigned>(hw, 8u), n_windows);
+        for (int t = 0; t < n_threads; t++) {
+            threads.emplace_back([this]() {
+                for (;;) {
+                    const int64_t w = next.fetch_add(1);
+                    if (w >= n_windows) break;
+                    const int64_t w0 = w * per_window, w1 = std::min(n_pairs, w0 + per_window);
+                    WindowPlan &wp = wps[(size_t)w];
+                    interseq_plan_window(wp, hm, w0, w1, no_dirs, dir_words_per_lane);
+                    memcpy(stage_order() + group_begin[(size_t)w] * 64, wp.order.data(), wp.order.size() * 4);
+                    memcpy(stage_desc() + group_begin[(size_t)w], wp.desc.data(), wp.desc.size() * sizeof(WarpDesc));
+                    ready[(size_t)w].store(1, std::memory_order_release);
+                }
+            });
+        }
+    }
+    // blocks until window w is planned; uploads its order / descriptors on `stream`
+    cudaError_t take(int64_t w, cudaStream_t stream) {
+        while (!ready[(size_t)w].load(std::memory_order_acquire)) std::this_thread::yield();
+        WindowPlan &wp = wps[(size_t)w];
+        wp.win.group_begin = group_begin[(size_t)w];
+        wp.win.group_end = group_begin[(size_t)w + 1];
+        plan.windows[(size_t)w] = wp.win;
+        cudaError_t e = cudaMemcpyAsync(plan.d_order.as<int32_t>() + wp.win.group_begin * 64,
+                                        stage_order() + wp.win.group_begin * 64, wp.order.size() * 4,
+                                        cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(plan.d_desc.as<WarpDesc>() + wp.win.group_begin, stage_desc() + wp.win.group_begin,
+                               wp.desc.size() * sizeof(WarpDesc), cudaMemcpyHostToDevice, stream);
+    }
+    int32_t *stage_order() const { return staging.as<int32_t>(); }
+    WarpDesc *stage_desc() const { return (WarpDesc *)(staging.as<char>() + (size_t)plan.n_groups * 64 * 4); }
+};
 
 }  // namespace bt

@@ -68,6 +68,55 @@ private:
     size_t cached_bytes_ = 0;
 };
 
+// Page-locked host staging buffers, cached the same way (cudaHostAlloc costs milliseconds).
+class PinnedPool {
+public:
+    static PinnedPool &instance() {
+        static PinnedPool pool;
+        return pool;
+    }
+    cudaError_t acquire(void **ptr, size_t bytes) {
+        const size_t size = DevicePool::round_up(bytes);
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            auto &bucket = free_[size];
+            if (!bucket.empty()) {
+                *ptr = bucket.back();
+                bucket.pop_back();
+                return cudaSuccess;
+            }
+        }
+        return cudaHostAlloc(ptr, size, cudaHostAllocDefault);
+    }
+    void release(void *ptr, size_t bytes) {
+        if (!ptr) return;
+        std::lock_guard<std::mutex> lock(mutex_);
+        free_[DevicePool::round_up(bytes)].push_back(ptr);
+    }
+
+private:
+    std::mutex mutex_;
+    std::map<size_t, std::vector<void *>> free_;
+};
+
+struct PinnedBuf {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    ~PinnedBuf() { if (ptr) PinnedPool::instance().release(ptr, bytes); }
+    cudaError_t alloc(size_t n) {
+        if (ptr) PinnedPool::instance().release(ptr, bytes);
+        ptr = nullptr;
+        if (n == 0) n = 1;
+        cudaError_t e = PinnedPool::instance().acquire(&ptr, n);
+        bytes = e == cudaSuccess ? n : 0;
+        return e;
+    }
+    template <class T> T *as() const { return (T *)ptr; }
+};
+
 // RAII device buffer backed by the pool.
 struct DevBuf {
     void *ptr = nullptr;
