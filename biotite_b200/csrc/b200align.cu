@@ -691,7 +691,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     CUDA_TRY(cudaMemcpyAsync(d_off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.s[0]));
     CUDA_TRY(cudaMemcpyAsync(d_matrix.ptr, matrix, mb, cudaMemcpyHostToDevice, st.s[0]));
     {
-        const int64_t first_end = std::min(n_pairs, interseq_pairs_per_window(n_pairs, 1));
+        const int64_t first_end = std::min(n_pairs, interseq_pairs_per_window(n_pairs, 2));
         CUDA_TRY(cudaMemcpyAsync(d_codes1.ptr, codes1, (size_t)h_off1[first_end], cudaMemcpyHostToDevice, st.s[0]));
         CUDA_TRY(cudaMemcpyAsync(d_codes2.ptr, codes2, (size_t)h_off2[first_end], cudaMemcpyHostToDevice, st.s[0]));
     }
@@ -702,7 +702,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     hm.off1 = h_off1; hm.off2 = h_off2;
     interseq_setup(plan, *params, n_pairs, score_only, mn);
     (void)mx;
-    StreamingPlanner planner(plan, hm, n_pairs, 1, params->affine != 0);
+    StreamingPlanner planner(plan, hm, n_pairs, 2, params->affine != 0);
     CUDA_TRY(planner.allocate(2));
     planner.start();
     const double t2 = now();
