@@ -670,3 +670,59 @@ def test_evalue_score_scaling():
     assert b.lam == pytest.approx(a.lam / 1000, rel=1e-9)
     assert b.k == pytest.approx(a.k, rel=1e-6)
     assert a.log_evalue(50, 300, 300 * 10000) == pytest.approx(b.log_evalue(50000, 300, 300 * 10000), rel=1e-6)
+
+
+# ---- packed kernels: ragged edge cases ---------------------------------------------------------------
+
+@pytest.mark.parametrize("gap", [(-10, -1), -7])
+@pytest.mark.parametrize("local,term", [(False, True), (False, False), (True, True)])
+def test_packed_kernels_ragged_lengths(gap, local, term, monkeypatch):
+    """Lengths 1..40 next to 1900..2000 (the packed route's limit), a pair count that is not a
+    multiple of the group size, all 24 protein symbols incl. B, Z, X and *."""
+    if isinstance(gap, int) and not local and not term:
+        pytest.skip("linear semi-global has no packed kernel")
+    monkeypatch.setenv("B200ALIGN_ROUTE", "packed")
+    rng = np.random.default_rng(51)
+    n_pairs = 203
+    len1 = np.where(rng.random(n_pairs) < 0.85, rng.integers(1, 40, n_pairs), rng.integers(1900, 2001, n_pairs))
+    len2 = np.where(rng.random(n_pairs) < 0.85, rng.integers(1, 40, n_pairs), rng.integers(1900, 2001, n_pairs))
+    off1 = np.concatenate(([0], np.cumsum(len1))).astype(np.int64)
+    off2 = np.concatenate(([0], np.cumsum(len2))).astype(np.int64)
+    codes1 = rng.integers(0, 24, off1[-1]).astype(np.uint8)
+    codes2 = rng.integers(0, 24, off2[-1]).astype(np.uint8)
+    for k in range(0, n_pairs, 4):   # some homologous pairs, including long ones
+        n = int(min(len1[k], len2[k]))
+        codes2[off2[k]:off2[k] + n] = codes1[off1[k]:off1[k] + n]
+    matrix = BLOSUM().score_matrix()
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, gap, term, local) as batch:
+        assert batch.kernel == "interseq_s16x2"
+        batch.run()
+        res = batch.fetch()
+    ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, matrix, gap, term, local)
+    assert np.array_equal(res.scores, ref_scores)
+    traces = res.traces()
+    for k in range(n_pairs):
+        assert np.array_equal(traces[k], ref_traces[k]), (k, len1[k], len2[k])
+
+
+def test_packed_kernels_nucleotide_matrix_and_range_guard(monkeypatch):
+    """The 15x15 NUC matrix through the packed kernels; a batch whose scores could leave the
+    16-bit range must be refused by the packed route even when it is forced."""
+    monkeypatch.setenv("B200ALIGN_ROUTE", "packed")
+    rng = np.random.default_rng(53)
+    codes1, off1, codes2, off2 = _random_batch(rng, 130, 50, 400, alphabet=15)
+    matrix = NUC().score_matrix()
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, (-10, -1), True, False) as batch:
+        assert batch.kernel == "interseq_s16x2"
+        batch.run()
+        res = batch.fetch()
+    ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, matrix, (-10, -1), True, False)
+    assert np.array_equal(res.scores, ref_scores)
+    assert all(np.array_equal(a, b) for a, b in zip(res.traces(), ref_traces))
+    big = (matrix * 100).astype(np.int32)   # 400 x 500 per match > 32767
+    with bt.DeviceBatch(codes1, off1, codes2, off2, big, (-1000, -100), True, False) as batch:
+        assert batch.kernel == "general_i32"
+        batch.run()
+        res = batch.fetch()
+    ref_scores, _ = oracle.batch(codes1, off1, codes2, off2, big, (-1000, -100), True, False, score_only=True)
+    assert np.array_equal(res.scores, ref_scores)
