@@ -254,6 +254,7 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
 
     int32_t best_lo = 0, best_hi = 0;          // optimum (local: running maximum of M)
     int32_t bidx_lo = 0, bidx_hi = 0;          // local: row-major index i*(m+1)+j of the first optimum
+    int32_t brow_lo = 0, brow_hi = 0;          // ... and its row
     uint32_t best2 = 0;                        // local score-only: packed running maximum
     for (int s = 0; s < d.stripes; s++) {
         const int r0 = s * IS_R;  // rows r0+1 .. r0+R of the DP table
@@ -409,7 +410,11 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                     slow = !inside;
                     if (inside) {
                         const int c_lo = (int16_t)(cm & 0xffffu), c_hi = (int16_t)(cm >> 16);
-                        slow = (c_lo >= best_lo && c_lo > 0) || (c_hi >= best_hi && c_hi > 0);
+                        // a new optimum, or a tie that could precede the current first optimum in
+                        // row-major order (only possible while that optimum lies in this stripe)
+                        slow = c_lo > best_lo || c_hi > best_hi ||
+                               (c_lo == best_lo && c_lo > 0 && brow_lo > r0 + 1) ||
+                               (c_hi == best_hi && c_hi > 0 && brow_hi > r0 + 1);
                     }
                 }
                 if (slow) {
@@ -419,11 +424,11 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                         const int v_lo = (int16_t)(Ml[r] & 0xffffu), v_hi = (int16_t)(Ml[r] >> 16);
                         if (row <= n_lo && col <= m_lo) {
                             const int idx = row * (m_lo + 1) + col;
-                            if (v_lo > best_lo || (v_lo == best_lo && v_lo > 0 && idx < bidx_lo)) { best_lo = v_lo; bidx_lo = idx; }
+                            if (v_lo > best_lo || (v_lo == best_lo && v_lo > 0 && idx < bidx_lo)) { best_lo = v_lo; bidx_lo = idx; brow_lo = row; }
                         }
                         if (row <= n_hi && col <= m_hi) {
                             const int idx = row * (m_hi + 1) + col;
-                            if (v_hi > best_hi || (v_hi == best_hi && v_hi > 0 && idx < bidx_hi)) { best_hi = v_hi; bidx_hi = idx; }
+                            if (v_hi > best_hi || (v_hi == best_hi && v_hi > 0 && idx < bidx_hi)) { best_hi = v_hi; bidx_hi = idx; brow_hi = row; }
                         }
                     }
                 }
@@ -593,7 +598,7 @@ interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
     uint32_t *rb_s = A.rowbuf + d.rowbuf_off * 3 + lane;
     uint2 *dir = TRACED ? (uint2 *)(A.dirs + d.dir_off) + lane : nullptr;
 
-    int32_t best_lo = 0, best_hi = 0, bidx_lo = 0, bidx_hi = 0;
+    int32_t best_lo = 0, best_hi = 0, bidx_lo = 0, bidx_hi = 0, brow_lo = 0, brow_hi = 0;
     uint32_t best2 = 0;
     for (int s = 0; s < d.stripes; s++) {
         const int r0 = s * IS_R;
@@ -686,7 +691,11 @@ interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                     slow = !inside;
                     if (inside) {
                         const int c_lo = (int16_t)(cm & 0xffffu), c_hi = (int16_t)(cm >> 16);
-                        slow = (c_lo >= best_lo && c_lo > 0) || (c_hi >= best_hi && c_hi > 0);
+                        // a new optimum, or a tie that could precede the current first optimum in
+                        // row-major order (only possible while that optimum lies in this stripe)
+                        slow = c_lo > best_lo || c_hi > best_hi ||
+                               (c_lo == best_lo && c_lo > 0 && brow_lo > r0 + 1) ||
+                               (c_hi == best_hi && c_hi > 0 && brow_hi > r0 + 1);
                     }
                 }
                 if (slow) {
@@ -696,11 +705,11 @@ interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                         const int v_lo = (int16_t)(Sl[r] & 0xffffu), v_hi = (int16_t)(Sl[r] >> 16);
                         if (row <= n_lo && col <= m_lo) {
                             const int idx = row * (m_lo + 1) + col;
-                            if (v_lo > best_lo || (v_lo == best_lo && v_lo > 0 && idx < bidx_lo)) { best_lo = v_lo; bidx_lo = idx; }
+                            if (v_lo > best_lo || (v_lo == best_lo && v_lo > 0 && idx < bidx_lo)) { best_lo = v_lo; bidx_lo = idx; brow_lo = row; }
                         }
                         if (row <= n_hi && col <= m_hi) {
                             const int idx = row * (m_hi + 1) + col;
-                            if (v_hi > best_hi || (v_hi == best_hi && v_hi > 0 && idx < bidx_hi)) { best_hi = v_hi; bidx_hi = idx; }
+                            if (v_hi > best_hi || (v_hi == best_hi && v_hi > 0 && idx < bidx_hi)) { best_hi = v_hi; bidx_hi = idx; brow_hi = row; }
                         }
                     }
                 }
