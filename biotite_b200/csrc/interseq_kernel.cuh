@@ -44,7 +44,22 @@ constexpr int IS_R = 16;            // rows per stripe
 constexpr int IS_THREADS = 128;     // 4 warps per block
 constexpr int IS_MAX_LEN = 2000;    // longest sequence routed here
 constexpr int IS_ROWW = 128;        // bytes per table entry row: 32 lanes x 4 bytes
-constexpr int IS_PREFETCH = 6;      // columns of L2 prefetch distance for the row buffer
+#ifndef BT_L2PF
+#define BT_L2PF 6
+#endif
+constexpr int IS_PREFETCH = BT_L2PF;  // columns of L2 prefetch distance for the row buffer
+#ifndef BT_ACC_SPLIT
+#define BT_ACC_SPLIT 2
+#endif
+#ifndef BT_PF_TRACED
+#define BT_PF_TRACED 3
+#endif
+#ifndef BT_PF_SCORE
+#define BT_PF_SCORE 2
+#endif
+constexpr int IS_WARPS_PER_SM = 9;  // affine kernels: one warp per block, 24 KiB of profile each
+constexpr int IS_SLACK = 32;        // columns of slack behind the row buffer / column codes: the
+                                    // column loop reads ahead without bounds checks
 
 // One group of 64 pairs handled by one warp.
 struct WarpDesc {
@@ -111,7 +126,11 @@ inline bool interseq_eligible(const BtParams &P, const PairMap &hm, int64_t n_pa
     if (P.banded || !P.use_matrix) return false;
     if (!P.affine && !P.local && !P.terminal_penalty) return false;  // linear semi-global: general kernel
     if (P.code_bytes != 1 || n_pairs < 64) return false;
-    if ((int64_t)P.n_rows * P.n_cols * IS_ROWW > 96 * 1024 || P.n_rows > 255 || P.n_cols > 255) return false;
+    if (P.n_rows > 255 || P.n_cols > 255) return false;
+    if (P.affine) {
+        // stripe profile of signed bytes: 1 KiB per column letter and warp
+        if (min_score < -128 || max_score > 127 || P.n_cols > 128) return false;
+    } else if ((int64_t)P.n_rows * P.n_cols * IS_ROWW > 96 * 1024) return false;  // per-lane score table
     int64_t nmax = 0, mmax = 0;
     for (int64_t k = 0; k < n_pairs; k++) {
         const int64_t n = hm.len1(k), m = hm.len2(k);
@@ -192,6 +211,20 @@ __global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes
 
 enum : int { IS_GLOBAL = 0, IS_SEMI = 1, IS_LOCAL = 2 };
 
+// v[idx] for a run-time idx in 0..15 as a select tree over the bits of idx (the obvious chain
+// of 16 compares makes ptxas keep 32 loop-invariant predicates alive across the column loop,
+// which starves the predicate-producing VIMNMX instructions)
+__device__ __forceinline__ uint32_t bt_pick16(const uint32_t (&v)[16], int idx) {
+    uint32_t a[8], b[4], c[2];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = (idx & 1) ? v[2 * k + 1] : v[2 * k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) b[k] = (idx & 2) ? a[2 * k + 1] : a[2 * k];
+#pragma unroll
+    for (int k = 0; k < 2; k++) c[k] = (idx & 4) ? b[2 * k + 1] : b[2 * k];
+    return (idx & 8) ? c[1] : c[0];
+}
+
 // Per-window scratch and per-batch result pointers handed to the kernels.
 struct InterseqArgs {
     const WarpDesc *desc;
@@ -213,21 +246,15 @@ struct InterseqArgs {
 // traceback kernel from the captured border M values, see there), IS_LOCAL = Smith-Waterman
 // (M clamped at 0, :659-666; clamping the gap states is not needed for scores or for the
 // first-priority trace because M >= 0 always wins a tie against a non-positive gap state).
-template <int MODE, bool TRACED>
-__global__ void __launch_bounds__(IS_THREADS, 3)
+template <int MODE, bool TRACED, int PF>
+__global__ void __launch_bounds__(32, IS_WARPS_PER_SM)
 interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
-    extern __shared__ uint32_t table[];  // [b][a][lane]: zero-extended s16 score, one copy per lane
-    const int lane = threadIdx.x & 31;
-    {
-        const int entries = C.n_rows * C.n_cols;
-        for (int e = threadIdx.x >> 5; e < entries; e += IS_THREADS / 32) {
-            const int a = e / C.n_cols, b = e % C.n_cols;
-            table[(b * C.n_rows + a) * 32 + lane] = (uint32_t)A.matrix[e] & 0xffffu;
-        }
-    }
-    __syncthreads();
-    const int64_t g = (int64_t)blockIdx.x * (IS_THREADS / 32) + (threadIdx.x >> 5);
-    if (g >= A.n_groups) return;
+    // One warp per block.  Shared memory: the stripe profile prof[half][b][lane][16 rows] (one
+    // signed byte per row: the score of the stripe's row letter against column letter b),
+    // rebuilt for every stripe from the matrix in global memory (L1-resident).
+    extern __shared__ uint4 smem_prof[];
+    const int lane = threadIdx.x;
+    const int64_t g = blockIdx.x;
     const WarpDesc d = A.desc[g];
     const int32_t p_lo = A.order[g * 64 + 2 * lane], p_hi = A.order[g * 64 + 2 * lane + 1];
     int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
@@ -237,14 +264,14 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
     const uint32_t ext2 = ((uint32_t)C.gap_ext & 0xffffu) * 0x10001u;
     const uint32_t open2 = ((uint32_t)C.gap_open & 0xffffu) * 0x10001u;
     const uint32_t neg2 = ((uint32_t)C.neg & 0xffffu) * 0x10001u;
-    const uint32_t col_stride = (uint32_t)C.n_rows * IS_ROWW;  // bytes between column letters
-    const char *tbase = (const char *)table + lane * 4;
+    // this lane's 16 profile bytes of (half, letter b): pbase + (half * n_cols + b) * 512
+    const uint32_t pbase = (uint32_t)__cvta_generic_to_shared(smem_prof) + lane * 16;
+    const uint32_t pbase_hi = pbase + (uint32_t)C.n_cols * 512u;
 
     const uint16_t *rc = A.rowcodes + d.rowcode_off + lane;
     const uint16_t *cc = A.colcodes + d.colcode_off + lane;
-    uint32_t *rb_m = A.rowbuf + d.rowbuf_off * 3 + lane;            // [j][lane] planes: M, F2, H
-    uint32_t *rb_f = rb_m + (int64_t)d.mmax * 32;
-    uint32_t *rb_h = rb_f + (int64_t)d.mmax * 32;
+    // row buffer: [j][plane][lane], planes M, F2, H of the row above the current stripe
+    uint32_t *const rb = A.rowbuf + d.rowbuf_off * 3 + lane;
     uint4 *dir = TRACED ? (uint4 *)(A.dirs + d.dir_off) + lane : nullptr;
     // two planes each (low / high pair): their last rows / columns are captured at different times
     uint32_t *lastrow_lo = MODE == IS_SEMI ? A.lastrow + d.rowbuf_off * 2 + lane : nullptr;
@@ -256,6 +283,17 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
     int32_t bidx_lo = 0, bidx_hi = 0;          // local: row-major index i*(m+1)+j of the first optimum
     int32_t brow_lo = 0, brow_hi = 0;          // ... and its row
     uint32_t best2 = 0;                        // local score-only: packed running maximum
+    // Row 0 of the table (pairwise.rs:747-780: M = G2 = -inf, H = G1 = open + (j-1)*ext, or 0
+    // without terminal penalty / local) goes through the row buffer like every other stripe
+    // boundary, so that the column loop below is the same for all stripes.
+    {
+        uint32_t h_row0 = MODE == IS_GLOBAL ? open2 : 0u;
+        uint32_t *w = rb;
+        for (int j = 0; j < d.mmax; j++, w += 96) {
+            w[0] = neg2; w[32] = neg2; w[64] = h_row0;
+            if (MODE == IS_GLOBAL) h_row0 = __vadd2(h_row0, ext2);
+        }
+    }
     for (int s = 0; s < d.stripes; s++) {
         const int r0 = s * IS_R;  // rows r0+1 .. r0+R of the DP table
         // column step at which this stripe holds the end cell (n, m) of the low / high pair
@@ -265,12 +303,36 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
         const int rl_lo = (n_lo - 1) / IS_R == s ? (n_lo - 1) % IS_R : -1;
         const int rl_hi = (n_hi - 1) / IS_R == s ? (n_hi - 1) % IS_R : -1;
         const bool rows_valid = r0 + IS_R <= n_lo && r0 + IS_R <= n_hi;  // no padding rows in this stripe
-        uint32_t rp_lo[IS_R], rp_hi[IS_R], Ml[IS_R], F1l[IS_R], Hl[IS_R];
+        uint32_t Ml[IS_R], F1l[IS_R], Hl[IS_R];
+        {
+            // profile of this stripe: byte r of prof[half][b][lane] = matrix[row letter r][b]
+            uint32_t a_lo[IS_R], a_hi[IS_R];
+#pragma unroll
+            for (int r = 0; r < IS_R; r++) {
+                const uint32_t v = rc[(r0 + r) * 32];
+                a_lo[r] = (v & 0xffu) * (uint32_t)C.n_cols;   // row offset in the matrix
+                a_hi[r] = (v >> 8) * (uint32_t)C.n_cols;
+            }
+            __syncwarp();
+            for (int b = 0; b < C.n_cols; b++) {
+                const int32_t *col = A.matrix + b;
+                uint32_t w_lo[4], w_hi[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    w_lo[q] = w_hi[q] = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        w_lo[q] |= ((uint32_t)__ldg(col + a_lo[4 * q + k]) & 0xffu) << (8 * k);
+                        w_hi[q] |= ((uint32_t)__ldg(col + a_hi[4 * q + k]) & 0xffu) << (8 * k);
+                    }
+                }
+                smem_prof[b * 32 + lane] = make_uint4(w_lo[0], w_lo[1], w_lo[2], w_lo[3]);
+                smem_prof[(C.n_cols + b) * 32 + lane] = make_uint4(w_hi[0], w_hi[1], w_hi[2], w_hi[3]);
+            }
+            __syncwarp();
+        }
 #pragma unroll
         for (int r = 0; r < IS_R; r++) {
-            const uint32_t v = rc[(int64_t)(r0 + r) * 32];
-            rp_lo[r] = (v & 0xffu) * IS_ROWW;
-            rp_hi[r] = (v >> 8) * IS_ROWW;
             // column 0 (pairwise.rs:707-745): M = G1 = -inf, H = G2 = open + (i-1)*ext
             // (semi-global / local: H = 0)
             Ml[r] = neg2;
@@ -280,52 +342,64 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
         // H(r0, 0): the origin for the first stripe, else column 0 of the row above
         uint32_t hu_prev = (s == 0 || MODE != IS_GLOBAL)
                                ? 0u : ((uint32_t)(C.gap_open + (r0 - 1) * C.gap_ext) & 0xffffu) * 0x10001u;
-        uint32_t h_row0 = MODE == IS_GLOBAL ? open2 : 0u;  // H(0, j) = open + (j-1)*ext (pairwise.rs:747-780) or 0
-        uint32_t nxt = cc[0];
-        // the row above the stripe is prefetched one column ahead: its L2/HBM latency hides
-        // behind the 16 rows of the current column
-        uint32_t nx_m = neg2, nx_f = neg2, nx_h = 0;
-        if (s > 0) { nx_m = rb_m[0]; nx_f = rb_f[0]; nx_h = rb_h[0]; }
-        for (int j = 0; j < d.mmax; j++) {
-            const uint32_t v = nxt;
-            uint32_t up_m = nx_m, up_f2 = nx_f, hu = nx_h;
-            if (s > 0 && j + IS_PREFETCH < d.mmax) {
-                // pull the row buffer towards L2 well ahead of the register prefetch below
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb_m + (int64_t)(j + IS_PREFETCH) * 32));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb_f + (int64_t)(j + IS_PREFETCH) * 32));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb_h + (int64_t)(j + IS_PREFETCH) * 32));
+        // The row above the stripe and the column letters are fetched PF columns ahead (their
+        // L2 / HBM latency hides behind PF x 16 rows of work); reads past the group's last
+        // column land in the slack behind the buffers and are never used.
+        const uint16_t *ccp = cc;
+        uint32_t *rbp = rb;
+        uint4 *dirp = TRACED ? dir + (int64_t)s * d.mmax * 32 : nullptr;
+        uint32_t q_c[PF], q_m[PF], q_f[PF], q_h[PF];
+#pragma unroll
+        for (int k = 0; k < PF; k++) {
+            q_c[k] = ccp[k * 32]; q_m[k] = rbp[k * 96]; q_f[k] = rbp[k * 96 + 32]; q_h[k] = rbp[k * 96 + 64];
+        }
+        // the column loop is unrolled PF times so that the look-ahead registers need no rotation
+        // (a register move would wait for the load it forwards)
+        for (int j0 = 0; j0 < d.mmax; j0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            const int j = j0 + u;
+            if (u > 0 && j >= d.mmax) break;
+            const uint32_t v = q_c[u];
+            uint32_t up_m = q_m[u], up_f2 = q_f[u];
+            const uint32_t hu = q_h[u];
+            q_c[u] = ccp[PF * 32];
+            q_m[u] = rbp[PF * 96]; q_f[u] = rbp[PF * 96 + 32]; q_h[u] = rbp[PF * 96 + 64];
+            if (IS_PREFETCH > 0) {
+                // pull the row buffer towards L2 well ahead of the register prefetch
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rbp + (PF + IS_PREFETCH) * 96));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rbp + (PF + IS_PREFETCH) * 96 + 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rbp + (PF + IS_PREFETCH) * 96 + 64));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ccp + (PF + IS_PREFETCH) * 32));
             }
-            if (j + 1 < d.mmax) {
-                nxt = cc[(int64_t)(j + 1) * 32];
-                if (s > 0) {
-                    nx_m = rb_m[(int64_t)(j + 1) * 32]; nx_f = rb_f[(int64_t)(j + 1) * 32];
-                    nx_h = rb_h[(int64_t)(j + 1) * 32];
-                }
-            }
-            const char *t_lo = tbase + (v & 0xffu) * col_stride;
-            const char *t_hi = tbase + (v >> 8) * col_stride;
-            if (s == 0) {
-                hu = h_row0;
-                if (MODE == IS_GLOBAL) h_row0 = __vadd2(h_row0, ext2);
-            }
+            // the 16 + 16 profile bytes of this column's letters
+            uint32_t pl[4], ph[4];
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(pl[0]), "=r"(pl[1]), "=r"(pl[2]), "=r"(pl[3]) : "r"(pbase + (v & 0xffu) * 512u));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(ph[0]), "=r"(ph[1]), "=r"(ph[2]), "=r"(ph[3]) : "r"(pbase_hi + (v >> 8) * 512u));
             // Rows are software-pipelined so that every state array is updated in place:
             // F1 and M of row r+1 are formed (from the previous column's M and H) before
             // H of row r overwrites Hl[r].
-            uint32_t acc[4] = {0, 0, 0, 0};  // nibbles: lo rows 0-7, lo rows 8-15, hi rows 0-7, hi rows 8-15
+            // direction nibbles: lo rows 0-7, lo rows 8-15, hi rows 0-7, hi rows 8-15; one set of
+            // accumulators per predicate (BT_ACC_SPLIT) shortens the chains of dependent adds
+            uint32_t acc[4 * BT_ACC_SPLIT] = {};
             uint32_t sim[IS_R];
 #pragma unroll
             for (int r = 0; r < IS_R; r++) {
-                const uint32_t s_lo = *(const uint32_t *)(t_lo + rp_lo[r]);
-                const uint32_t s_hi = *(const uint32_t *)(t_hi + rp_hi[r]);
-                sim[r] = s_hi * 65536u + s_lo;
+                // sign-extend byte r of the low / high pair's profile into the two 16-bit halves
+                constexpr uint32_t k = 0;
+                const uint32_t sel = (uint32_t)(r & 3) * 0x1111u + 0xC480u;
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(sim[r]) : "r"(pl[r >> 2]), "r"(ph[r >> 2]), "r"(sel));
+                (void)k;
             }
-#define BT_ACC_LO(r) acc[(r) >> 3]
-#define BT_ACC_HI(r) acc[2 + ((r) >> 3)]
+#define BT_ACC_LO(r, b) acc[((b) % BT_ACC_SPLIT) * 4 + ((r) >> 3)]
+#define BT_ACC_HI(r, b) acc[((b) % BT_ACC_SPLIT) * 4 + 2 + ((r) >> 3)]
 #define BT_BIT(r, b) ((1u << (b)) << (4 * ((r) & 7)))
 #define BT_ROW_F1_M(r, diag_h)                                                               \
     {                                                                                        \
         const uint32_t fe = __vadd2(F1l[r], ext2);                                           \
-        if (TRACED) { BT_MAX_PRED(F1l[r], Ml[r], fe, BT_ACC_LO(r), BT_ACC_HI(r), BT_BIT(r, 2)); } \
+        if (TRACED) { BT_MAX_PRED(F1l[r], Ml[r], fe, BT_ACC_LO(r, 2), BT_ACC_HI(r, 2), BT_BIT(r, 2)); } \
         else F1l[r] = __vmaxs2(Ml[r], fe);                                                   \
         Ml[r] = MODE == IS_LOCAL ? __viaddmax_s16x2(diag_h, sim[r], 0u) : __vadd2(diag_h, sim[r]); \
     }
@@ -337,29 +411,31 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                 const uint32_t fv = __vadd2(up_f2, ext2);
                 if (TRACED) {
                     uint32_t t;
-                    BT_MAX_PRED(up_f2, up_m, fv, BT_ACC_LO(r), BT_ACC_HI(r), BT_BIT(r, 3));     // o2
-                    BT_MAX_PRED(t, F1l[r], up_f2, BT_ACC_LO(r), BT_ACC_HI(r), BT_BIT(r, 1));   // hG
+                    BT_MAX_PRED(up_f2, up_m, fv, BT_ACC_LO(r, 3), BT_ACC_HI(r, 3), BT_BIT(r, 3));     // o2
+                    BT_MAX_PRED(t, F1l[r], up_f2, BT_ACC_LO(r, 1), BT_ACC_HI(r, 1), BT_BIT(r, 1));   // hG
                     const uint32_t to = __vadd2(t, open2);
-                    BT_MAX_PRED(Hl[r], Ml[r], to, BT_ACC_LO(r), BT_ACC_HI(r), BT_BIT(r, 0));   // hM
+                    BT_MAX_PRED(Hl[r], Ml[r], to, BT_ACC_LO(r, 0), BT_ACC_HI(r, 0), BT_BIT(r, 0));   // hM
                 } else {
                     up_f2 = __vmaxs2(up_m, fv);
                     Hl[r] = __viaddmax_s16x2(__vmaxs2(F1l[r], up_f2), open2, Ml[r]);
                 }
                 up_m = Ml[r];
             }
-            if (s + 1 < d.stripes) {
-                rb_m[(int64_t)j * 32] = up_m; rb_f[(int64_t)j * 32] = up_f2; rb_h[(int64_t)j * 32] = Hl[IS_R - 1];
+            rbp[0] = up_m; rbp[32] = up_f2; rbp[64] = Hl[IS_R - 1];
+            if (TRACED) {
+#pragma unroll
+                for (int k = 1; k < BT_ACC_SPLIT; k++) {
+                    acc[0] |= acc[4 * k]; acc[1] |= acc[4 * k + 1]; acc[2] |= acc[4 * k + 2]; acc[3] |= acc[4 * k + 3];
+                }
+                *dirp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+                dirp += 32;
             }
-            if (TRACED) dir[((int64_t)s * d.mmax + j) * 32] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
 
             if (MODE == IS_GLOBAL) {
                 // optimum: H(n, m) (pairwise.rs:866-879)
                 if (j == j_lo || j == j_hi) {
-#pragma unroll
-                    for (int r = 0; r < IS_R; r++) {
-                        if (j == j_lo && r0 + r + 1 == n_lo) best_lo = (int16_t)(Hl[r] & 0xffffu);
-                        if (j == j_hi && r0 + r + 1 == n_hi) best_hi = (int16_t)(Hl[r] >> 16);
-                    }
+                    if (j == j_lo) best_lo = (int16_t)(bt_pick16(Hl, rl_lo) & 0xffffu);
+                    if (j == j_hi) best_hi = (int16_t)(bt_pick16(Hl, rl_hi) >> 16);
                 }
             } else if (MODE == IS_SEMI) {
                 // border capture: M along the pair's last row and last column
@@ -433,6 +509,8 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                     }
                 }
             }
+            ccp += 32; rbp += 96;
+        }
         }
     }
     if (MODE == IS_LOCAL && !TRACED) {
@@ -912,8 +990,8 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     for (int sl = 0; sl < n_slots; sl++) {
         SlotBuffers &b = plan.slots[sl];
         if ((e = b.rowcodes.alloc((size_t)plan.max_rowcodes * 2)) != cudaSuccess) goto fail;
-        if ((e = b.colcodes.alloc((size_t)plan.max_colcodes * 2)) != cudaSuccess) goto fail;
-        if ((e = b.rowbuf.alloc((size_t)plan.max_rowbuf * 12)) != cudaSuccess) goto fail;
+        if ((e = b.colcodes.alloc((size_t)(plan.max_colcodes + IS_SLACK * 32) * 2)) != cudaSuccess) goto fail;
+        if ((e = b.rowbuf.alloc((size_t)(plan.max_rowbuf + IS_SLACK * 32) * 12)) != cudaSuccess) goto fail;
         if ((e = b.dirs.alloc((size_t)plan.max_dir_words * 4)) != cudaSuccess) goto fail;
         if (plan.C.mode == IS_SEMI) {
             if ((e = b.lastrow.alloc((size_t)plan.max_rowbuf * 8)) != cudaSuccess) goto fail;
@@ -952,13 +1030,20 @@ inline cudaError_t interseq_launch_linear_fill(const InterseqConst &C, const Int
     return cudaGetLastError();
 }
 
+// register prefetch distance (columns) of the row above the stripe: the score-only kernels spend
+// less time per column and have registers to spare, so they look further ahead
+template <bool TRACED> constexpr int interseq_pf() { return TRACED ? BT_PF_TRACED : BT_PF_SCORE; }
+
 template <int MODE, bool TRACED>
-inline cudaError_t interseq_launch_fill(const InterseqConst &C, const InterseqArgs &A, unsigned grid, size_t smem,
-                                        cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(interseq_fill_kernel<MODE, TRACED>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+inline cudaError_t interseq_launch_fill(const InterseqConst &C, const InterseqArgs &A, cudaStream_t stream) {
+    // profile: 2 halves x n_cols letters x 32 lanes x 16 rows
+    const size_t smem = (size_t)2 * C.n_cols * 512;
+    auto kernel = interseq_fill_kernel<MODE, TRACED, interseq_pf<TRACED>()>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    interseq_fill_kernel<MODE, TRACED><<<grid, IS_THREADS, smem, stream>>>(C, A);
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    kernel<<<(unsigned)A.n_groups, 32, smem, stream>>>(C, A);
     return cudaGetLastError();
 }
 
@@ -988,16 +1073,16 @@ inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, i
     }
     switch (plan.C.mode) {
     case IS_GLOBAL:
-        e = traced ? interseq_launch_fill<IS_GLOBAL, true>(plan.C, A, grid, smem, stream)
-                   : interseq_launch_fill<IS_GLOBAL, false>(plan.C, A, grid, smem, stream);
+        e = traced ? interseq_launch_fill<IS_GLOBAL, true>(plan.C, A, stream)
+                   : interseq_launch_fill<IS_GLOBAL, false>(plan.C, A, stream);
         break;
     case IS_SEMI:
-        e = traced ? interseq_launch_fill<IS_SEMI, true>(plan.C, A, grid, smem, stream)
-                   : interseq_launch_fill<IS_SEMI, false>(plan.C, A, grid, smem, stream);
+        e = traced ? interseq_launch_fill<IS_SEMI, true>(plan.C, A, stream)
+                   : interseq_launch_fill<IS_SEMI, false>(plan.C, A, stream);
         break;
     default:
-        e = traced ? interseq_launch_fill<IS_LOCAL, true>(plan.C, A, grid, smem, stream)
-                   : interseq_launch_fill<IS_LOCAL, false>(plan.C, A, grid, smem, stream);
+        e = traced ? interseq_launch_fill<IS_LOCAL, true>(plan.C, A, stream)
+                   : interseq_launch_fill<IS_LOCAL, false>(plan.C, A, stream);
         break;
     }
     if (e == cudaSuccess) (*launches)++;
@@ -1082,8 +1167,8 @@ struct StreamingPlanner {
         for (int sl = 0; sl < n_slots; sl++) {
             SlotBuffers &b = plan.slots[sl];
             if ((e = b.rowcodes.alloc((size_t)plan.max_rowcodes * 2)) != cudaSuccess) return e;
-            if ((e = b.colcodes.alloc((size_t)plan.max_colcodes * 2)) != cudaSuccess) return e;
-            if ((e = b.rowbuf.alloc((size_t)plan.max_rowbuf * 12)) != cudaSuccess) return e;
+            if ((e = b.colcodes.alloc((size_t)(plan.max_colcodes + IS_SLACK * 32) * 2)) != cudaSuccess) return e;
+            if ((e = b.rowbuf.alloc((size_t)(plan.max_rowbuf + IS_SLACK * 32) * 12)) != cudaSuccess) return e;
             if ((e = b.dirs.alloc((size_t)plan.max_dir_words * 4)) != cudaSuccess) return e;
             if (plan.C.mode == IS_SEMI) {
                 if ((e = b.lastrow.alloc((size_t)plan.max_rowbuf * 8)) != cudaSuccess) return e;
