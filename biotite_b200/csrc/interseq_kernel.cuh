@@ -878,29 +878,69 @@ struct WindowPlan {
     int64_t cells = 0;
 };
 
-// Sort one window by (len1, len2) (two stable counting passes over 16-bit keys), deal the
-// pairs to groups of 64 - longest first, because the block scheduler hands out groups in
-// index order and the tail of a window should consist of its cheapest groups - and lay out
-// the window's scratch.
-inline void interseq_plan_window(WindowPlan &wp, const PairMap &hm, int64_t w0, int64_t w1, int score_only,
-                                 int dir_words_per_lane) {
-    const int64_t cnt = w1 - w0;
-    std::vector<int32_t> tmp((size_t)cnt), sorted((size_t)cnt), count(IS_MAX_LEN + 2, 0);
-    for (int64_t k = w0; k < w1; k++) count[(size_t)hm.len2(k) + 1]++;
+// Pair ids `ids[0..cnt)` sorted by (len1, len2) ascending: two stable counting passes.
+inline void interseq_sort_pairs(const PairMap &hm, const int32_t *ids, int64_t id0, int64_t cnt,
+                                std::vector<int32_t> &sorted) {
+    std::vector<int32_t> tmp((size_t)cnt), count(IS_MAX_LEN + 2, 0);
+    sorted.resize((size_t)cnt);
+    auto id = [&](int64_t q) -> int32_t { return ids ? ids[q] : (int32_t)(id0 + q); };
+    for (int64_t q = 0; q < cnt; q++) count[(size_t)hm.len2(id(q)) + 1]++;
     for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
-    for (int64_t k = w0; k < w1; k++) tmp[(size_t)count[(size_t)hm.len2(k)]++] = (int32_t)k;
+    for (int64_t q = 0; q < cnt; q++) { const int32_t k = id(q); tmp[(size_t)count[(size_t)hm.len2(k)]++] = k; }
     std::fill(count.begin(), count.end(), 0);
-    for (int64_t k = w0; k < w1; k++) count[(size_t)hm.len1(k) + 1]++;
+    for (int64_t q = 0; q < cnt; q++) count[(size_t)hm.len1(id(q)) + 1]++;
     for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
     for (int64_t q = 0; q < cnt; q++) {
         const int32_t k = tmp[(size_t)q];
         sorted[(size_t)count[(size_t)hm.len1(k)]++] = k;
     }
+}
+
+// Lay out one window: its pairs are sorted by (len1, len2) (unless `presorted` already holds
+// them in ascending order) and dealt to groups of 64 - longest first, because the block
+// scheduler hands out groups in index order and the tail of a window should consist of its
+// cheapest groups.  A streamed window is the run of consecutive pairs [w0, w1); a resident
+// batch is sorted as a whole first, so that the groups of one window cost about the same.
+// Cost (row steps of the fill kernel) of the group of 64 slots starting at `slots`.
+inline int64_t interseq_group_cost(const PairMap &hm, const int32_t *slots) {
+    int64_t nmax = 1, mmax = 1;
+    for (int q = 0; q < 64; q++) {
+        if (slots[q] < 0) continue;
+        nmax = std::max<int64_t>(nmax, hm.len1(slots[q])); mmax = std::max<int64_t>(mmax, hm.len2(slots[q]));
+    }
+    return (nmax + IS_R - 1) / IS_R * mmax;
+}
+
+// Reorder whole groups of `order` (64 slots each) by descending cost (stable).
+inline void interseq_order_groups_by_cost(const PairMap &hm, std::vector<int32_t> &order) {
+    const int64_t groups = (int64_t)order.size() / 64;
+    std::vector<int64_t> cost((size_t)groups);
+    std::vector<int32_t> perm((size_t)groups);
+    for (int64_t g = 0; g < groups; g++) { cost[(size_t)g] = interseq_group_cost(hm, order.data() + g * 64); perm[(size_t)g] = (int32_t)g; }
+    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return cost[(size_t)a] > cost[(size_t)b]; });
+    std::vector<int32_t> out(order.size());
+    for (int64_t g = 0; g < groups; g++) memcpy(out.data() + g * 64, order.data() + (int64_t)perm[(size_t)g] * 64, 64 * 4);
+    order.swap(out);
+}
+
+inline void interseq_plan_window(WindowPlan &wp, const PairMap &hm, int64_t w0, int64_t w1, int score_only,
+                                 int dir_words_per_lane, const int32_t *slots = nullptr, int64_t n_slot_ids = 0) {
     Window &win = wp.win;
     win.pair_begin = w0; win.pair_end = w1;
-    const int64_t groups = (cnt + 63) / 64;
-    wp.order.assign((size_t)groups * 64, -1);
-    std::copy(sorted.rbegin(), sorted.rend(), wp.order.begin());
+    int64_t groups;
+    if (slots) {
+        // resident batch: the groups were formed and ordered globally (interseq_prepare)
+        groups = n_slot_ids / 64;
+        wp.order.assign(slots, slots + n_slot_ids);
+    } else {
+        const int64_t cnt = w1 - w0;
+        std::vector<int32_t> sorted;
+        interseq_sort_pairs(hm, nullptr, w0, cnt, sorted);
+        groups = (cnt + 63) / 64;
+        wp.order.assign((size_t)groups * 64, -1);
+        std::copy(sorted.rbegin(), sorted.rend(), wp.order.begin());
+        interseq_order_groups_by_cost(hm, wp.order);
+    }
     wp.desc.resize((size_t)groups);
     for (int64_t g = 0; g < groups; g++) {
         int nmax = 1, mmax = 1;
@@ -947,6 +987,18 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     const int64_t per_window = interseq_pairs_per_window(n_pairs, waves_per_window);
     const int64_t n_windows = (n_pairs + per_window - 1) / per_window;
     std::vector<WindowPlan> wps((size_t)n_windows);
+    // The whole batch is resident: sort it globally by (len1, len2), form the groups of 64, order
+    // the groups by descending cost and cut the windows from that list, so that the groups of a
+    // window cost about the same and no window waits for a straggler.
+    std::vector<int32_t> global;
+    const int64_t groups_per_window = per_window / 64;
+    if (n_windows > 1) {
+        std::vector<int32_t> sorted;
+        interseq_sort_pairs(hm, nullptr, 0, n_pairs, sorted);
+        global.assign((size_t)((n_pairs + 63) / 64 * 64), -1);
+        std::copy(sorted.rbegin(), sorted.rend(), global.begin());
+        interseq_order_groups_by_cost(hm, global);
+    }
     {
         // windows are independent: plan them on a few host threads
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -957,7 +1009,13 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
                 const int64_t w = next.fetch_add(1);
                 if (w >= n_windows) break;
                 const int64_t w0 = w * per_window, w1 = std::min(n_pairs, w0 + per_window);
-                interseq_plan_window(wps[(size_t)w], hm, w0, w1, score_only, P.affine ? 4 : 2);
+                if (global.empty()) {
+                    interseq_plan_window(wps[(size_t)w], hm, w0, w1, score_only, P.affine ? 4 : 2);
+                } else {
+                    const int64_t g0 = w * groups_per_window * 64;
+                    const int64_t g1 = std::min<int64_t>((int64_t)global.size(), g0 + groups_per_window * 64);
+                    interseq_plan_window(wps[(size_t)w], hm, w0, w1, score_only, P.affine ? 4 : 2, global.data() + g0, g1 - g0);
+                }
             }
         };
         std::vector<std::thread> threads;
