@@ -52,9 +52,8 @@ GAP = (-10, -1)
 ALGO_LANE_INSTR_PER_CELL = 3.0  # affine 3-state recurrence, s16x2 DPX: 6 instr / 2 cells
 DIR_BYTES_PER_CELL = 0.5        # 4-bit first-optimal directions
 # dram__bytes_read.sum + dram__bytes_write.sum of one interseq_fill_kernel<GLOBAL,traced> launch over
-# 3.619e10 cells: 15.82 GB + 32.08 GB (profiles/r01_interseq_fill_ncu_full.txt, ncu --set full)
-NCU_DRAM_BYTES_PER_CELL = (15.815499e9 + 32.083982e9) / 3.6188e10
-
+# 3.015e10 cells: 11.25 GB + 22.71 GB (profiles/r01_interseq_fill_v3_ncu_full.txt, ncu --set full)
+NCU_DRAM_BYTES_PER_CELL = (11.250585e9 + 22.706602e9) / 3.015e10
 
 def make_c2(n_pairs, seed):
     """BASELINE config 2: lengths N(300,30^2) clipped to [200,400]; the second sequence is a
@@ -361,7 +360,7 @@ def main():
         "peak_s32_dpx": peak[1] * 1e-12, "peak_dual_issue": peak[2] * 1e-12,
         "traffic": NCU_DRAM_BYTES_PER_CELL * cells / n_fill_launches,
         "traffic_note": "bytes per fill launch scaled from the ncu --set full capture in profiles/ "
-                        "(1.32 B/cell: 0.5 direction nibbles + row buffer write/read)",
+                        "(1.13 B/cell: 0.5 direction nibbles + row buffer write/read + packed codes)",
         "hbm": {"bound": "hbm", "achieved": cells * DIR_BYTES_PER_CELL / fill_s * 1e-9,
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
                 "frac": cells * DIR_BYTES_PER_CELL / fill_s * 1e-9 / hbm_peak,

@@ -649,8 +649,8 @@ extern "C" void bt_batch_destroy(BtBatch *b) { delete b; }
 static int align_batch_pipelined(const BtParams *params, const void *codes1, const int64_t *off1,
                                  const void *codes2, const int64_t *off2, int64_t n_pairs,
                                  const int32_t *matrix, int32_t score_only, int32_t mn, int32_t mx,
-                                 int32_t *scores_out, int64_t *trace_len_out, int32_t *first_out,
-                                 uint8_t *ops_out) {
+                                 const PairScan &scan, int32_t *scores_out, int64_t *trace_len_out,
+                                 int32_t *first_out, uint8_t *ops_out) {
     const int64_t *h_off1 = off1, *h_off2 = off2;   // the caller's host arrays stay valid during the call
     const int64_t total1 = h_off1[n_pairs], total2 = h_off2[n_pairs];
     const bool trace = getenv("B200ALIGN_TRACE") != nullptr;
@@ -690,11 +690,6 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     CUDA_TRY(cudaMemcpyAsync(d_off1.ptr, off1, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.s[0]));
     CUDA_TRY(cudaMemcpyAsync(d_off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.s[0]));
     CUDA_TRY(cudaMemcpyAsync(d_matrix.ptr, matrix, mb, cudaMemcpyHostToDevice, st.s[0]));
-    {
-        const int64_t first_end = std::min(n_pairs, interseq_pairs_per_window(n_pairs, 2));
-        CUDA_TRY(cudaMemcpyAsync(d_codes1.ptr, codes1, (size_t)h_off1[first_end], cudaMemcpyHostToDevice, st.s[0]));
-        CUDA_TRY(cudaMemcpyAsync(d_codes2.ptr, codes2, (size_t)h_off2[first_end], cudaMemcpyHostToDevice, st.s[0]));
-    }
     // plan the windows on worker threads while the first copies are in flight; windows are
     // launched as soon as they are planned
     InterseqPlan plan;
@@ -702,8 +697,15 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     hm.off1 = h_off1; hm.off2 = h_off2;
     interseq_setup(plan, *params, n_pairs, score_only, mn);
     (void)mx;
-    StreamingPlanner planner(plan, hm, n_pairs, 2, params->affine != 0);
-    CUDA_TRY(planner.allocate(2));
+    const char *waves_env = getenv("B200ALIGN_WAVES");
+    const int waves = waves_env ? std::max(1, atoi(waves_env)) : 2;
+    StreamingPlanner planner(plan, hm, n_pairs, waves, params->affine != 0);
+    {
+        const int64_t first_end = planner.bounds[1];
+        CUDA_TRY(cudaMemcpyAsync(d_codes1.ptr, codes1, (size_t)h_off1[first_end], cudaMemcpyHostToDevice, st.s[0]));
+        CUDA_TRY(cudaMemcpyAsync(d_codes2.ptr, codes2, (size_t)h_off2[first_end], cudaMemcpyHostToDevice, st.s[0]));
+    }
+    CUDA_TRY(planner.allocate(2, scan.nmax, scan.mmax));
     planner.start();
     const double t2 = now();
     CUDA_TRY(cudaEventRecord(st.ready, st.s[0]));
@@ -771,10 +773,10 @@ extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const 
         for (int64_t k = 1; k < cnt; k++) { mn = std::min(mn, matrix[k]); mx = std::max(mx, matrix[k]); }
         PairMap hm;
         hm.off1 = off1; hm.off2 = off2;
-        bool monotone = off1[0] == 0 && off2[0] == 0;
-        for (int64_t k = 0; k < n_pairs && monotone; k++) monotone = off1[k + 1] >= off1[k] && off2[k + 1] >= off2[k];
-        if (monotone && interseq_eligible(*params, hm, n_pairs, mn, mx))
-            return align_batch_pipelined(params, codes1, off1, codes2, off2, n_pairs, matrix, score_only, mn, mx,
+        // every length in [1, IS_MAX_LEN] (checked by the scan) makes the offsets monotone
+        const PairScan scan = interseq_scan(hm, n_pairs);
+        if (off1[0] == 0 && off2[0] == 0 && interseq_eligible(*params, hm, n_pairs, mn, mx, &scan))
+            return align_batch_pipelined(params, codes1, off1, codes2, off2, n_pairs, matrix, score_only, mn, mx, scan,
                                          scores_out, trace_len_out, first_out, ops_out);
     }
     BtBatch *raw = nullptr;

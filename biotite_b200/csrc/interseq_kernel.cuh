@@ -121,8 +121,44 @@ struct InterseqIO {
 // ---------------------------------------------------------------------------------------
 // eligibility: proven-exact 16-bit range (see DESIGN.md "16-bit safety")
 // ---------------------------------------------------------------------------------------
+// One threaded pass over the pair lengths: everything routing and allocation need to know.
+struct PairScan {
+    bool in_range = true;      // 1 <= len <= IS_MAX_LEN for every sequence
+    int64_t nmax = 0, mmax = 0;
+    double total = 0.0, max_pair = 0.0, max_diag = 0.0;
+};
+
+inline PairScan interseq_scan(const PairMap &hm, int64_t n_pairs) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(hw, 8u), n_pairs / 65536));
+    std::vector<PairScan> part((size_t)n_threads);
+    auto work = [&](int t) {
+        PairScan r;
+        const int64_t k0 = n_pairs * t / n_threads, k1 = n_pairs * (t + 1) / n_threads;
+        for (int64_t k = k0; k < k1; k++) {
+            const int64_t n = hm.len1(k), m = hm.len2(k);
+            if (n < 1 || m < 1 || n > IS_MAX_LEN || m > IS_MAX_LEN) r.in_range = false;
+            r.nmax = std::max(r.nmax, n); r.mmax = std::max(r.mmax, m);
+            const double c = (double)n * (double)m;
+            r.total += c; r.max_pair = std::max(r.max_pair, c); r.max_diag = std::max(r.max_diag, (double)(n + m));
+        }
+        part[(size_t)t] = r;
+    };
+    std::vector<std::thread> threads;
+    for (int t = 1; t < n_threads; t++) threads.emplace_back(work, t);
+    work(0);
+    for (std::thread &t : threads) t.join();
+    PairScan r;
+    for (const PairScan &q : part) {
+        r.in_range = r.in_range && q.in_range;
+        r.nmax = std::max(r.nmax, q.nmax); r.mmax = std::max(r.mmax, q.mmax);
+        r.total += q.total; r.max_pair = std::max(r.max_pair, q.max_pair); r.max_diag = std::max(r.max_diag, q.max_diag);
+    }
+    return r;
+}
+
 inline bool interseq_eligible(const BtParams &P, const PairMap &hm, int64_t n_pairs, int32_t min_score,
-                              int32_t max_score) {
+                              int32_t max_score, const PairScan *scan_in = nullptr) {
     if (P.banded || !P.use_matrix) return false;
     if (!P.affine && !P.local && !P.terminal_penalty) return false;  // linear semi-global: general kernel
     if (P.code_bytes != 1 || n_pairs < 64) return false;
@@ -131,31 +167,22 @@ inline bool interseq_eligible(const BtParams &P, const PairMap &hm, int64_t n_pa
         // stripe profile of signed bytes: 1 KiB per column letter and warp
         if (min_score < -128 || max_score > 127 || P.n_cols > 128) return false;
     } else if ((int64_t)P.n_rows * P.n_cols * IS_ROWW > 96 * 1024) return false;  // per-lane score table
-    int64_t nmax = 0, mmax = 0;
-    for (int64_t k = 0; k < n_pairs; k++) {
-        const int64_t n = hm.len1(k), m = hm.len2(k);
-        if (n < 1 || m < 1 || n > IS_MAX_LEN || m > IS_MAX_LEN) return false;
-        nmax = std::max(nmax, n); mmax = std::max(mmax, m);
-    }
+    const PairScan scan = scan_in ? *scan_in : interseq_scan(hm, n_pairs);
+    if (!scan.in_range) return false;
+    const int64_t nmax = scan.nmax, mmax = scan.mmax;
     // Routing by a simple cost model: the packed kernel runs one group of 64 pairs per warp,
     // so a batch with few groups leaves most of the chip idle; the general kernel runs one
     // block per pair and is bound by ~1.2 us per anti-diagonal.  Measured rates on B200:
-    // ~1.0e9 cells/s per resident warp (1776 warps) for the packed kernel, ~9e10 cells/s for a
-    // full grid of the general kernel.
+    // ~1.0e9 cells/s per resident warp for the packed kernel, ~9e10 cells/s for a full grid of
+    // the general kernel.
     // B200ALIGN_ROUTE=packed|general overrides the cost model (tests exercise both routes on the
     // same inputs); the exactness conditions below always apply.
     const char *forced = getenv("B200ALIGN_ROUTE");
     if (forced && strcmp(forced, "general") == 0) return false;
     if (!(forced && strcmp(forced, "packed") == 0)) {
-        double total = 0.0, max_pair = 0.0, max_diag = 0.0;
-        for (int64_t k = 0; k < n_pairs; k++) {
-            const double n = (double)hm.len1(k), m = (double)hm.len2(k);
-            total += n * m; max_pair = std::max(max_pair, n * m); max_diag = std::max(max_diag, n + m);
-        }
-        const double groups = (double)((n_pairs + 63) / 64);
-        const double t_packed = std::max(64.0 * max_pair / 1.0e9, total / 1.8e12) * (groups > 1776.0 ? 1.0 : 1.0);
+        const double t_packed = std::max(64.0 * scan.max_pair / 1.0e9, scan.total / 1.8e12);
         const double waves = std::ceil((double)n_pairs / 888.0);
-        const double t_general = std::max(total / 9.0e10, max_diag * 1.2e-6 * waves);
+        const double t_general = std::max(scan.total / 9.0e10, scan.max_diag * 1.2e-6 * waves);
         if (t_general < t_packed) return false;
     }
     const int64_t open = P.gap_open, ext = P.affine ? P.gap_ext : P.gap_open;
@@ -1181,6 +1208,7 @@ struct StreamingPlanner {
     InterseqPlan &plan;
     PairMap hm;
     int64_t n_pairs, per_window, n_windows;
+    std::vector<int64_t> bounds;                // pair range of window w: [bounds[w], bounds[w + 1])
     int no_dirs, dir_words_per_lane;
     std::vector<WindowPlan> wps;
     std::vector<int64_t> group_begin;           // n_windows + 1
@@ -1192,13 +1220,27 @@ struct StreamingPlanner {
     StreamingPlanner(InterseqPlan &p, const PairMap &map, int64_t n, int waves, bool affine)
         : plan(p), hm(map), n_pairs(n), no_dirs(p.C.score_only), dir_words_per_lane(affine ? 4 : 2) {
         per_window = interseq_pairs_per_window(n_pairs, waves);
-        n_windows = (n_pairs + per_window - 1) / per_window;
+        // A short first window lets the kernels start while most of the input is still on its
+        // way, a short last window shortens the final device-to-host copy nobody overlaps.
+        bounds.push_back(0);
+        if (n_pairs > 3 * per_window) {
+            const int64_t edge = (per_window / 4 + 63) / 64 * 64;
+            bounds.push_back(edge);
+            const int64_t inner = n_pairs - 2 * edge, k = std::max<int64_t>(1, (inner + per_window - 1) / per_window);
+            const int64_t step = ((inner + k - 1) / k + 63) / 64 * 64;
+            for (int64_t q = 1; q < k; q++) bounds.push_back(edge + q * step);
+            bounds.push_back(n_pairs - edge);
+        } else {
+            for (int64_t q = per_window; q < n_pairs; q += per_window) bounds.push_back(q);
+        }
+        bounds.push_back(n_pairs);
+        n_windows = (int64_t)bounds.size() - 1;
         wps.resize((size_t)n_windows);
         ready.reset(new std::atomic<int>[(size_t)n_windows]);
         group_begin.assign((size_t)n_windows + 1, 0);
         for (int64_t w = 0; w < n_windows; w++) {
             ready[(size_t)w].store(0);
-            const int64_t cnt = std::min(n_pairs, (w + 1) * per_window) - w * per_window;
+            const int64_t cnt = bounds[(size_t)w + 1] - bounds[(size_t)w];
             group_begin[(size_t)w + 1] = group_begin[(size_t)w] + (cnt + 63) / 64;
         }
         plan.windows.assign((size_t)n_windows, Window{});
@@ -1208,9 +1250,7 @@ struct StreamingPlanner {
         for (std::thread &t : threads) t.join();
     }
     // device allocations: order / descriptors of all windows, `n_slots` scratch sets sized by bounds
-    cudaError_t allocate(int n_slots) {
-        int64_t nmax = 1, mmax = 1;
-        for (int64_t k = 0; k < n_pairs; k++) { nmax = std::max(nmax, hm.len1(k)); mmax = std::max(mmax, hm.len2(k)); }
+    cudaError_t allocate(int n_slots, int64_t nmax, int64_t mmax) {
         int64_t gmax = 0;
         for (int64_t w = 0; w < n_windows; w++) gmax = std::max(gmax, group_begin[(size_t)w + 1] - group_begin[(size_t)w]);
         const int64_t stripes = (nmax + IS_R - 1) / IS_R;
@@ -1243,7 +1283,7 @@ struct StreamingPlanner {
                 for (;;) {
                     const int64_t w = next.fetch_add(1);
                     if (w >= n_windows) break;
-                    const int64_t w0 = w * per_window, w1 = std::min(n_pairs, w0 + per_window);
+                    const int64_t w0 = bounds[(size_t)w], w1 = bounds[(size_t)w + 1];
                     WindowPlan &wp = wps[(size_t)w];
                     interseq_plan_window(wp, hm, w0, w1, no_dirs, dir_words_per_lane);
                     memcpy(stage_order() + group_begin[(size_t)w] * 64, wp.order.data(), wp.order.size() * 4);
