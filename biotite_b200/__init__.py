@@ -43,3 +43,5 @@ from .batch import (
     pack_sequences,
 )
 from .statistics import EValueEstimator
+from .cigar import CigarOp, read_alignment_from_cigar, write_alignment_to_cigar
+from .fasta import alignment_from_fasta, alignment_to_fasta, alignments_to_fasta

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "bt_last_error", "bt_version", "bt_device_count", "bt_set_device", "bt_get_device",
     "bt_align_pair", "bt_tracelist_count", "bt_tracelist_length", "bt_tracelist_copy",
     "bt_tracelist_free", "bt_batch_create", "bt_batch_create_indexed", "bt_batch_ops_bytes", "bt_batch_run", "bt_batch_fetch_scores",
-    "bt_batch_fetch_traces", "bt_batch_timings", "bt_microbench", "bt_batch_cells", "bt_batch_launches", "bt_batch_kernel",
+    "bt_batch_fetch_traces", "bt_batch_fetch_cigar", "bt_batch_fetch_gapped", "bt_batch_timings", "bt_microbench", "bt_batch_cells", "bt_batch_launches", "bt_batch_kernel",
     "bt_batch_destroy", "bt_align_batch", "bt_expand_traces", "bt_pinned_alloc",
     "bt_pinned_free", "bt_pool_trim",
 ]
@@ -97,6 +97,8 @@ def load():
     lib.bt_batch_run.argtypes = [_vp, ctypes.POINTER(ctypes.c_float)]
     lib.bt_batch_fetch_scores.argtypes = [_vp, _vp]
     lib.bt_batch_fetch_traces.argtypes = [_vp, _vp, _vp, _vp]
+    lib.bt_batch_fetch_cigar.argtypes = [_vp, _i32, _vp, _vp, _vp]
+    lib.bt_batch_fetch_gapped.argtypes = [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]
     lib.bt_batch_timings.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     lib.bt_microbench.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     lib.bt_batch_cells.restype = _i64

@@ -184,6 +184,56 @@ class DeviceBatch:
             return result
         return BatchResult(scores, trace_len, first, ops, self._ops_offsets(), self.bands)
 
+    # ---- wire formats emitted on the device (csrc/emit_kernel.cuh) ---------------------------
+    def cigars(self, distinguish_matches=False, hard_clip=False, include_terminal_gaps=False,
+               as_string=True, swapped=None):
+        """
+        CIGAR of every pair of a traced batch after :meth:`run`, produced on the GPU from the
+        compact traces: the batched ``write_alignment_to_cigar`` (reference
+        ``align/cigar.py:196-392``; reference = first, segment = second sequence).  Returns a
+        list of strings, or of ``(n, 2)`` ``(operation, length)`` arrays if not `as_string`.
+        """
+        from . import cigar as _cigar
+        n = self.n_pairs
+        total = int(self._lib.bt_batch_ops_bytes(self._handle))
+        n_ops = np.empty(n, dtype=np.int32)
+        words = np.empty(total, dtype=np.uint32)
+        flags = (1 if distinguish_matches else 0) | (2 if hard_clip else 0) | (4 if include_terminal_gaps else 0)
+        swapped = None if swapped is None else np.ascontiguousarray(swapped, dtype=np.uint8)
+        _cabi.check(self._lib.bt_batch_fetch_cigar(self._handle, flags, _cabi.ptr(swapped),
+                                                   _cabi.ptr(n_ops), _cabi.ptr(words)))
+        off = self._ops_offsets()
+        return (_cigar.cigar_strings if as_string else _cigar.cigar_arrays)(n_ops, words, off)
+
+    def gapped_sequences(self, alphabet1, alphabet2=None, swapped=None, as_bytes=False):
+        """
+        The two gapped strings of every pair (``Alignment.get_gapped_sequences``, reference
+        ``align/alignment.py:233-243``), written by the GPU from the compact traces.  The
+        alphabets must consist of single characters.  Returns a list of ``(str, str)``.
+        """
+        alphabet2 = alphabet1 if alphabet2 is None else alphabet2
+        tables = []
+        for alphabet in (alphabet1, alphabet2):
+            symbols = [str(x) for x in alphabet.get_symbols()]
+            if any(len(x) != 1 for x in symbols):
+                raise ValueError("The alphabet uses symbols other than single characters")
+            tables.append(np.frombuffer("".join(symbols).encode("latin-1"), dtype=np.uint8).copy())
+        n = self.n_pairs
+        total = int(self._lib.bt_batch_ops_bytes(self._handle))
+        n_cols = np.empty(n, dtype=np.int64)
+        g1 = np.empty(total, dtype=np.uint8)
+        g2 = np.empty(total, dtype=np.uint8)
+        swapped = None if swapped is None else np.ascontiguousarray(swapped, dtype=np.uint8)
+        _cabi.check(self._lib.bt_batch_fetch_gapped(
+            self._handle, _cabi.ptr(tables[0]), len(tables[0]), _cabi.ptr(tables[1]), len(tables[1]),
+            _cabi.ptr(swapped), _cabi.ptr(n_cols), _cabi.ptr(g1), _cabi.ptr(g2)))
+        off = self._ops_offsets()
+        if as_bytes:
+            return n_cols, g1, g2, off
+        b1, b2 = g1.tobytes(), g2.tobytes()
+        return [(b1[off[k]:off[k] + n_cols[k]].decode("latin-1"), b2[off[k]:off[k] + n_cols[k]].decode("latin-1"))
+                for k in range(n)]
+
     def close(self):
         if self._handle is not None:
             self._lib.bt_batch_destroy(self._handle)

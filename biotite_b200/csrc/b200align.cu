@@ -24,6 +24,7 @@
 #include "interseq_kernel.cuh"
 #include "banded_kernel.cuh"
 #include "microbench.cuh"
+#include "emit_kernel.cuh"
 
 using namespace bt;
 
@@ -632,6 +633,77 @@ extern "C" int bt_batch_fetch_traces(BtBatch *b, int64_t *trace_len_out, int32_t
         CUDA_TRY(cudaMemcpyAsync(ops_out, b->ops.ptr, (size_t)b->ops_total, cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
+    return BT_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// wire formats straight from the device-resident compact traces (emit_kernel.cuh)
+// ---------------------------------------------------------------------------------------
+static int emit_args(BtBatch *b, const uint8_t *swapped, DevBuf &d_swapped, EmitArgs *A) {
+    if (!b) return fail(BT_ERR_INVALID_ARG, "batch is NULL");
+    if (b->score_only || b->stats) return fail(BT_ERR_INVALID_ARG, "the batch holds no traces");
+    if (!b->ran) return fail(BT_ERR_INVALID_ARG, "bt_batch_run has not been called");
+    CUDA_TRY(cudaSetDevice(b->device));
+    if (swapped) {
+        CUDA_TRY(d_swapped.alloc((size_t)b->n_pairs));
+        CUDA_TRY(cudaMemcpyAsync(d_swapped.ptr, swapped, (size_t)b->n_pairs, cudaMemcpyHostToDevice, b->stream));
+    }
+    A->codes1 = b->codes1.ptr; A->codes2 = b->codes2.ptr;
+    A->map = b->dev_map();
+    A->bands = b->P.banded ? b->bands.as<int64_t>() : nullptr;
+    A->swapped = swapped ? d_swapped.as<uint8_t>() : nullptr;
+    A->trace_len = b->trace_len.as<int64_t>(); A->first = b->first.as<int32_t>(); A->ops = b->ops.as<uint8_t>();
+    A->code_bytes = b->P.code_bytes;
+    A->n_pairs = b->n_pairs;
+    return BT_OK;
+}
+
+extern "C" int bt_batch_fetch_cigar(BtBatch *b, int32_t flags, const uint8_t *swapped, int32_t *n_ops_out,
+                                    uint32_t *cigar_out) {
+    if (!n_ops_out || !cigar_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    DevBuf d_swapped, d_nops, d_cigar;
+    EmitArgs A{};
+    int st = emit_args(b, swapped, d_swapped, &A);
+    if (st) return st;
+    if (b->n_pairs == 0) return BT_OK;
+    CUDA_TRY(d_nops.alloc((size_t)b->n_pairs * 4));
+    CUDA_TRY(d_cigar.alloc((size_t)std::max<int64_t>(b->ops_total, 1) * 4));
+    emit_cigar_kernel<<<(unsigned)((b->n_pairs + 127) / 128), 128, 0, b->stream>>>(A, flags, d_nops.as<int32_t>(),
+                                                                                   d_cigar.as<uint32_t>());
+    CUDA_TRY(cudaGetLastError());
+    b->launches++;
+    CUDA_TRY(cudaMemcpyAsync(n_ops_out, d_nops.ptr, (size_t)b->n_pairs * 4, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(cigar_out, d_cigar.ptr, (size_t)b->ops_total * 4, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return BT_OK;
+}
+
+extern "C" int bt_batch_fetch_gapped(BtBatch *b, const uint8_t *symbols1, int32_t n_symbols1, const uint8_t *symbols2,
+                                     int32_t n_symbols2, const uint8_t *swapped, int64_t *n_columns_out,
+                                     uint8_t *gapped1_out, uint8_t *gapped2_out) {
+    if (!symbols1 || !symbols2 || !n_columns_out || !gapped1_out || !gapped2_out || n_symbols1 < 1 || n_symbols2 < 1)
+        return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    DevBuf d_swapped, d_sym, d_cols, d_g1, d_g2;
+    EmitArgs A{};
+    int st = emit_args(b, swapped, d_swapped, &A);
+    if (st) return st;
+    if (b->n_pairs == 0) return BT_OK;
+    const size_t total = (size_t)std::max<int64_t>(b->ops_total, 1);
+    CUDA_TRY(d_sym.alloc((size_t)n_symbols1 + (size_t)n_symbols2));
+    CUDA_TRY(d_cols.alloc((size_t)b->n_pairs * 8));
+    CUDA_TRY(d_g1.alloc(total));
+    CUDA_TRY(d_g2.alloc(total));
+    CUDA_TRY(cudaMemcpyAsync(d_sym.ptr, symbols1, (size_t)n_symbols1, cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_sym.as<uint8_t>() + n_symbols1, symbols2, (size_t)n_symbols2, cudaMemcpyHostToDevice, b->stream));
+    emit_gapped_kernel<<<(unsigned)((b->n_pairs + 127) / 128), 128, 0, b->stream>>>(
+        A, d_sym.as<uint8_t>(), n_symbols1, d_sym.as<uint8_t>() + n_symbols1, n_symbols2, d_g1.as<uint8_t>(),
+        d_g2.as<uint8_t>(), d_cols.as<int64_t>());
+    CUDA_TRY(cudaGetLastError());
+    b->launches++;
+    CUDA_TRY(cudaMemcpyAsync(n_columns_out, d_cols.ptr, (size_t)b->n_pairs * 8, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(gapped1_out, d_g1.ptr, (size_t)b->ops_total, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaMemcpyAsync(gapped2_out, d_g2.ptr, (size_t)b->ops_total, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
     return BT_OK;
 }
 

@@ -142,6 +142,28 @@ int bt_batch_run(BtBatch *batch, float *device_ms);
 int bt_batch_fetch_scores(BtBatch *batch, int32_t *scores_out);
 int bt_batch_fetch_traces(BtBatch *batch, int64_t *trace_len_out, int32_t *first_out,
                           uint8_t *ops_out);
+/*
+ * Wire formats emitted on the device from the compact traces of a traced batch, without
+ * expanding them to (L,2) arrays first.
+ *
+ * bt_batch_fetch_cigar replaces a loop over write_alignment_to_cigar
+ * (src/biotite/sequence/align/cigar.py:196-392; reference = sequence 1, segment = sequence 2):
+ * cigar_out has bt_batch_ops_bytes() uint32 entries, the operations of pair k start at its
+ * step-byte offset and are BAM-encoded (length << 4 | op, op numbering of cigar.py:20-35),
+ * n_ops_out[k] is their number.  flags: 1 = distinguish matches ('=' / 'X'), 2 = hard clip,
+ * 4 = include terminal gaps.  swapped (NULL or one byte per pair) marks pairs whose two
+ * sequences were exchanged by the caller (align_banded, banded.py:217-224).
+ *
+ * bt_batch_fetch_gapped replaces Alignment.get_gapped_sequences (alignment.py:233-243, the
+ * payload of fasta.set_alignment, io/fasta/convert.py:236-262): the two gapped strings of
+ * pair k ('-' = gap, symbolsN[code] otherwise) start at its step-byte offset in gapped1_out /
+ * gapped2_out (bt_batch_ops_bytes() bytes each) and have n_columns_out[k] characters.
+ */
+int bt_batch_fetch_cigar(BtBatch *batch, int32_t flags, const uint8_t *swapped, int32_t *n_ops_out,
+                         uint32_t *cigar_out);
+int bt_batch_fetch_gapped(BtBatch *batch, const uint8_t *symbols1, int32_t n_symbols1,
+                          const uint8_t *symbols2, int32_t n_symbols2, const uint8_t *swapped,
+                          int64_t *n_columns_out, uint8_t *gapped1_out, uint8_t *gapped2_out);
 /* device time of the last run split into DP fill and traceback kernels (CUDA events) */
 int bt_batch_timings(const BtBatch *batch, float *fill_ms, float *traceback_ms);
 /* DP cells the batch updates per run (sum of len1*len2, or in-band in-sequence cells) */
