@@ -25,6 +25,7 @@
 #include "banded_kernel.cuh"
 #include "microbench.cuh"
 #include "emit_kernel.cuh"
+#include "xdrop_kernel.cuh"
 
 using namespace bt;
 
@@ -883,6 +884,139 @@ extern "C" int bt_expand_traces(int64_t n_pairs, const int64_t *trace_len, const
 struct BtTraceList {
     std::vector<std::vector<int64_t>> traces;  // each 2*L values
 };
+
+// ---------------------------------------------------------------------------------------
+// X-drop extension of regions (align_local_gapped's native part, localgapped.rs:57-70)
+// ---------------------------------------------------------------------------------------
+template <bool TRACED>
+static cudaError_t xdrop_launch(const XdropArgs &A, bool affine, int64_t n_regions, cudaStream_t s) {
+    if (affine) xdrop_fill_kernel<true, TRACED><<<(unsigned)n_regions, XD_THREADS, 0, s>>>(A);
+    else xdrop_fill_kernel<false, TRACED><<<(unsigned)n_regions, XD_THREADS, 0, s>>>(A);
+    return cudaGetLastError();
+}
+
+extern "C" int bt_xdrop_regions(const BtParams *params, const void *codes1, const int64_t *off1,
+                                const void *codes2, const int64_t *off2, int64_t n_regions,
+                                const int32_t *matrix, int32_t threshold, int64_t max_table_size,
+                                int32_t score_only, int64_t max_number, int32_t *scores_out,
+                                int32_t *status_out, BtTraceList **lists_out) {
+    int st = check_params(params);
+    if (st) return st;
+    if (n_regions < 0 || !off1 || !off2 || !scores_out || !status_out)
+        return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (!score_only && !lists_out) return fail(BT_ERR_INVALID_ARG, "lists_out is NULL");
+    if (params->use_matrix && !matrix) return fail(BT_ERR_INVALID_ARG, "matrix is NULL");
+    if (threshold < 0) return fail(BT_ERR_INVALID_ARG, "The threshold value must be a non-negative integer");
+    if (max_table_size <= 0) return fail(BT_ERR_INVALID_ARG, "Maximum table size must be a positve value");
+    if (max_number < 1) return fail(BT_ERR_INVALID_ARG, "Maximum number of returned alignments must be at least 1");
+    if (lists_out) for (int64_t r = 0; r < n_regions; r++) lists_out[r] = nullptr;
+    if (n_regions == 0) return BT_OK;
+    if (bt_device_count() <= 0) return fail(BT_ERR_CUDA, "no CUDA device available");
+    const bool affine = params->affine != 0;
+    const int cb = params->code_bytes;
+    const int64_t total1 = off1[n_regions], total2 = off2[n_regions];
+    struct StreamGuard {
+        cudaStream_t s = nullptr;
+        ~StreamGuard() { if (s) cudaStreamDestroy(s); }
+    } sg;
+    CUDA_TRY(cudaStreamCreateWithFlags(&sg.s, cudaStreamNonBlocking));
+    cudaStream_t s = sg.s;
+    DevBuf d_c1, d_c2, d_o1, d_o2, d_mat, d_roll, d_roll_off, d_max, d_dims, d_status, d_flag, d_dirs, d_dir_off;
+    CUDA_TRY(d_c1.alloc((size_t)total1 * cb));
+    CUDA_TRY(d_c2.alloc((size_t)total2 * cb));
+    CUDA_TRY(d_o1.alloc((size_t)(n_regions + 1) * 8));
+    CUDA_TRY(d_o2.alloc((size_t)(n_regions + 1) * 8));
+    CUDA_TRY(d_flag.alloc(4));
+    CUDA_TRY(cudaMemsetAsync(d_flag.ptr, 0, 4, s));
+    if (total1) CUDA_TRY(cudaMemcpyAsync(d_c1.ptr, codes1, (size_t)total1 * cb, cudaMemcpyHostToDevice, s));
+    if (total2) CUDA_TRY(cudaMemcpyAsync(d_c2.ptr, codes2, (size_t)total2 * cb, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_o1.ptr, off1, (size_t)(n_regions + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_o2.ptr, off2, (size_t)(n_regions + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (params->use_matrix) {
+        const size_t mb = (size_t)params->n_rows * params->n_cols * 4;
+        CUDA_TRY(d_mat.alloc(mb));
+        CUDA_TRY(cudaMemcpyAsync(d_mat.ptr, matrix, mb, cudaMemcpyHostToDevice, s));
+        // the reference would panic on an out-of-range code (scoring.rs:63)
+        if (total1) validate_codes_kernel<<<(int)std::min<int64_t>(592, (total1 + 255) / 256), 256, 0, s>>>(
+            d_c1.ptr, total1, cb, (uint64_t)params->n_rows, d_flag.as<int>());
+        if (total2) validate_codes_kernel<<<(int)std::min<int64_t>(592, (total2 + 255) / 256), 256, 0, s>>>(
+            d_c2.ptr, total2, cb, (uint64_t)params->n_cols, d_flag.as<int>());
+        CUDA_TRY(cudaGetLastError());
+    }
+    const int states = affine ? 3 : 1;
+    std::vector<int64_t> roll_off((size_t)n_regions + 1, 0);
+    for (int64_t r = 0; r < n_regions; r++) {
+        if (off1[r + 1] < off1[r] || off2[r + 1] < off2[r]) return fail(BT_ERR_INVALID_ARG, "offsets must not decrease");
+        roll_off[(size_t)r + 1] = roll_off[(size_t)r] + 3 * states * (off1[r + 1] - off1[r] + 1);
+    }
+    CUDA_TRY(d_roll.alloc((size_t)roll_off[(size_t)n_regions] * 4));
+    CUDA_TRY(d_roll_off.alloc((size_t)(n_regions + 1) * 8));
+    CUDA_TRY(cudaMemcpyAsync(d_roll_off.ptr, roll_off.data(), (size_t)(n_regions + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(d_max.alloc((size_t)n_regions * 4));
+    CUDA_TRY(d_dims.alloc((size_t)n_regions * 16));
+    CUDA_TRY(d_status.alloc((size_t)n_regions * 4));
+    CUDA_TRY(cudaMemsetAsync(d_status.ptr, 0, (size_t)n_regions * 4, s));
+
+    XdropArgs A{};
+    A.codes1 = d_c1.ptr; A.codes2 = d_c2.ptr; A.off1 = d_o1.as<int64_t>(); A.off2 = d_o2.as<int64_t>();
+    A.code_bytes = cb;
+    A.matrix = d_mat.as<int32_t>(); A.n_cols = params->n_cols; A.use_matrix = params->use_matrix;
+    A.match = params->match_score; A.mismatch = params->mismatch_score;
+    A.gap_open = params->gap_open; A.gap_ext = affine ? params->gap_ext : params->gap_open;
+    A.threshold = threshold; A.max_table_size = max_table_size;
+    A.roll = d_roll.as<int32_t>(); A.roll_off = d_roll_off.as<int64_t>();
+    A.max_score = d_max.as<int32_t>(); A.dims = d_dims.as<int64_t>(); A.status = d_status.as<int32_t>();
+    CUDA_TRY(xdrop_launch<false>(A, affine, n_regions, s));
+    std::vector<int32_t> h_max((size_t)n_regions);
+    std::vector<int64_t> h_dims((size_t)n_regions * 2);
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(h_max.data(), d_max.ptr, (size_t)n_regions * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h_dims.data(), d_dims.ptr, (size_t)n_regions * 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(status_out, d_status.ptr, (size_t)n_regions * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&flag, d_flag.ptr, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (flag) return fail(BT_ERR_INVALID_CODE, "a sequence code is outside the substitution matrix");
+    for (int64_t r = 0; r < n_regions; r++) scores_out[r] = wsub(h_max[(size_t)r], wadd(threshold, 1));
+    if (score_only) return BT_OK;
+
+    // second pass: directions into tables shaped like the reference's (rows x cols)
+    std::vector<int64_t> dir_off((size_t)n_regions + 1, 0);
+    for (int64_t r = 0; r < n_regions; r++)
+        dir_off[(size_t)r + 1] = dir_off[(size_t)r] + (status_out[r] ? 0 : h_dims[(size_t)2 * r] * h_dims[(size_t)2 * r + 1]);
+    const int64_t dir_bytes = dir_off[(size_t)n_regions];
+    cudaError_t e = d_dirs.alloc((size_t)dir_bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(BT_ERR_OOM, "out of device memory (X-drop direction tables, %lld bytes)", (long long)dir_bytes); }
+    CUDA_TRY(cudaMemsetAsync(d_dirs.ptr, 0, (size_t)std::max<int64_t>(dir_bytes, 1), s));
+    CUDA_TRY(d_dir_off.alloc((size_t)(n_regions + 1) * 8));
+    CUDA_TRY(cudaMemcpyAsync(d_dir_off.ptr, dir_off.data(), (size_t)(n_regions + 1) * 8, cudaMemcpyHostToDevice, s));
+    A.dirs = d_dirs.as<uint8_t>(); A.dir_off = d_dir_off.as<int64_t>();
+    CUDA_TRY(xdrop_launch<true>(A, affine, n_regions, s));
+    std::vector<uint8_t> h_dirs((size_t)std::max<int64_t>(dir_bytes, 1));
+    if (dir_bytes) CUDA_TRY(cudaMemcpyAsync(h_dirs.data(), d_dirs.ptr, (size_t)dir_bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+
+    // traceback on the host (trace.rs:21-142): starts = every cell holding the maximum, row-major
+    for (int64_t r = 0; r < n_regions; r++) {
+        if (status_out[r]) continue;
+        const int64_t rows = h_dims[(size_t)2 * r], cols = h_dims[(size_t)2 * r + 1];
+        const uint8_t *dir = h_dirs.data() + dir_off[(size_t)r];
+        std::unique_ptr<BtTraceList> list(new BtTraceList());
+        std::vector<Path> paths;
+        const int64_t off[3] = {-cols - 1, -1, -cols};
+        for (int64_t idx = 0; idx < rows * cols && (int64_t)paths.size() < max_number; idx++) {
+            if (!(dir[idx] & DIR_MARK)) continue;
+            enumerate_from(dir, affine, off, Start{idx, ST_MATCH}, max_number, max_number, paths);
+        }
+        if ((int64_t)paths.size() > max_number) paths.resize((size_t)max_number);
+        for (const Path &path : paths) {
+            std::vector<int64_t> trace_rows;
+            path_to_trace(path, cols, false, 0, trace_rows);
+            list->traces.push_back(std::move(trace_rows));
+        }
+        lists_out[r] = list.release();
+    }
+    return BT_OK;
+}
 
 extern "C" int64_t bt_tracelist_count(const BtTraceList *l) { return l ? (int64_t)l->traces.size() : 0; }
 extern "C" int64_t bt_tracelist_length(const BtTraceList *l, int64_t k) {

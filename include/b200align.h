@@ -182,6 +182,24 @@ int bt_align_batch(const BtParams *params, const void *codes1, const int64_t *of
                    uint8_t *ops_out);
 
 /*
+ * Local X-drop extension of regions: the native part of align_local_gapped, replaces
+ * `align_region` (src/rust/sequence/align/localgapped.rs:57-70; called from
+ * src/biotite/sequence/align/localgapped.py:235-266 once per side of the seed).  Region r
+ * aligns codes1[off1[r]..off1[r+1]) with codes2[off2[r]..off2[r+1]) starting at their first
+ * symbols; all regions of a call run concurrently (one thread block each).  scores_out[r] is
+ * the region's score, status_out[r] = 1 where the reference would raise MemoryError
+ * ("Maximum table size exceeded").  Unless score_only, lists_out[r] receives up to max_number
+ * co-optimal traces in the reference's order (free with bt_tracelist_free; NULL for a region
+ * whose status is 1).  params: affine / gap_open / gap_ext, use_matrix or match / mismatch,
+ * n_rows / n_cols, code_bytes; local, terminal_penalty and banded are ignored.
+ */
+int bt_xdrop_regions(const BtParams *params, const void *codes1, const int64_t *off1,
+                     const void *codes2, const int64_t *off2, int64_t n_regions,
+                     const int32_t *matrix, int32_t threshold, int64_t max_table_size,
+                     int32_t score_only, int64_t max_number, int32_t *scores_out,
+                     int32_t *status_out, BtTraceList **lists_out);
+
+/*
  * Host-side expansion of compact traces into the reference's (L,2) int64 layout.
  * rows_off[k] (n_pairs+1 entries) = prefix sum of trace_len; out has 2*rows_off[n_pairs]
  * entries.  bands as in bt_batch_create (NULL for align_optimal).

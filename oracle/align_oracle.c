@@ -501,6 +501,129 @@ static result_t *run_banded(const params_t *p, int64_t lower, int64_t upper,
     return res;
 }
 
+/* ---- align_region: local X-drop extension (localgapped.rs) ------------------------------ */
+
+/* localgapped.rs:182-310 (fill_xdrop), :446-489 (linear rule), :558-641 (affine rule).
+ * A score of 0 marks an unreached cell; the (0,0) anchor holds threshold + 1; the table is
+ * filled antidiagonal by antidiagonal, every candidate is pruned against the running
+ * maximum.  `status` = 1 when the reference's doubling table (100 x 100 initially,
+ * localgapped.rs:45, :232-256) would exceed max_table_size. */
+static result_t *run_region(const params_t *p, score_t threshold, int64_t max_number,
+                            int64_t max_table_size, int *status) {
+    const int64_t n = p->n, m = p->m, stride = m + 1;
+    const score_t init = wadd(threshold, 1);
+    cell_t *table = (cell_t *)calloc((size_t)((n + 1) * stride), sizeof(cell_t));
+    table[0].m = init;
+    score_t max_score = init;
+    int64_t rows = n + 1 < 100 ? n + 1 : 100, cols = m + 1 < 100 ? m + 1 : 100;
+    int64_t i_min_k0 = 0, i_max_k0 = 0, i_min_k1 = 0, i_max_k1 = 0, i_min_k2, i_max_k2;
+    *status = 0;
+    for (int64_t k = 1; k <= n + m; k++) {
+        i_min_k2 = i_min_k1; i_max_k2 = i_max_k1;
+        i_min_k1 = i_min_k0; i_max_k1 = i_max_k0;
+        i_min_k0 = k; i_max_k0 = 0;
+        int64_t i_min = i_min_k1 < i_min_k2 + 1 ? i_min_k1 : i_min_k2 + 1;
+        const int64_t lo = k > m ? k - m : 0;
+        if (i_min < lo) i_min = lo;
+        int64_t i_max = i_max_k1 + 1 > i_max_k2 + 1 ? i_max_k1 + 1 : i_max_k2 + 1;
+        if (i_max > n) i_max = n;
+        if (i_min > i_max) break;
+        const int64_t j_max = k - i_min;
+        if (i_max >= rows) {
+            if (rows * 2 * cols > max_table_size) { *status = 1; break; }
+            rows *= 2;
+        }
+        if (j_max >= cols) {
+            if (rows * cols * 2 > max_table_size) { *status = 1; break; }
+            cols *= 2;
+        }
+        for (int64_t i = i_min; i <= i_max; i++) {
+            const int64_t j = k - i;
+            const cell_t zero = {0, 0, 0, 0};
+            const cell_t *fd = (i > 0 && j > 0) ? &table[(i - 1) * stride + j - 1] : NULL;
+            const cell_t f1 = j > 0 ? table[i * stride + j - 1] : zero;
+            const cell_t f2 = i > 0 ? table[(i - 1) * stride + j] : zero;
+            const score_t sim = fd ? similarity(p, p->code1[i - 1], p->code2[j - 1]) : 0;
+            cell_t out = {0, 0, 0, 0};
+            int valid = 0;
+            if (!p->affine) {
+                const score_t a = (fd && fd->m != 0) ? wadd(fd->m, sim) : 0;
+                const score_t b = wadd(f1.m, p->gap_open), c = wadd(f2.m, p->gap_open);
+                uint8_t dir = 0;
+                const score_t sc = p->score_only ? smax(smax(a, b), c) : trace_linear(a, b, c, &dir);
+                if (sc >= wsub(max_score, threshold)) {
+                    if (sc > max_score) max_score = sc;
+                    out.m = sc; out.dir = dir; valid = 1;
+                }
+            } else {
+                const score_t mm = (fd && fd->m != 0) ? wadd(fd->m, sim) : 0;
+                const score_t g1m = (fd && fd->g1 != 0) ? wadd(fd->g1, sim) : 0;
+                const score_t g2m = (fd && fd->g2 != 0) ? wadd(fd->g2, sim) : 0;
+                const score_t mg1 = wadd(f1.m, p->gap_open), g1g1 = wadd(f1.g1, p->gap_ext);
+                const score_t mg2 = wadd(f2.m, p->gap_open), g2g2 = wadd(f2.g2, p->gap_ext);
+                score_t ms, g1s, g2s;
+                uint8_t dir = 0;
+                if (p->score_only) {
+                    ms = smax(smax(mm, g1m), g2m); g1s = smax(mg1, g1g1); g2s = smax(mg2, g2g2);
+                } else {
+                    ms = trace_linear(mm, g1m, g2m, &dir);
+                    if (mg1 > g1g1) { dir |= A_MG1; g1s = mg1; }
+                    else if (mg1 < g1g1) { dir |= A_G1G1; g1s = g1g1; }
+                    else { dir |= A_MG1 | A_G1G1; g1s = mg1; }
+                    if (mg2 > g2g2) { dir |= A_MG2; g2s = mg2; }
+                    else if (mg2 < g2g2) { dir |= A_G2G2; g2s = g2g2; }
+                    else { dir |= A_MG2 | A_G2G2; g2s = mg2; }
+                }
+                score_t req = wsub(max_score, threshold);
+                if (ms >= req) {
+                    out.m = ms; valid = 1;
+                    if (ms > max_score) { max_score = ms; req = wsub(max_score, threshold); }
+                }
+                if (g1s >= req) {
+                    out.g1 = g1s; valid = 1;
+                    if (g1s > max_score) { max_score = g1s; req = wsub(max_score, threshold); }
+                }
+                if (g2s >= req) {
+                    out.g2 = g2s; valid = 1;
+                    if (g2s > max_score) max_score = g2s;
+                }
+                out.dir = dir;
+            }
+            if (valid) {
+                if (i_min_k0 == k) i_min_k0 = i;
+                i_max_k0 = i;
+                table[i * stride + j] = out;
+            }
+        }
+    }
+    result_t *res;
+    if (*status) {
+        res = (result_t *)calloc(1, sizeof(result_t));
+    } else {
+        /* localgapped.rs:491-511, :621-641: every cell holding the maximum (of M), row-major */
+        int64_t n_starts = 0, cap = 16;
+        int64_t *starts = (int64_t *)malloc((size_t)cap * sizeof(int64_t));
+        int *states = NULL;
+        if (!p->score_only) {
+            score_t best = INT32_MIN;
+            for (int64_t idx = 0; idx < (n + 1) * stride; idx++) {
+                const score_t v = table[idx].m;
+                if (v > best) { best = v; n_starts = 0; }
+                if (v == best) {
+                    if (n_starts == cap) { cap *= 2; starts = (int64_t *)realloc(starts, (size_t)cap * sizeof(int64_t)); }
+                    starts[n_starts++] = idx;
+                }
+            }
+            states = (int *)calloc((size_t)(n_starts ? n_starts : 1), sizeof(int));
+        }
+        const int64_t offs[3] = {-stride - 1, -1, -stride};
+        res = finish(table, p, wsub(max_score, init), starts, states, n_starts, offs, stride, max_number, 0, 0);
+        free(starts); free(states);
+    }
+    free(table);
+    return res;
+}
+
 /* ---- exported C interface (ctypes) ------------------------------------------------- */
 
 static void setup(params_t *p, const int64_t *code1, int64_t n, const int64_t *code2,
@@ -539,6 +662,18 @@ void *oracle_align_banded(const int64_t *code1, int64_t n, const int64_t *code2,
     setup(&p, code1, n, code2, m, matrix, n_rows, n_cols, match, mismatch, affine,
           gap_open, gap_ext, local, 1, score_only, 1);
     return run_banded(&p, lower, upper, max_number);
+}
+
+/* localgapped.rs:57-70 `align_region`; *status = 1: "Maximum table size exceeded" */
+void *oracle_align_region(const int64_t *code1, int64_t n, const int64_t *code2, int64_t m,
+                          const int32_t *matrix, int64_t n_rows, int64_t n_cols,
+                          int32_t match, int32_t mismatch, int affine, int32_t gap_open,
+                          int32_t gap_ext, int32_t threshold, int score_only, int64_t max_number,
+                          int64_t max_table_size, int *status) {
+    params_t p;
+    setup(&p, code1, n, code2, m, matrix, n_rows, n_cols, match, mismatch, affine,
+          gap_open, gap_ext, 0, 1, score_only, 0);
+    return run_region(&p, threshold, max_number, max_table_size, status);
 }
 
 int32_t oracle_result_score(const void *r) { return ((const result_t *)r)->score; }

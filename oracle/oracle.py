@@ -61,6 +61,9 @@ def _load():
         lib.oracle_align_banded.restype = ctypes.c_void_p
         lib.oracle_align_banded.argtypes = common + [
             ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int64]
+        lib.oracle_align_region.restype = ctypes.c_void_p
+        lib.oracle_align_region.argtypes = common + [
+            ctypes.c_int32, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int)]
         lib.oracle_result_score.restype = ctypes.c_int32
         lib.oracle_result_score.argtypes = [ctypes.c_void_p]
         lib.oracle_result_count.restype = ctypes.c_int64
@@ -141,6 +144,81 @@ def align_banded(code1, code2, scoring, gap_penalty, lower_diag, upper_diag, loc
         n_cols, match, mismatch, affine, gap_open, gap_ext, int(lower_diag),
         int(upper_diag), int(local), int(score_only), int(max_number))
     return _collect(lib, handle)
+
+
+def align_region(code1, code2, scoring, gap_penalty, threshold, max_number, score_only,
+                 max_table_size):
+    """Same contract as the reference's native ``align_region`` (localgapped.rs:57-70)."""
+    lib = _load()
+    c1 = np.ascontiguousarray(code1, dtype=np.int64)
+    c2 = np.ascontiguousarray(code2, dtype=np.int64)
+    mat, n_rows, n_cols, match, mismatch = _scoring_args(scoring)
+    affine, gap_open, gap_ext = _gap_args(gap_penalty)
+    status = ctypes.c_int(0)
+    handle = lib.oracle_align_region(
+        _ptr(c1, _i64p), len(c1), _ptr(c2, _i64p), len(c2), _ptr(mat, _i32p), n_rows,
+        n_cols, match, mismatch, affine, gap_open, gap_ext, int(threshold), int(score_only),
+        int(max_number), int(min(max_table_size, 2**62)), ctypes.byref(status))
+    traces, score = _collect(lib, handle)
+    if status.value:
+        raise MemoryError("Maximum table size exceeded")
+    return traces, score
+
+
+def align_local_gapped(code1, code2, scoring, seed, threshold, gap_penalty=-10, max_number=1,
+                       direction="both", score_only=False, max_table_size=None,
+                       region=None):
+    """
+    The reference's ``align_local_gapped`` wrapper (localgapped.py:186-311) over `region`
+    (default: this module's ``align_region``): split at the seed, reverse the upstream part,
+    shift and combine the traces.  Returns ``(traces, score)``.
+    """
+    import itertools
+    region = region or align_region
+    if max_table_size is None:
+        max_table_size = np.iinfo(np.int64).max
+    s1, s2 = int(seed[0]), int(seed[1])
+    upstream = direction in ("both", "upstream") and s1 != 0 and s2 != 0
+    downstream = direction in ("both", "downstream")
+    code1, code2 = np.asarray(code1), np.asarray(code2)
+    total, up_traces, down_traces = 0, [], []
+    if upstream:
+        traces, score = region(code1[s1 - 1::-1], code2[s2 - 1::-1], scoring, gap_penalty,
+                               threshold, max_number, score_only, max_table_size)
+        total += score
+        for trace in traces:
+            trace = trace[::-1].copy()
+            mask = trace != -1
+            trace[mask] *= -1
+            trace[mask[:, 0], 0] += s1 - 1
+            trace[mask[:, 1], 1] += s2 - 1
+            up_traces.append(trace)
+    if downstream:
+        traces, score = region(code1[s1 + 1:], code2[s2 + 1:], scoring, gap_penalty, threshold,
+                               max_number, score_only, max_table_size)
+        total += score
+        for trace in traces:
+            trace = trace.copy()
+            trace[trace[:, 0] != -1, 0] += s1 + 1
+            trace[trace[:, 1] != -1, 1] += s2 + 1
+            down_traces.append(trace)
+    if isinstance(scoring, tuple):
+        total += scoring[0] if code1[s1] == code2[s2] else scoring[1]
+    else:
+        total += int(scoring[code1[s1], code2[s2]])
+    if score_only:
+        return [], total
+    seed_row = np.array([[s1, s2]], dtype=np.int64)
+    if upstream and downstream:
+        combos = itertools.islice(itertools.product(up_traces, down_traces), max_number)
+        traces = [np.concatenate([u, seed_row, d]) for u, d in combos]
+    elif upstream:
+        traces = [np.concatenate([u, seed_row]) for u in up_traces]
+    elif downstream:
+        traces = [np.concatenate([seed_row, d]) for d in down_traces]
+    else:
+        traces = [seed_row]
+    return traces, total
 
 
 def prepare_band(len1, len2, band):

@@ -7,8 +7,8 @@ Sources (read-only, reference test *data*, no reference source code is copied):
   tests/sequence/data/cas9.fasta                               10 Cas9 sequences
   tests/sequence/data/legacy_consistency/params.json           parameters per file
   tests/sequence/data/legacy_consistency/legacy_alignments.tar.gz
-        630 FASTA alignments; the 360 align_optimal + 180 align_banded ones
-        are kept (align_local_gapped is out of scope)
+        630 FASTA alignments: 360 align_optimal + 180 align_banded + 90 align_local_gapped
+        (the X-drop extension)
   README.rst:108-115                                           avidin/streptavidin (C1)
 
 Output: tests/golden/legacy_alignments.json.gz
@@ -52,7 +52,7 @@ def main(ref_root):
     with tarfile.open(legacy / "legacy_alignments.tar.gz", "r:gz") as tar:
         for name in sorted(params):
             entry = params[name]
-            if entry["method"] not in ("align_optimal", "align_banded"):
+            if entry["method"] not in ("align_optimal", "align_banded", "align_local_gapped"):
                 continue
             with io.TextIOWrapper(tar.extractfile(name), encoding="utf-8") as f:
                 rows = read_fasta(f.read())
