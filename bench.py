@@ -257,6 +257,8 @@ def main():
 
     dist = None
     if world > 1:
+        # NCCL prints its version banner to stdout; the contract is ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
