@@ -482,7 +482,7 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     if (b->route == ROUTE_INTERSEQ) {
         CUDA_TRY(b->is_start.alloc((size_t)n_pairs * 8));
         st = interseq_prepare(b->interseq, *params, hm, n_pairs, b->stats ? 2 : b->score_only, mn, mx,
-                              &b->cells, 1, 3, s);
+                              &b->cells, 1, 4, s);
         if (st == BT_ERR_OOM) return fail(st, "out of device memory (inter-sequence plan)");
         if (st) return fail(st, "inter-sequence plan failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else if (b->route == ROUTE_BANDED) {
@@ -744,45 +744,69 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
         CUDA_TRY(d_first.alloc((size_t)n_pairs * 8));
         CUDA_TRY(d_ops.alloc((size_t)(total1 + total2)));
     }
+    // Four streams: all input copies are queued up front on `h2d` (the device code buffers hold
+    // the whole batch, so a window's input never waits for a scratch slot), the two compute
+    // streams alternate windows / scratch slots, and `d2h` returns a window's results as soon as
+    // its kernels are done - no compute stream ever waits for a copy of another window.
     struct Streams {
-        cudaStream_t s[2] = {nullptr, nullptr};
-        cudaEvent_t ready = nullptr;
+        cudaStream_t s[2] = {nullptr, nullptr}, h2d = nullptr, d2h = nullptr;
+        std::vector<cudaEvent_t> in_ready, plan_ready, k_done;
         ~Streams() {
             for (cudaStream_t x : s) if (x) cudaStreamDestroy(x);
-            if (ready) cudaEventDestroy(ready);
+            if (h2d) cudaStreamDestroy(h2d);
+            if (d2h) cudaStreamDestroy(d2h);
+            for (cudaEvent_t e : in_ready) cudaEventDestroy(e);
+            for (cudaEvent_t e : plan_ready) cudaEventDestroy(e);
+            for (cudaEvent_t e : k_done) cudaEventDestroy(e);
         }
     } st;
     CUDA_TRY(cudaStreamCreateWithFlags(&st.s[0], cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&st.s[1], cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&st.ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&st.h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&st.d2h, cudaStreamNonBlocking));
 
     const double t1 = now();
-    // start moving data before the host plans the windows: offsets, matrix and the codes of
-    // the first window
-    CUDA_TRY(cudaMemsetAsync(d_flag.ptr, 0, 4, st.s[0]));
-    CUDA_TRY(cudaMemcpyAsync(d_off1.ptr, off1, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.s[0]));
-    CUDA_TRY(cudaMemcpyAsync(d_off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.s[0]));
-    CUDA_TRY(cudaMemcpyAsync(d_matrix.ptr, matrix, mb, cudaMemcpyHostToDevice, st.s[0]));
-    // plan the windows on worker threads while the first copies are in flight; windows are
-    // launched as soon as they are planned
+    // plan the windows on worker threads while the copies are in flight; windows are launched
+    // as soon as they are planned
     InterseqPlan plan;
     PairMap hm;
     hm.off1 = h_off1; hm.off2 = h_off2;
     interseq_setup(plan, *params, n_pairs, score_only, mn);
     (void)mx;
     const char *waves_env = getenv("B200ALIGN_WAVES");
-    const int waves = waves_env ? std::max(1, atoi(waves_env)) : 2;
+    const int waves = waves_env ? std::max(1, atoi(waves_env)) : 3;
     StreamingPlanner planner(plan, hm, n_pairs, waves, params->affine != 0);
-    {
-        const int64_t first_end = planner.bounds[1];
-        CUDA_TRY(cudaMemcpyAsync(d_codes1.ptr, codes1, (size_t)h_off1[first_end], cudaMemcpyHostToDevice, st.s[0]));
-        CUDA_TRY(cudaMemcpyAsync(d_codes2.ptr, codes2, (size_t)h_off2[first_end], cudaMemcpyHostToDevice, st.s[0]));
+    cudaEvent_t tev0 = nullptr;
+    if (trace) { cudaEventCreate(&tev0); cudaEventRecord(tev0, st.h2d); }
+    CUDA_TRY(cudaMemsetAsync(d_flag.ptr, 0, 4, st.h2d));
+    CUDA_TRY(cudaMemcpyAsync(d_off1.ptr, off1, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.h2d));
+    CUDA_TRY(cudaMemcpyAsync(d_off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.h2d));
+    CUDA_TRY(cudaMemcpyAsync(d_matrix.ptr, matrix, mb, cudaMemcpyHostToDevice, st.h2d));
+    // input codes of window w on the copy stream; in_ready[w] fires when they have arrived
+    auto enqueue_inputs = [&](int64_t w) -> cudaError_t {
+        const int64_t p0 = planner.bounds[(size_t)w], p1 = planner.bounds[(size_t)w + 1];
+        const int64_t a1 = h_off1[p0], b1 = h_off1[p1], a2 = h_off2[p0], b2 = h_off2[p1];
+        cudaError_t e = cudaMemcpyAsync((char *)d_codes1.ptr + a1, (const char *)codes1 + a1, (size_t)(b1 - a1), cudaMemcpyHostToDevice, st.h2d);
+        if (e == cudaSuccess) e = cudaMemcpyAsync((char *)d_codes2.ptr + a2, (const char *)codes2 + a2, (size_t)(b2 - a2), cudaMemcpyHostToDevice, st.h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(st.in_ready[(size_t)w], st.h2d);
+        return e;
+    };
+    for (int64_t w = 0; w < planner.n_windows; w++) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+        CUDA_TRY(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+        st.in_ready.push_back(e0);
+        CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        st.plan_ready.push_back(e2);
+        CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        st.k_done.push_back(e1);
     }
+    // the copy engine serves its queue in order: input codes, then group order / descriptors
+    // of a window (uploaded as soon as it is planned), then the next window's input codes, ...
+    // (the host enqueues all of this within the first few milliseconds)
+    CUDA_TRY(enqueue_inputs(0));
     CUDA_TRY(planner.allocate(2, scan.nmax, scan.mmax));
     planner.start();
     const double t2 = now();
-    CUDA_TRY(cudaEventRecord(st.ready, st.s[0]));
-    CUDA_TRY(cudaStreamWaitEvent(st.s[1], st.ready, 0));
 
     PairMap dm;
     dm.off1 = d_off1.as<int64_t>(); dm.off2 = d_off2.as<int64_t>();
@@ -790,18 +814,22 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
                   d_score.as<int32_t>(), d_len.as<int64_t>(), d_first.as<int32_t>(), d_ops.as<uint8_t>(),
                   d_start.as<int32_t>()};
     int64_t launches = 0;
+    std::vector<cudaEvent_t> tev;   // B200ALIGN_TRACE: per window [start, h2d done, kernels done, d2h done]
+    auto mark = [&](cudaStream_t s) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e); } };
     for (size_t w = 0; w < plan.windows.size(); w++) {
         const int slot = (int)(w & 1);
         cudaStream_t s = st.s[slot];
-        CUDA_TRY(planner.take((int64_t)w, s));
+        CUDA_TRY(planner.take((int64_t)w, st.h2d));
+        CUDA_TRY(cudaEventRecord(st.plan_ready[w], st.h2d));
+        if ((int64_t)w + 1 < planner.n_windows) CUDA_TRY(enqueue_inputs((int64_t)w + 1));
+        CUDA_TRY(cudaStreamWaitEvent(s, st.plan_ready[w], 0));
+        mark(s);
         const Window &win = plan.windows[w];
         const int64_t a1 = h_off1[win.pair_begin], b1 = h_off1[win.pair_end];
         const int64_t a2 = h_off2[win.pair_begin], b2 = h_off2[win.pair_end];
         const int64_t np = win.pair_end - win.pair_begin;
-        if (w > 0) {
-            CUDA_TRY(cudaMemcpyAsync((char *)d_codes1.ptr + a1, (const char *)codes1 + a1, (size_t)(b1 - a1), cudaMemcpyHostToDevice, s));
-            CUDA_TRY(cudaMemcpyAsync((char *)d_codes2.ptr + a2, (const char *)codes2 + a2, (size_t)(b2 - a2), cudaMemcpyHostToDevice, s));
-        }
+        CUDA_TRY(cudaStreamWaitEvent(s, st.in_ready[w], 0));
+        mark(s);
         validate_codes_kernel<<<(int)std::min<int64_t>(592, (b1 - a1 + 255) / 256), 256, 0, s>>>(
             (const char *)d_codes1.ptr + a1, b1 - a1, 1, (uint64_t)params->n_rows, d_flag.as<int>());
         validate_codes_kernel<<<(int)std::min<int64_t>(592, (b2 - a2 + 255) / 256), 256, 0, s>>>(
@@ -809,21 +837,38 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(interseq_fill_window(plan, win, slot, io, s, &launches));
         CUDA_TRY(interseq_traceback_window(plan, win, slot, io, s, &launches));
+        mark(s);
+        CUDA_TRY(cudaEventRecord(st.k_done[w], s));
+        cudaStream_t r = st.d2h;
+        CUDA_TRY(cudaStreamWaitEvent(r, st.k_done[w], 0));
         if (scores_out)
-            CUDA_TRY(cudaMemcpyAsync(scores_out + win.pair_begin, d_score.as<int32_t>() + win.pair_begin, (size_t)np * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(scores_out + win.pair_begin, d_score.as<int32_t>() + win.pair_begin, (size_t)np * 4, cudaMemcpyDeviceToHost, r));
         if (!score_only) {
             if (trace_len_out)
-                CUDA_TRY(cudaMemcpyAsync(trace_len_out + win.pair_begin, d_len.as<int64_t>() + win.pair_begin, (size_t)np * 8, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaMemcpyAsync(trace_len_out + win.pair_begin, d_len.as<int64_t>() + win.pair_begin, (size_t)np * 8, cudaMemcpyDeviceToHost, r));
             if (first_out)
-                CUDA_TRY(cudaMemcpyAsync(first_out + 2 * win.pair_begin, d_first.as<int32_t>() + 2 * win.pair_begin, (size_t)np * 8, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaMemcpyAsync(first_out + 2 * win.pair_begin, d_first.as<int32_t>() + 2 * win.pair_begin, (size_t)np * 8, cudaMemcpyDeviceToHost, r));
             if (ops_out)
-                CUDA_TRY(cudaMemcpyAsync(ops_out + a1 + a2, d_ops.as<uint8_t>() + a1 + a2, (size_t)(b1 - a1 + b2 - a2), cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaMemcpyAsync(ops_out + a1 + a2, d_ops.as<uint8_t>() + a1 + a2, (size_t)(b1 - a1 + b2 - a2), cudaMemcpyDeviceToHost, r));
         }
+        mark(r);
     }
     int flag = 0;
     const double t3 = now();
+    CUDA_TRY(cudaStreamSynchronize(st.h2d));
     CUDA_TRY(cudaStreamSynchronize(st.s[0]));
     CUDA_TRY(cudaStreamSynchronize(st.s[1]));
+    CUDA_TRY(cudaStreamSynchronize(st.d2h));
+    if (trace) {
+        for (size_t w = 0; w * 4 + 3 < tev.size(); w++) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, tev0, tev[w * 4]); cudaEventElapsedTime(&b, tev0, tev[w * 4 + 1]);
+            cudaEventElapsedTime(&c, tev0, tev[w * 4 + 2]); cudaEventElapsedTime(&d, tev0, tev[w * 4 + 3]);
+            fprintf(stderr, "[b200align]   window %zu: start %.2f  h2d done %.2f  kernels done %.2f  d2h done %.2f ms\n", w, a, b, c, d);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        cudaEventDestroy(tev0);
+    }
     if (trace)
         fprintf(stderr, "[b200align] alloc %.2f ms, plan %.2f ms, enqueue %.2f ms, drain %.2f ms, windows %zu\n",
                 t1 - t0, t2 - t1, t3 - t2, now() - t3, plan.windows.size());

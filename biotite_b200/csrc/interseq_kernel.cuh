@@ -882,18 +882,19 @@ __global__ void interseq_linear_traceback_kernel(const InterseqConst C, const In
 // host side
 // ---------------------------------------------------------------------------------------
 
-// Groups per window: a whole number of full waves of the fill kernel (3 blocks of 4 warps
-// per SM), so that windows launched one after the other lose little to partial waves.
-inline int64_t interseq_window_groups() {
+// Groups per wave of the affine fill kernel (one warp per block, IS_WARPS_PER_SM blocks per SM):
+// windows are whole numbers of waves, so that they lose little to partial waves.
+inline int64_t interseq_wave_groups() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return (int64_t)sms * 3 * (IS_THREADS / 32) * 3;
+    return (int64_t)sms * IS_WARPS_PER_SM;
 }
 
 // Pairs per window for a batch of n_pairs when a window should span `waves` full waves.
 inline int64_t interseq_pairs_per_window(int64_t n_pairs, int waves) {
-    const int64_t win_pairs = interseq_window_groups() / 3 * waves * 64;
+    int64_t win_pairs = interseq_wave_groups() * waves * 64;
+    if (const char *g = getenv("B200ALIGN_WIN_GROUPS")) win_pairs = std::max<int64_t>(64, atoll(g) * 64);
     const int64_t n_windows = std::max<int64_t>(1, (n_pairs + win_pairs - 1) / win_pairs);
     return ((n_pairs + n_windows - 1) / n_windows + 63) / 64 * 64;  // balanced windows
 }
