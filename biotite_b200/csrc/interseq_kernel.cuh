@@ -121,6 +121,15 @@ struct InterseqIO {
 // ---------------------------------------------------------------------------------------
 // eligibility: proven-exact 16-bit range (see DESIGN.md "16-bit safety")
 // ---------------------------------------------------------------------------------------
+// Host threads this process may use for planning: the machine's hardware threads divided by the
+// processes sharing it (one per GPU under torchrun: LOCAL_WORLD_SIZE), B200ALIGN_THREADS overrides.
+inline unsigned interseq_host_threads() {
+    if (const char *t = getenv("B200ALIGN_THREADS")) return (unsigned)std::max(1, atoi(t));
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (const char *w = getenv("LOCAL_WORLD_SIZE")) hw = std::max(1u, hw / (unsigned)std::max(1, atoi(w)));
+    return hw;
+}
+
 // One threaded pass over the pair lengths: everything routing and allocation need to know.
 struct PairScan {
     bool in_range = true;      // 1 <= len <= IS_MAX_LEN for every sequence
@@ -129,7 +138,7 @@ struct PairScan {
 };
 
 inline PairScan interseq_scan(const PairMap &hm, int64_t n_pairs) {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned hw = interseq_host_threads();
     const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(hw, 8u), n_pairs / 65536));
     std::vector<PairScan> part((size_t)n_threads);
     auto work = [&](int t) {
@@ -1029,7 +1038,7 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     }
     {
         // windows are independent: plan them on a few host threads
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned hw = interseq_host_threads();
         const int n_threads = (int)std::min<int64_t>(std::min<unsigned>(hw, 8u), n_windows);
         std::atomic<int64_t> next{0};
         auto work = [&]() {
@@ -1277,7 +1286,7 @@ struct StreamingPlanner {
         return cudaSuccess;
     }
     void start() {
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned hw = interseq_host_threads();
         const int n_threads = (int)std::min<int64_t>(std::min<unsigned>(hw, 8u), n_windows);
         for (int t = 0; t < n_threads; t++) {
             threads.emplace_back([this]() {
