@@ -438,13 +438,17 @@ def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True,
         stop = min(stop, n)
         i_idx = np.repeat(np.arange(rows_done, stop, dtype=np.int32), n - np.arange(rows_done, stop))
         j_idx = np.concatenate([np.arange(i, n, dtype=np.int32) for i in range(rows_done, stop)])
-        # one very long sequence would send the whole chunk to the general kernel: pairs whose
-        # sequences fit the packed kernels are run separately from the rest
-        short = (lengths[i_idx] <= _PACKED_MAX_LEN) & (lengths[j_idx] <= _PACKED_MAX_LEN)
+        # The packed 16-bit kernels are chosen per batch from its longest first / second
+        # sequence: orient every pair shorter-first (the matrix is symmetric, so is the score)
+        # and run the pairs whose shorter sequence keeps the scores inside the 16-bit range
+        # separately from the few that need the 32-bit kernel.
+        swap = lengths[i_idx] > lengths[j_idx]
+        first, second = np.where(swap, j_idx, i_idx), np.where(swap, i_idx, j_idx)
+        short = (lengths[first] <= _packed_shorter_bound(scoring, gap_penalty)) & (lengths[second] <= _PACKED_MAX_LEN)
         for mask in (short, ~short):
             if not mask.any():
                 continue
-            a, b = i_idx[mask], j_idx[mask]
+            a, b = first[mask], second[mask]
             with DeviceBatch(pool.codes, pool.offsets, pool.codes, pool.offsets, scoring, gap_penalty,
                              terminal_penalty, local, None, True, idx1=a, idx2=b) as batch:
                 batch.run()
@@ -455,7 +459,17 @@ def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True,
     return out
 
 
-_PACKED_MAX_LEN = 2000   # IS_MAX_LEN of csrc/interseq_kernel.cuh
+_PACKED_MAX_LEN = 8000   # IS_MAX_LEN of csrc/interseq_kernel.cuh
+
+
+def _packed_shorter_bound(scoring, gap_penalty):
+    """Longest shorter sequence whose scores provably stay below 2^15 (the `highest` bound of
+    interseq_eligible, csrc/interseq_kernel.cuh)."""
+    if isinstance(scoring, tuple):
+        return 0
+    best = max(int(np.max(scoring)), 1)
+    gap_open = gap_penalty[0] if isinstance(gap_penalty, tuple) else gap_penalty
+    return (32766 + int(gap_open) - best) // best
 
 
 def feng_doolittle_distances(sequences, matrix, gap_penalty=-10, terminal_penalty=True):

@@ -893,7 +893,14 @@ extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const 
         hm.off1 = off1; hm.off2 = off2;
         // every length in [1, IS_MAX_LEN] (checked by the scan) makes the offsets monotone
         const PairScan scan = interseq_scan(hm, n_pairs);
-        if (off1[0] == 0 && off2[0] == 0 && interseq_eligible(*params, hm, n_pairs, mn, mx, &scan))
+        // the streaming path sizes its two scratch slots from the longest sequences of the batch;
+        // batches with very long pairs go through the resident path, whose windows follow the
+        // actual direction-table sizes
+        const double slot_dirs = score_only ? 0.0 : (double)(interseq_pairs_per_window(n_pairs, 3) / 64) *
+                                                        (double)((scan.nmax + IS_R - 1) / IS_R) * (double)scan.mmax *
+                                                        128.0 * (params->affine ? 4 : 2);
+        if (off1[0] == 0 && off2[0] == 0 && slot_dirs <= (double)IS_DIR_BUDGET &&
+            interseq_eligible(*params, hm, n_pairs, mn, mx, &scan))
             return align_batch_pipelined(params, codes1, off1, codes2, off2, n_pairs, matrix, score_only, mn, mx, scan,
                                          scores_out, trace_len_out, first_out, ops_out);
     }

@@ -42,7 +42,8 @@ namespace bt {
 
 constexpr int IS_R = 16;            // rows per stripe
 constexpr int IS_THREADS = 128;     // 4 warps per block
-constexpr int IS_MAX_LEN = 2000;    // longest sequence routed here
+constexpr int IS_MAX_LEN = 8000;    // longest sequence routed here
+constexpr int64_t IS_DIR_BUDGET = 40ll << 30;  // direction nibbles resident per window (bytes)
 constexpr int IS_ROWW = 128;        // bytes per table entry row: 32 lanes x 4 bytes
 #ifndef BT_L2PF
 #define BT_L2PF 6
@@ -1022,22 +1023,46 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     score_only = interseq_setup(plan, P, n_pairs, score_only, min_score);
 
     const int64_t per_window = interseq_pairs_per_window(n_pairs, waves_per_window);
-    const int64_t n_windows = (n_pairs + per_window - 1) / per_window;
-    std::vector<WindowPlan> wps((size_t)n_windows);
+    const int64_t groups_per_window = per_window / 64;
+    const int dwpl = P.affine ? 4 : 2;
     // The whole batch is resident: sort it globally by (len1, len2), form the groups of 64, order
     // the groups by descending cost and cut the windows from that list, so that the groups of a
-    // window cost about the same and no window waits for a straggler.
+    // window cost about the same and no window waits for a straggler.  A window also ends when
+    // its direction nibbles would exceed IS_DIR_BUDGET (long pairs: 5000 x 5000 residues need
+    // 0.8 GB per group).
     std::vector<int32_t> global;
-    const int64_t groups_per_window = per_window / 64;
-    if (n_windows > 1) {
+    std::vector<int64_t> wstart{0};            // first group of every window (+ end)
+    const int64_t n_groups_total = (n_pairs + 63) / 64;
+    {
         std::vector<int32_t> sorted;
         interseq_sort_pairs(hm, nullptr, 0, n_pairs, sorted);
-        global.assign((size_t)((n_pairs + 63) / 64 * 64), -1);
+        global.assign((size_t)(n_groups_total * 64), -1);
         std::copy(sorted.rbegin(), sorted.rend(), global.begin());
-        interseq_order_groups_by_cost(hm, global);
+        if (n_groups_total > groups_per_window) interseq_order_groups_by_cost(hm, global);
+        int64_t in_window = 0, dir_bytes = 0;
+        for (int64_t g = 0; g < n_groups_total; g++) {
+            int64_t bytes = 0;
+            if (!score_only) {
+                int64_t nmax = 1, mmax = 1;
+                for (int q = 0; q < 64; q++) {
+                    const int32_t k = global[(size_t)(g * 64 + q)];
+                    if (k < 0) continue;
+                    nmax = std::max(nmax, hm.len1(k)); mmax = std::max(mmax, hm.len2(k));
+                }
+                bytes = (nmax + IS_R - 1) / IS_R * mmax * 32 * dwpl * 4;
+            }
+            if (in_window > 0 && (in_window >= groups_per_window || dir_bytes + bytes > IS_DIR_BUDGET)) {
+                wstart.push_back(g);
+                in_window = 0; dir_bytes = 0;
+            }
+            in_window++; dir_bytes += bytes;
+        }
+        wstart.push_back(n_groups_total);
     }
+    const int64_t n_windows = (int64_t)wstart.size() - 1;
+    std::vector<WindowPlan> wps((size_t)n_windows);
     {
-        // windows are independent: plan them on a few host threads
+        // windows are independent: lay them out on a few host threads
         const unsigned hw = interseq_host_threads();
         const int n_threads = (int)std::min<int64_t>(std::min<unsigned>(hw, 8u), n_windows);
         std::atomic<int64_t> next{0};
@@ -1045,14 +1070,8 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
             for (;;) {
                 const int64_t w = next.fetch_add(1);
                 if (w >= n_windows) break;
-                const int64_t w0 = w * per_window, w1 = std::min(n_pairs, w0 + per_window);
-                if (global.empty()) {
-                    interseq_plan_window(wps[(size_t)w], hm, w0, w1, score_only, P.affine ? 4 : 2);
-                } else {
-                    const int64_t g0 = w * groups_per_window * 64;
-                    const int64_t g1 = std::min<int64_t>((int64_t)global.size(), g0 + groups_per_window * 64);
-                    interseq_plan_window(wps[(size_t)w], hm, w0, w1, score_only, P.affine ? 4 : 2, global.data() + g0, g1 - g0);
-                }
+                const int64_t g0 = wstart[(size_t)w] * 64, g1 = wstart[(size_t)w + 1] * 64;
+                interseq_plan_window(wps[(size_t)w], hm, 0, 0, score_only, dwpl, global.data() + g0, g1 - g0);
             }
         };
         std::vector<std::thread> threads;

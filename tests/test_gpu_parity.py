@@ -727,3 +727,81 @@ def test_packed_kernels_nucleotide_matrix_and_range_guard(monkeypatch):
         res = batch.fetch()
     ref_scores, _ = oracle.batch(codes1, off1, codes2, off2, big, (-1000, -100), True, False, score_only=True)
     assert np.array_equal(res.scores, ref_scores)
+
+
+# ---- long sequences on the packed route (IS_MAX_LEN = 8000, memory-aware windows) ---------------
+
+def test_packed_route_long_database_sequences(monkeypatch):
+    """Config 3 at its real length clip: queries <= 600 against database sequences up to 5000
+    residues, local affine score-only, through the packed 16-bit kernels."""
+    monkeypatch.setenv("B200ALIGN_ROUTE", "packed")
+    rng = np.random.default_rng(101)
+    queries = _random_proteins(rng, 4, 200, 600)
+    lengths = [30, 31, 64, 700, 1999, 2001, 3100, 4999, 5000]
+    db = [bt.ProteinSequence() for _ in range(24)]
+    for k, seq in enumerate(db):
+        n = lengths[k % len(lengths)]
+        seq.code = rng.integers(0, 20, n).astype(np.uint8)
+        # plant a diverged copy of a query so that the optimum is not trivial
+        q = queries[k % 4].code
+        at = int(rng.integers(0, max(1, n - len(q))))
+        piece = q[:max(0, min(len(q), n - at))].copy()
+        flip = rng.random(len(piece)) < 0.2
+        piece[flip] = rng.integers(0, 20, int(flip.sum()))
+        seq.code[at:at + len(piece)] = piece
+    idx1 = np.repeat(np.arange(4, dtype=np.int32), len(db))
+    idx2 = np.tile(np.arange(len(db), dtype=np.int32), 4)
+    res = bt.align_indexed_batch(queries, db, idx1, idx2, BLOSUM(), (-10, -1), local=True, score_only=True)
+    for k in range(len(idx1)):
+        ref = oracle_align_optimal(queries[idx1[k]], db[idx2[k]], BLOSUM(), (-10, -1), local=True, score_only=True)
+        assert res.scores[k] == ref, k
+
+
+def test_packed_route_long_traced_pairs(monkeypatch):
+    """2500-residue pairs, global affine with traces, packed route: 200 MB of direction nibbles
+    per group, windows cut by the direction budget."""
+    monkeypatch.setenv("B200ALIGN_ROUTE", "packed")
+    rng = np.random.default_rng(55)
+    n_pairs = 64
+    len1 = rng.integers(2300, 2600, n_pairs)
+    off1 = np.concatenate(([0], np.cumsum(len1))).astype(np.int64)
+    codes1 = rng.integers(0, 20, off1[-1]).astype(np.uint8)
+    seqs2 = []
+    for k in range(n_pairs):
+        a = codes1[off1[k]:off1[k + 1]].copy()
+        flip = rng.random(len(a)) < 0.3
+        a[flip] = rng.integers(0, 20, int(flip.sum()))
+        seqs2.append(np.delete(a, rng.choice(len(a), 40, replace=False)))
+    off2 = np.concatenate(([0], np.cumsum([len(s) for s in seqs2]))).astype(np.int64)
+    codes2 = np.concatenate(seqs2)
+    matrix = BLOSUM().score_matrix()
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, (-10, -1), True, False) as batch:
+        assert batch.kernel == "interseq_s16x2"
+        batch.run()
+        res = batch.fetch()
+    traces = res.traces()
+    for k in range(0, n_pairs, 11):
+        ref_traces, ref_score = oracle.align_optimal(codes1[off1[k]:off1[k + 1]], codes2[off2[k]:off2[k + 1]],
+                                                     matrix, (-10, -1), True, False, False, 1)
+        assert res.scores[k] == ref_score and np.array_equal(traces[k], ref_traces[0]), k
+
+
+def test_all_vs_all_with_sequences_beyond_the_16_bit_range():
+    """A few sequences long enough that their mutual alignments leave the 16-bit score range
+    (shorter sequence > 2976 residues with BLOSUM62): those pairs take the 32-bit kernel, all
+    others stay packed; pairs are oriented shorter-first."""
+    rng = np.random.default_rng(77)
+    seqs = _random_proteins(rng, 70, 40, 200)
+    base = np.full(3300, 18, dtype=np.uint8)        # tryptophan: 11 per matched residue
+    base[::50] = rng.integers(0, 20, len(base[::50]))
+    for n in (3050, 3300):
+        seq = bt.ProteinSequence()
+        seq.code = base[:n].copy()
+        seqs.append(seq)
+    got = bt.all_vs_all_scores(seqs, BLOSUM(), (-10, -1), terminal_penalty=False)
+    assert np.array_equal(got, got.T)
+    checks = [(70, 71), (70, 70), (3, 71), (0, 70), (5, 9)]
+    for i, j in checks:
+        ref = oracle_align_optimal(seqs[i], seqs[j], BLOSUM(), (-10, -1), terminal_penalty=False, score_only=True)
+        assert got[i, j] == ref, (i, j)
+    assert got[70, 71] > 32767      # the shared 3050-residue prefix scores beyond int16

@@ -27,7 +27,7 @@ def db_lengths(count, cap):
 # C3: 1000 queries (300 +- 100) x database sample, local, score only
 n_q, n_db = 1000, int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 q_codes, q_off = pool(np.clip(np.rint(rng.normal(300, 100, n_q)), 50, 600).astype(np.int64))
-d_codes, d_off = pool(db_lengths(n_db, 2000))
+d_codes, d_off = pool(db_lengths(n_db, 5000))
 idx1 = np.repeat(np.arange(n_q, dtype=np.int32), n_db)
 idx2 = np.tile(np.arange(n_db, dtype=np.int32), n_q)
 t0 = time.perf_counter()
@@ -40,7 +40,7 @@ with bt.DeviceBatch(q_codes, q_off, d_codes, d_off, matrix, (-10, -1), True, Tru
                       "create_s": t1 - t0}))
 # C5: all-vs-all of N proteins, semi-global, scores
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 3000
-codes, off = pool(db_lengths(n, 2000))
+codes, off = pool(db_lengths(n, 2900))   # longer pairs leave the 16-bit range: see all_vs_all_scores
 i_idx, j_idx = np.triu_indices(n)
 i_idx, j_idx = i_idx.astype(np.int32), j_idx.astype(np.int32)
 t0 = time.perf_counter()
