@@ -916,29 +916,45 @@ struct WindowPlan {
     int64_t cells = 0;
 };
 
-// Pair ids `ids[0..cnt)` sorted by (len1, len2) ascending: two stable counting passes.
-inline void interseq_sort_pairs(const PairMap &hm, const int32_t *ids, int64_t id0, int64_t cnt,
-                                std::vector<int32_t> &sorted) {
-    std::vector<int32_t> tmp((size_t)cnt), count(IS_MAX_LEN + 2, 0);
-    sorted.resize((size_t)cnt);
-    auto id = [&](int64_t q) -> int32_t { return ids ? ids[q] : (int32_t)(id0 + q); };
-    for (int64_t q = 0; q < cnt; q++) count[(size_t)hm.len2(id(q)) + 1]++;
-    for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
-    for (int64_t q = 0; q < cnt; q++) { const int32_t k = id(q); tmp[(size_t)count[(size_t)hm.len2(k)]++] = k; }
-    std::fill(count.begin(), count.end(), 0);
-    for (int64_t q = 0; q < cnt; q++) count[(size_t)hm.len1(id(q)) + 1]++;
-    for (size_t c = 1; c < count.size(); c++) count[c] += count[c - 1];
-    for (int64_t q = 0; q < cnt; q++) {
-        const int32_t k = tmp[(size_t)q];
-        sorted[(size_t)count[(size_t)hm.len1(k)]++] = k;
-    }
+// Runs f(t, begin, end) on n_threads chunks of [0, cnt).
+template <typename F>
+inline void interseq_parallel_chunks(int64_t cnt, int n_threads, F f) {
+    std::vector<std::thread> threads;
+    for (int t = 1; t < n_threads; t++) threads.emplace_back(f, t, cnt * t / n_threads, cnt * (t + 1) / n_threads);
+    f(0, (int64_t)0, cnt / n_threads);
+    for (std::thread &t : threads) t.join();
 }
 
-// Lay out one window: its pairs are sorted by (len1, len2) (unless `presorted` already holds
-// them in ascending order) and dealt to groups of 64 - longest first, because the block
-// scheduler hands out groups in index order and the tail of a window should consist of its
-// cheapest groups.  A streamed window is the run of consecutive pairs [w0, w1); a resident
-// batch is sorted as a whole first, so that the groups of one window cost about the same.
+// One stable counting pass: out = in (or the identity id0 + q) ordered by key(id) ascending.
+template <typename K>
+inline void interseq_counting_pass(const int32_t *in, int64_t id0, int64_t cnt, K key, int32_t *out, int n_threads) {
+    const size_t buckets = IS_MAX_LEN + 2;
+    std::vector<int64_t> hist((size_t)n_threads * buckets, 0);
+    auto id = [&](int64_t q) -> int32_t { return in ? in[q] : (int32_t)(id0 + q); };
+    interseq_parallel_chunks(cnt, n_threads, [&](int t, int64_t b, int64_t e) {
+        int64_t *h = hist.data() + (size_t)t * buckets;
+        for (int64_t q = b; q < e; q++) h[(size_t)key(id(q))]++;
+    });
+    int64_t run = 0;   // bucket-major, thread-minor prefix: keeps the pass stable
+    for (size_t c = 0; c < buckets; c++)
+        for (int t = 0; t < n_threads; t++) { int64_t &h = hist[(size_t)t * buckets + c]; const int64_t v = h; h = run; run += v; }
+    interseq_parallel_chunks(cnt, n_threads, [&](int t, int64_t b, int64_t e) {
+        int64_t *h = hist.data() + (size_t)t * buckets;
+        for (int64_t q = b; q < e; q++) { const int32_t k = id(q); out[h[(size_t)key(k)]++] = k; }
+    });
+}
+
+// Pair ids `ids[0..cnt)` sorted by (len1, len2) ascending: two stable counting passes
+// (threaded for large batches).
+inline void interseq_sort_pairs(const PairMap &hm, const int32_t *ids, int64_t id0, int64_t cnt,
+                                std::vector<int32_t> &sorted) {
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(interseq_host_threads(), 16u), cnt / 262144));
+    std::vector<int32_t> tmp((size_t)cnt);
+    sorted.resize((size_t)cnt);
+    interseq_counting_pass(ids, id0, cnt, [&](int32_t k) { return hm.len2(k); }, tmp.data(), n_threads);
+    interseq_counting_pass(tmp.data(), 0, cnt, [&](int32_t k) { return hm.len1(k); }, sorted.data(), n_threads);
+}
+
 // Cost (row steps of the fill kernel) of the group of 64 slots starting at `slots`.
 inline int64_t interseq_group_cost(const PairMap &hm, const int32_t *slots) {
     int64_t nmax = 1, mmax = 1;
@@ -954,10 +970,15 @@ inline void interseq_order_groups_by_cost(const PairMap &hm, std::vector<int32_t
     const int64_t groups = (int64_t)order.size() / 64;
     std::vector<int64_t> cost((size_t)groups);
     std::vector<int32_t> perm((size_t)groups);
-    for (int64_t g = 0; g < groups; g++) { cost[(size_t)g] = interseq_group_cost(hm, order.data() + g * 64); perm[(size_t)g] = (int32_t)g; }
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(interseq_host_threads(), 16u), groups / 8192));
+    interseq_parallel_chunks(groups, n_threads, [&](int, int64_t b, int64_t e) {
+        for (int64_t g = b; g < e; g++) { cost[(size_t)g] = interseq_group_cost(hm, order.data() + g * 64); perm[(size_t)g] = (int32_t)g; }
+    });
     std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return cost[(size_t)a] > cost[(size_t)b]; });
     std::vector<int32_t> out(order.size());
-    for (int64_t g = 0; g < groups; g++) memcpy(out.data() + g * 64, order.data() + (int64_t)perm[(size_t)g] * 64, 64 * 4);
+    interseq_parallel_chunks(groups, n_threads, [&](int, int64_t b, int64_t e) {
+        for (int64_t g = b; g < e; g++) memcpy(out.data() + g * 64, order.data() + (int64_t)perm[(size_t)g] * 64, 64 * 4);
+    });
     order.swap(out);
 }
 
