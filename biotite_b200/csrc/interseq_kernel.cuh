@@ -731,16 +731,24 @@ interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
         }
         uint32_t hu_prev = MODE == IS_GLOBAL ? ((uint32_t)(r0 * C.gap_open) & 0xffffu) * 0x10001u : 0u;  // S(r0, 0)
         uint32_t s_row0 = MODE == IS_GLOBAL ? gap2 : 0u;  // S(0, j) = j * g (pairwise.rs:452-467)
-        uint32_t nxt = cc[0];
-        uint32_t nx_s = 0;
-        if (s > 0) nx_s = rb_s[0];
-        for (int j = 0; j < d.mmax; j++) {
-            const uint32_t v = nxt;
-            uint32_t up = nx_s;
-            if (j + 1 < d.mmax) {
-                nxt = cc[(int64_t)(j + 1) * 32];
-                if (s > 0) nx_s = rb_s[(int64_t)(j + 1) * 32];
-            }
+        // look-ahead registers for column code and row above, LPF columns ahead; the loop is
+        // unrolled LPF times so that they need no rotation (reads past the last column land in
+        // the slack behind the buffers); both streams are pulled into L2 further ahead
+        constexpr int LPF = 2;
+        uint32_t q_c[LPF], q_s[LPF];
+#pragma unroll
+        for (int k = 0; k < LPF; k++) { q_c[k] = cc[(int64_t)k * 32]; q_s[k] = s > 0 ? rb_s[(int64_t)k * 32] : 0u; }
+        for (int j0 = 0; j0 < d.mmax; j0 += LPF) {
+#pragma unroll
+        for (int u = 0; u < LPF; u++) {
+            const int j = j0 + u;
+            if (u > 0 && j >= d.mmax) break;
+            const uint32_t v = q_c[u];
+            uint32_t up = q_s[u];
+            q_c[u] = cc[(int64_t)(j + LPF) * 32];
+            if (s > 0) q_s[u] = rb_s[(int64_t)(j + LPF) * 32];
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(cc + (int64_t)(j + LPF + IS_PREFETCH) * 32));
+            if (s > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(rb_s + (int64_t)(j + LPF + IS_PREFETCH) * 32));
             const char *t_lo = tbase + (v & 0xffu) * col_stride;
             const char *t_hi = tbase + (v >> 8) * col_stride;
             if (s == 0) {
@@ -829,6 +837,7 @@ interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                     }
                 }
             }
+        }
         }
     }
     if (MODE == IS_LOCAL && !TRACED) {
