@@ -530,7 +530,17 @@ def feng_doolittle_distances(sequences, matrix, gap_penalty=-10, terminal_penalt
 
 def _resolve_scoring(matrix, packed1, packed2):
     if isinstance(matrix, tuple):
-        return (int(matrix[0]), int(matrix[1]))
+        match, mismatch = int(matrix[0]), int(matrix[1])
+        # A (match, mismatch) pair over small alphabets is the same function as the matrix
+        # `match` on the diagonal, `mismatch` elsewhere (scoring.rs:101-108): handing the kernels
+        # that matrix makes such batches eligible for the packed 16-bit route.
+        sizes = [len(p.alphabet) for p in (packed1, packed2) if p.alphabet is not None]
+        if len(sizes) == 2 and max(sizes) <= 64 and packed1.codes.dtype == np.uint8 \
+                and packed2.codes.dtype == np.uint8 and -128 <= min(match, mismatch) and max(match, mismatch) <= 127:
+            table = np.full((sizes[0], sizes[1]), mismatch, dtype=np.int32)
+            np.fill_diagonal(table, match)
+            return table
+        return (match, mismatch)
     if isinstance(matrix, SubstitutionMatrix):
         for packed, alph in ((packed1, matrix.get_alphabet1()), (packed2, matrix.get_alphabet2())):
             if packed.alphabet is not None and not alph.extends(packed.alphabet):

@@ -805,3 +805,29 @@ def test_all_vs_all_with_sequences_beyond_the_16_bit_range():
         ref = oracle_align_optimal(seqs[i], seqs[j], BLOSUM(), (-10, -1), terminal_penalty=False, score_only=True)
         assert got[i, j] == ref, (i, j)
     assert got[70, 71] > 32767      # the shared 3050-residue prefix scores beyond int16
+
+
+def test_match_mismatch_tuples_take_the_packed_route(monkeypatch):
+    """A (match, mismatch) pair over a small alphabet is run as the equivalent matrix, so
+    nucleotide batches scored with tuples use the packed kernels; results as the reference's
+    tuple scoring (scoring.rs:101-108), computed by the oracle with the tuple itself."""
+    monkeypatch.setenv("B200ALIGN_ROUTE", "packed")   # the batch is small: skip the cost model
+    rng = np.random.default_rng(91)
+    seqs1 = [_random_seq(rng, int(rng.integers(60, 300))) for _ in range(192)]
+    seqs2 = []
+    for s in seqs1:
+        code = s.code.copy()
+        flip = rng.random(len(code)) < 0.2
+        code[flip] = rng.integers(0, 4, int(flip.sum()))
+        t = bt.NucleotideSequence()
+        t.code = np.delete(code, rng.choice(len(code), 5, replace=False))
+        seqs2.append(t)
+    for gap, local, term in (((-8, -2), False, True), (-6, True, True), ((-5, -1), False, False)):
+        res = bt.align_optimal_batch(seqs1, seqs2, (5, -4), gap, term, local)
+        for k in range(0, 192, 13):
+            ref = oracle_align_optimal(seqs1[k], seqs2[k], (5, -4), gap, term, local, max_number=1)[0]
+            assert res.scores[k] == ref.score and np.array_equal(res.trace(k), ref.trace), (gap, local, term, k)
+    p1, p2 = bt.pack_sequences(seqs1), bt.pack_sequences(seqs2)
+    from biotite_b200.batch import _resolve_scoring
+    with bt.DeviceBatch(p1.codes, p1.offsets, p2.codes, p2.offsets, _resolve_scoring((5, -4), p1, p2), (-8, -2)) as b:
+        assert b.kernel == "interseq_s16x2"
