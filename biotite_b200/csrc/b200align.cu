@@ -360,6 +360,9 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
                              int32_t score_only, bool force_general, BtBatch **batch_out) {
     if (!batch_out) return fail(BT_ERR_INVALID_ARG, "batch_out is NULL");
     *batch_out = nullptr;
+    const bool trace_create = getenv("B200ALIGN_TRACE") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tc0 = now_ms();
     int st = check_params(params);
     if (st) return st;
     if (n_pairs < 0 || n_seq1 < 0 || n_seq2 < 0 || !off1 || !off2) return fail(BT_ERR_INVALID_ARG, "bad pair offsets");
@@ -440,10 +443,13 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     // route: packed 16-bit inter-sequence kernels when they are provably exact
     b->route = ROUTE_GENERAL;
     const PairMap hm = b->host_map();
+    const double tc1 = now_ms();
     if (!force_general && interseq_eligible(*params, hm, n_pairs, mn, mx))
         b->route = ROUTE_INTERSEQ;
     else if (!force_general && !b->stats && banded_eligible(*params, hm, b->h_bands, n_pairs, mn, mx))
         b->route = ROUTE_BANDED;
+    const double tc2 = now_ms();
+    if (trace_create) fprintf(stderr, "[b200align] create: host copies / checks %.1f ms, routing %.1f ms\n", tc1 - tc0, tc2 - tc1);
 
     const size_t cb = (size_t)params->code_bytes;
     CUDA_TRY(b->codes1.alloc((size_t)b->total1 * cb));
@@ -483,6 +489,7 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
         CUDA_TRY(b->is_start.alloc((size_t)n_pairs * 8));
         st = interseq_prepare(b->interseq, *params, hm, n_pairs, b->stats ? 2 : b->score_only, mn, mx,
                               &b->cells, 1, 4, s);
+        if (trace_create) fprintf(stderr, "[b200align] create: uploads + packed plan %.1f ms\n", now_ms() - tc2);
         if (st == BT_ERR_OOM) return fail(st, "out of device memory (inter-sequence plan)");
         if (st) return fail(st, "inter-sequence plan failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else if (b->route == ROUTE_BANDED) {

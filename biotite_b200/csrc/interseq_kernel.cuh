@@ -27,6 +27,7 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -1060,15 +1061,21 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     // window cost about the same and no window waits for a straggler.  A window also ends when
     // its direction nibbles would exceed IS_DIR_BUDGET (long pairs: 5000 x 5000 residues need
     // 0.8 GB per group).
+    const bool trace_plan = getenv("B200ALIGN_TRACE") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tp0 = now_ms();
+    double tp1 = tp0, tp2 = tp0, tp3 = tp0;
     std::vector<int32_t> global;
     std::vector<int64_t> wstart{0};            // first group of every window (+ end)
     const int64_t n_groups_total = (n_pairs + 63) / 64;
     {
         std::vector<int32_t> sorted;
         interseq_sort_pairs(hm, nullptr, 0, n_pairs, sorted);
+        tp1 = now_ms();
         global.assign((size_t)(n_groups_total * 64), -1);
         std::copy(sorted.rbegin(), sorted.rend(), global.begin());
         if (n_groups_total > groups_per_window) interseq_order_groups_by_cost(hm, global);
+        tp2 = now_ms();
         int64_t in_window = 0, dir_bytes = 0;
         for (int64_t g = 0; g < n_groups_total; g++) {
             int64_t bytes = 0;
@@ -1109,6 +1116,7 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
         work();
         for (std::thread &t : threads) t.join();
     }
+    tp3 = now_ms();
     plan.windows.clear();
     plan.order.clear();
     plan.desc.clear();
@@ -1127,6 +1135,9 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     }
     plan.n_groups = (int64_t)plan.desc.size();
     if (cells_out) *cells_out = cells;
+    if (trace_plan)
+        fprintf(stderr, "[b200align] plan: sort %.1f ms, group order %.1f ms, window cut + layout %.1f ms, merge %.1f ms\n",
+                tp1 - tp0, tp2 - tp1, tp3 - tp2, now_ms() - tp3);
 
     cudaError_t e;
     if ((e = plan.d_order.alloc(plan.order.size() * 4)) != cudaSuccess) goto fail;
