@@ -182,7 +182,9 @@ class DeviceBatch:
             result = BatchResult(scores, trace_len, None, None, np.zeros(0, dtype=np.int64), self.bands)
             result.gap_counts = first
             return result
-        return BatchResult(scores, trace_len, first, ops, self._ops_offsets(), self.bands)
+        # step-byte offsets are only needed to expand traces (10^8 score-only pairs: skip 1.4 s)
+        ops_off = np.zeros(0, dtype=np.int64) if self.score_only else self._ops_offsets()
+        return BatchResult(scores, trace_len, first, ops, ops_off, self.bands)
 
     # ---- wire formats emitted on the device (csrc/emit_kernel.cuh) ---------------------------
     def cigars(self, distinguish_matches=False, hard_clip=False, include_terminal_gaps=False,

@@ -393,11 +393,23 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     for (int64_t k = 0; k < n_seq2; k++)
         if (off2[k + 1] < off2[k]) return fail(BT_ERR_INVALID_ARG, "offsets must be non-decreasing");
     if (idx1) {
-        b->h_idx1.assign(idx1, idx1 + n_pairs);
-        b->h_idx2.assign(idx2, idx2 + n_pairs);
-        for (int64_t k = 0; k < n_pairs; k++)
-            if (idx1[k] < 0 || idx1[k] >= n_seq1 || idx2[k] < 0 || idx2[k] >= n_seq2)
-                return fail(BT_ERR_INVALID_ARG, "pair index out of range");
+        // copy + range check on a few threads (10^8 pairs: 0.8 GB of indices)
+        b->h_idx1.resize((size_t)n_pairs);
+        b->h_idx2.resize((size_t)n_pairs);
+        {
+            const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(interseq_host_threads(), 16u), n_pairs / 1048576));
+            std::vector<int> bad((size_t)n_threads, 0);
+            interseq_parallel_chunks(n_pairs, n_threads, [&](int t, int64_t lo, int64_t hi) {
+                int any = 0;
+                for (int64_t k = lo; k < hi; k++) {
+                    const int32_t a = idx1[k], c = idx2[k];
+                    any |= (a < 0) | (a >= n_seq1) | (c < 0) | (c >= n_seq2);
+                    b->h_idx1[(size_t)k] = a; b->h_idx2[(size_t)k] = c;
+                }
+                bad[(size_t)t] = any;
+            });
+            for (int v : bad) if (v) return fail(BT_ERR_INVALID_ARG, "pair index out of range");
+        }
         if (score_only == 0) {   // step bytes of pair k start at the prefix sum of len1 + len2
             b->h_ops_off.resize((size_t)n_pairs);
             int64_t acc = 0;

@@ -1121,11 +1121,34 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     plan.order.clear();
     plan.desc.clear();
     int64_t cells = 0;
+    {
+        // concatenate the windows' group orders / descriptors (copied on a few threads)
+        int64_t g = 0;
+        for (WindowPlan &wp : wps) {
+            wp.win.group_begin = g;
+            g += (int64_t)wp.desc.size();
+            wp.win.group_end = g;
+        }
+        plan.order.resize((size_t)g * 64);
+        plan.desc.resize((size_t)g);
+        const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(interseq_host_threads(), 8u), n_windows));
+        std::atomic<int64_t> next{0};
+        auto copy = [&]() {
+            for (;;) {
+                const int64_t w = next.fetch_add(1);
+                if (w >= n_windows) break;
+                WindowPlan &wp = wps[(size_t)w];
+                if (!wp.order.empty()) memcpy(plan.order.data() + wp.win.group_begin * 64, wp.order.data(), wp.order.size() * 4);
+                if (!wp.desc.empty()) memcpy(plan.desc.data() + wp.win.group_begin, wp.desc.data(), wp.desc.size() * sizeof(WarpDesc));
+                std::vector<int32_t>().swap(wp.order);
+            }
+        };
+        std::vector<std::thread> threads;
+        for (int t = 1; t < n_threads; t++) threads.emplace_back(copy);
+        copy();
+        for (std::thread &t : threads) t.join();
+    }
     for (WindowPlan &wp : wps) {
-        wp.win.group_begin = (int64_t)plan.desc.size();
-        wp.win.group_end = wp.win.group_begin + (int64_t)wp.desc.size();
-        plan.order.insert(plan.order.end(), wp.order.begin(), wp.order.end());
-        plan.desc.insert(plan.desc.end(), wp.desc.begin(), wp.desc.end());
         plan.max_dir_words = std::max(plan.max_dir_words, wp.win.dir_words);
         plan.max_rowbuf = std::max(plan.max_rowbuf, wp.win.rowbuf_entries);
         plan.max_rowcodes = std::max(plan.max_rowcodes, wp.win.rowcodes);

@@ -1,0 +1,154 @@
+"""
+One-vs-many scoring at database scale (BASELINE config 3: many queries against a sequence
+database, local Smith-Waterman, score only).  The reference would call ``align_optimal(q, d,
+..., local=True, score_only=True)`` for every (query, database sequence) pair
+(``src/biotite/sequence/align/pairwise.py:117-244``); here the database is cut into chunks,
+every chunk becomes one indexed GPU batch (no pair is materialised beyond two int32 index
+arrays), and the host prepares chunk ``k + 1`` (index arrays, global sort, window plan, uploads)
+on a worker thread while the GPU scores chunk ``k``.
+
+Multi-GPU: the *database* is sharded (every rank holds all queries):
+:func:`database_shard` gives rank ``r`` of ``world`` its slice with equal residue counts; ranks
+score their slices independently, the only exchange is the final gather of the score columns.
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+from .batch import DeviceBatch, _check_gap_penalty, _resolve_scoring, pack_sequences
+
+__all__ = ["search_scores", "search_scores_sharded", "database_shard"]
+
+
+def database_shard(db_lengths, rank, world_size):
+    """``(begin, end)`` of rank `rank`'s contiguous database slice; slices hold (nearly) the
+    same number of residues, hence the same number of DP cells against any query set."""
+    lengths = np.asarray(db_lengths, dtype=np.int64)
+    prefix = np.concatenate(([0], np.cumsum(lengths)))
+    targets = prefix[-1] * np.arange(1, world_size) / world_size
+    cuts = np.searchsorted(prefix, targets, side="left")
+    bounds = np.maximum.accumulate(np.concatenate(([0], cuts, [len(lengths)])))
+    return int(bounds[rank]), int(bounds[rank + 1])
+
+
+def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, terminal_penalty=True,
+                  chunk_size=100_000, db_range=None, out=None, timings=None):
+    """
+    Optimal alignment score of every query against every database sequence.
+
+    Parameters
+    ----------
+    queries, database : list of Sequence or PackedSequences
+    matrix, gap_penalty, local, terminal_penalty
+        As for ``align_optimal``; the default is local affine scoring.
+    chunk_size : int
+        Database sequences per GPU batch (``len(queries) * chunk_size`` pairs).
+    db_range : (int, int), optional
+        Score only this slice of the database (see :func:`database_shard`).
+    out : ndarray, optional
+        Preallocated ``(len(queries), n_db)`` int32 result.
+    timings : dict, optional
+        Receives ``device_ms`` (sum of the CUDA-event times of the batches) and ``cells``.
+
+    Returns
+    -------
+    scores : ndarray, shape=(len(queries), n_db), dtype=int32
+    """
+    _check_gap_penalty(gap_penalty)
+    q = queries if hasattr(queries, "offsets") else pack_sequences(queries)
+    d = database if hasattr(database, "offsets") else pack_sequences(database)
+    scoring = _resolve_scoring(matrix, q, d)
+    begin, end = (0, len(d)) if db_range is None else (int(db_range[0]), int(db_range[1]))
+    n_q, n_db = len(q), end - begin
+    scores = np.empty((n_q, n_db), dtype=np.int32) if out is None else out
+    if scores.shape != (n_q, n_db):
+        raise ValueError(f"out must have shape {(n_q, n_db)}")
+    chunks = [(c, min(end, c + chunk_size)) for c in range(begin, end, chunk_size)]
+    total_ms, total_cells = 0.0, 0
+
+    def prepare(lo, hi):
+        # database chunk as its own pool: offsets rebased, codes sliced (views, no copies)
+        off = d.offsets[lo:hi + 1] - d.offsets[lo]
+        codes = d.codes[d.offsets[lo]:d.offsets[hi]]
+        idx1 = np.repeat(np.arange(n_q, dtype=np.int32), hi - lo)
+        idx2 = np.tile(np.arange(hi - lo, dtype=np.int32), n_q)
+        return DeviceBatch(q.codes, q.offsets, codes, off, scoring, gap_penalty, terminal_penalty, local,
+                           None, True, idx1=idx1, idx2=idx2)
+
+    # one page-locked staging buffer for the chunks' scores (a pageable D2H target costs
+    # more than the GPU work of small chunks)
+    from . import _cabi
+    staging = _cabi.pinned_empty((n_q * min(chunk_size, max(n_db, 1)),), np.int32)
+    pending = {}
+
+    def prepare_into(k):
+        try:
+            pending[k] = prepare(*chunks[k])
+        except BaseException as exc:   # re-raised on the consuming thread
+            pending[k] = exc
+
+    worker = None
+    if chunks:
+        prepare_into(0)
+    for k, (lo, hi) in enumerate(chunks):
+        batch = pending.pop(k)
+        if isinstance(batch, BaseException):
+            raise batch
+        if k + 1 < len(chunks):
+            worker = threading.Thread(target=prepare_into, args=(k + 1,))
+            worker.start()
+        try:
+            t0 = time.perf_counter()
+            total_ms += batch.run()
+            total_cells += batch.cells
+            t1 = time.perf_counter()
+            part = staging[:n_q * (hi - lo)]
+            batch.fetch(out=(part, None, None, None))
+            scores[:, lo - begin:hi - begin] = part.reshape(n_q, hi - lo)
+            t2 = time.perf_counter()
+        finally:
+            batch.close()
+            if worker is not None:
+                worker.join()
+                worker = None
+        if os.environ.get("B200ALIGN_TRACE"):
+            print(f"[search] chunk {k}: run {t1 - t0:.2f} s, fetch {t2 - t1:.2f} s, wait for next chunk "
+                  f"{time.perf_counter() - t2:.2f} s", file=sys.stderr)
+    if timings is not None:
+        timings["device_ms"] = total_ms
+        timings["cells"] = total_cells
+    return scores
+
+
+def search_scores_sharded(queries, database, matrix, gap_penalty=(-10, -1), local=True,
+                          terminal_penalty=True, chunk_size=100_000, group=None, compute=None, dst=0):
+    """
+    Collective call (one process per GPU, ``torch.distributed``): rank ``r`` scores all queries
+    against its :func:`database_shard`; rank `dst` receives the full ``(n_queries, n_db)``
+    matrix, the other ranks ``None``.  No collective on the data path, only the final gather.
+    `compute` defaults to :func:`search_scores`; the CPU test-suite injects the oracle.
+    """
+    import os
+
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    d = database if hasattr(database, "offsets") else pack_sequences(database)
+    lo, hi = database_shard(d.lengths, rank, world)
+    if compute is None:
+        from . import _cabi
+        _cabi.check(_cabi.load().bt_set_device(int(os.environ.get("LOCAL_RANK", rank))))
+        compute = search_scores
+    part = compute(queries, d, matrix, gap_penalty, local, terminal_penalty, chunk_size, (lo, hi))
+    gathered = [None] * world if rank == dst else None
+    dist.gather_object((lo, part), gathered, dst=dst, group=group)
+    if rank != dst:
+        return None
+    gathered.sort(key=lambda item: item[0])
+    return np.concatenate([g[1] for g in gathered], axis=1)

@@ -96,3 +96,64 @@ def test_two_rank_gloo_gather_matches_single_process(tmp_path):
     assert np.array_equal(got["scores"], ref.scores)
     assert np.array_equal(got["rows_off"], rows_off)
     assert np.array_equal(got["flat"], flat)
+
+
+# ---- database search (config 3): the database is sharded, every rank holds all queries -----------
+
+def _search_inputs(seed=5, n_q=5, n_db=41):
+    rng = np.random.default_rng(seed)
+    from biotite_b200.batch import PackedSequences
+    def pool(count, lo, hi):
+        lengths = rng.integers(lo, hi, count)
+        off = np.concatenate(([0], np.cumsum(lengths))).astype(np.int64)
+        return PackedSequences(rng.integers(0, 20, off[-1]).astype(np.uint8), off, bt.ProteinSequence.alphabet)
+    return pool(n_q, 20, 60), pool(n_db, 5, 120)
+
+
+def _oracle_search(queries, database, matrix, gap, local, term, chunk_size, db_range):
+    from oracle import oracle
+    lo, hi = db_range
+    out = np.zeros((len(queries), hi - lo), dtype=np.int32)
+    for i in range(len(queries)):
+        qc = queries.codes[queries.offsets[i]:queries.offsets[i + 1]]
+        for j in range(lo, hi):
+            dc = database.codes[database.offsets[j]:database.offsets[j + 1]]
+            out[i, j - lo] = oracle.align_optimal(qc, dc, matrix.score_matrix(), gap, term, local, True, 1)[1]
+    return out
+
+
+def _search_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    queries, database = _search_inputs()
+    res = bt.search_scores_sharded(queries, database, bt.SubstitutionMatrix.std_protein_matrix(), (-10, -1),
+                                   compute=_oracle_search)
+    if rank == 0:
+        np.save(out_path, res)
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_database_shard_balances_residues():
+    rng = np.random.default_rng(2)
+    lengths = np.clip(rng.lognormal(np.log(270), 0.7, 5000), 30, 5000).astype(np.int64)
+    for world in (1, 2, 3, 8):
+        bounds = [bt.database_shard(lengths, r, world) for r in range(world)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == len(lengths)
+        assert all(bounds[r][1] == bounds[r + 1][0] for r in range(world - 1))
+        per = np.array([lengths[a:b].sum() for a, b in bounds])
+        assert per.max() <= per.mean() + lengths.max()
+
+
+def test_two_rank_gloo_database_search(tmp_path):
+    import torch.multiprocessing as mp
+    out = tmp_path / "scores.npy"
+    mp.spawn(_search_worker, args=(2, _free_port(), str(out)), nprocs=2, join=True)
+    queries, database = _search_inputs()
+    ref = _oracle_search(queries, database, bt.SubstitutionMatrix.std_protein_matrix(), (-10, -1), True, True,
+                         0, (0, len(database)))
+    assert np.array_equal(np.load(out), ref)

@@ -831,3 +831,28 @@ def test_match_mismatch_tuples_take_the_packed_route(monkeypatch):
     from biotite_b200.batch import _resolve_scoring
     with bt.DeviceBatch(p1.codes, p1.offsets, p2.codes, p2.offsets, _resolve_scoring((5, -4), p1, p2), (-8, -2)) as b:
         assert b.kernel == "interseq_s16x2"
+
+
+def test_search_scores_matches_oracle(monkeypatch):
+    """Config 3 through the chunked, pipelined search API: every query against every database
+    sequence (local affine, score only), database chunks smaller than the database."""
+    monkeypatch.setenv("B200ALIGN_ROUTE", "packed")
+    rng = np.random.default_rng(19)
+    queries = _random_proteins(rng, 8, 60, 300)
+    database = _random_proteins(rng, 50, 30, 900)
+    for k in range(0, 50, 3):      # plant diverged copies of query fragments
+        q = queries[k % 8].code
+        piece = q[:min(len(q), len(database[k].code))].copy()
+        flip = rng.random(len(piece)) < 0.25
+        piece[flip] = rng.integers(0, 20, int(flip.sum()))
+        database[k].code[:len(piece)] = piece
+    timings = {}
+    got = bt.search_scores(queries, database, BLOSUM(), (-10, -1), chunk_size=16, timings=timings)
+    assert got.shape == (8, 50) and timings["cells"] == sum(len(q) for q in queries) * sum(len(d) for d in database)
+    for i in range(8):
+        for j in range(0, 50, 4):
+            assert got[i, j] == oracle_align_optimal(queries[i], database[j], BLOSUM(), (-10, -1), local=True,
+                                                     score_only=True), (i, j)
+    lo, hi = bt.database_shard([len(d) for d in database], 1, 2)
+    part = bt.search_scores(queries, database, BLOSUM(), (-10, -1), chunk_size=16, db_range=(lo, hi))
+    assert np.array_equal(part, got[:, lo:hi])
