@@ -1061,6 +1061,14 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     // window cost about the same and no window waits for a straggler.  A window also ends when
     // its direction nibbles would exceed IS_DIR_BUDGET (long pairs: 5000 x 5000 residues need
     // 0.8 GB per group).
+    // a batch is "uniform" when no pair costs more than a few times the average one: then
+    // stragglers cannot dominate a window and the batch-wide sort buys nothing
+    bool uniform = false;
+    {
+        const PairScan scan = interseq_scan(hm, n_pairs);
+        uniform = scan.max_pair * (double)n_pairs <= 4.0 * scan.total;
+        if (const char *f = getenv("B200ALIGN_SORT")) uniform = strcmp(f, "window") == 0;
+    }
     const bool trace_plan = getenv("B200ALIGN_TRACE") != nullptr;
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tp0 = now_ms();
@@ -1069,12 +1077,27 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     std::vector<int64_t> wstart{0};            // first group of every window (+ end)
     const int64_t n_groups_total = (n_pairs + 63) / 64;
     {
-        std::vector<int32_t> sorted;
-        interseq_sort_pairs(hm, nullptr, 0, n_pairs, sorted);
-        tp1 = now_ms();
         global.assign((size_t)(n_groups_total * 64), -1);
-        std::copy(sorted.rbegin(), sorted.rend(), global.begin());
-        if (n_groups_total > groups_per_window) interseq_order_groups_by_cost(hm, global);
+        if (!uniform) {
+            std::vector<int32_t> sorted;
+            interseq_sort_pairs(hm, nullptr, 0, n_pairs, sorted);
+            tp1 = now_ms();
+            std::copy(sorted.rbegin(), sorted.rend(), global.begin());
+            if (n_groups_total > groups_per_window) interseq_order_groups_by_cost(hm, global);
+        } else {
+            // pairs of about the same size: windows of consecutive pairs, sorted one by one -
+            // their results stay contiguous, which the traceback's step-byte stores like
+            for (int64_t w0 = 0; w0 < n_pairs; w0 += per_window) {
+                const int64_t cnt = std::min(per_window, n_pairs - w0);
+                std::vector<int32_t> sorted, seg((size_t)((cnt + 63) / 64 * 64), -1);
+                interseq_sort_pairs(hm, nullptr, w0, cnt, sorted);
+                std::copy(sorted.rbegin(), sorted.rend(), seg.begin());
+                interseq_order_groups_by_cost(hm, seg);
+                // per_window is a multiple of 64, so only the last segment carries padding
+                std::copy(seg.begin(), seg.end(), global.begin() + w0);
+            }
+            tp1 = now_ms();
+        }
         tp2 = now_ms();
         int64_t in_window = 0, dir_bytes = 0;
         for (int64_t g = 0; g < n_groups_total; g++) {
