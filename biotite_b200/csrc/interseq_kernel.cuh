@@ -599,7 +599,23 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
     // score-only and statistics batches carry no step bytes
     uint8_t *out = (traced && !C.stats) ? ops + A.map.ops(p) : nullptr;
     GapStats gs(C.terminal != 0);
-    auto emit = [&](int op, int &len) { if (C.stats) gs.push(op); else out[len] = (uint8_t)op; len++; };
+    // step bytes are written four at a time once the output position is word-aligned (one
+    // store transaction instead of four; the unaligned head and the tail go out as bytes)
+    uint32_t ew = 0;
+    int enb = 0;
+    const int ealign = (int)((uintptr_t)out & 3u);
+    auto emit = [&](int op, int &len) {
+        if (C.stats) gs.push(op);
+        else if (enb == 0 && ((ealign + len) & 3) != 0) out[len] = (uint8_t)op;
+        else {
+            ew |= (uint32_t)op << (8 * enb);
+            if (++enb == 4) { *(uint32_t *)(out + len - 3) = ew; ew = 0; enb = 0; }
+        }
+        len++;
+    };
+    auto emit_flush = [&](int len) {
+        for (int k = 0; k < enb; k++) out[len - enb + k] = (uint8_t)(ew >> (8 * k));
+    };
     auto nibble = [&](int i, int j) -> uint32_t {  // 1-based table cell (i, j)
         const int rg = i - 1, s = rg / IS_R, r = rg % IS_R;
         const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 128 + (r >> 3)];
@@ -670,6 +686,7 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
             if (MODE == IS_LOCAL) value -= opened ? C.gap_open : C.gap_ext;
         }
     }
+    if (!C.stats && out) emit_flush(len);
     trace_len[p] = len;
     if (C.stats) { gs.finish(); fi = gs.opens; fj = gs.exts; }   // statistics travel in `first`
     first[2 * p] = fi;
@@ -871,7 +888,23 @@ __global__ void interseq_linear_traceback_kernel(const InterseqConst C, const In
     const uint32_t *base = A.dirs + d.dir_off + lane * 2 + half;
     uint8_t *out = C.stats ? nullptr : ops + A.map.ops(p);
     GapStats gs(C.terminal != 0);
-    auto emit = [&](int op, int &len) { if (C.stats) gs.push(op); else out[len] = (uint8_t)op; len++; };
+    // step bytes are written four at a time once the output position is word-aligned (one
+    // store transaction instead of four; the unaligned head and the tail go out as bytes)
+    uint32_t ew = 0;
+    int enb = 0;
+    const int ealign = (int)((uintptr_t)out & 3u);
+    auto emit = [&](int op, int &len) {
+        if (C.stats) gs.push(op);
+        else if (enb == 0 && ((ealign + len) & 3) != 0) out[len] = (uint8_t)op;
+        else {
+            ew |= (uint32_t)op << (8 * enb);
+            if (++enb == 4) { *(uint32_t *)(out + len - 3) = ew; ew = 0; enb = 0; }
+        }
+        len++;
+    };
+    auto emit_flush = [&](int len) {
+        for (int k = 0; k < enb; k++) out[len - enb + k] = (uint8_t)(ew >> (8 * k));
+    };
     int i = n, j = m, len = 0, fi = 0, fj = 0;
     int32_t value = 0;
     if (MODE == IS_LOCAL) { i = A.start[2 * p]; j = A.start[2 * p + 1]; value = A.score[p]; }
@@ -892,6 +925,7 @@ __global__ void interseq_linear_traceback_kernel(const InterseqConst C, const In
             else { emit(OP_TO2, len); i--; }
         }
     }
+    if (!C.stats && out) emit_flush(len);
     trace_len[p] = len;
     if (C.stats) { gs.finish(); fi = gs.opens; fj = gs.exts; }
     first[2 * p] = fi;
