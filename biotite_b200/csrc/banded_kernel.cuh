@@ -326,25 +326,58 @@ __global__ void banded_traceback_kernel(const BandConst C, const BandArgs A, int
     }
     uint8_t *out = ops + A.map.ops(p);
     int i = si, sj = ssj, len = 0, fi = 0, fsj = 0;
+    // step bytes go out four at a time once the position is word-aligned (see the packed kernels)
+    uint32_t ew = 0;
+    int enb = 0;
+    const int ealign = (int)((uintptr_t)out & 3u);
+    auto emit = [&](uint32_t op) {
+        if (enb == 0 && ((ealign + len) & 3) != 0) out[len] = (uint8_t)op;
+        else {
+            ew |= op << (8 * enb);
+            if (++enb == 4) { *(uint32_t *)(out + len - 3) = ew; ew = 0; enb = 0; }
+        }
+        len++;
+    };
     while (i >= 1 && sj >= 0) {
         const int jb = sj - (i - 1) - lower + 1;
         if (jb < 1 || jb > W) break;
-        const uint32_t nb = nibble(i, sj);
-        fi = i; fsj = sj;
         if (st == ST_MATCH) {
-            out[len++] = OP_DIAG; i--; sj--;
-            if (i >= 1 && sj >= 0) {
-                const uint32_t pn = nibble(i, sj);
+            // A diagonal run stays on band column jb and visits (i-1, sj-1), (i-2, sj-2), ...:
+            // their direction words are fetched together, so that a 10 kb trace pays one memory
+            // latency per BD_AHEAD steps instead of one per step.
+            constexpr int BD_AHEAD = 8;
+            uint32_t ahead[BD_AHEAD];
+#pragma unroll
+            for (int t = 0; t < BD_AHEAD; t++) {
+                const int ii = i - 1 - t, jj = sj - 1 - t;
+                ahead[t] = 0;
+                if (ii >= 1 && jj >= 0) {
+                    const int rg = ii - 1, s = rg / BD_R;
+                    ahead[t] = base[((int64_t)s * d.cw + (jj - (s * BD_R + lower))) * 64 + ((rg % BD_R) >> 3)];
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < BD_AHEAD; t++) {
+                fi = i; fsj = sj;
+                emit(OP_DIAG); i--; sj--;
+                if (!(i >= 1 && sj >= 0)) break;
+                const uint32_t pn = (ahead[t] >> (4 * ((i - 1) & 7))) & 0xfu;
                 st = (pn & 1u) ? ST_MATCH : ((pn & 2u) ? ST_GAP1 : ST_GAP2);
+                if (st != ST_MATCH) break;
             }
         } else if (st == ST_GAP1) {
-            out[len++] = OP_TO1; sj--;
+            const uint32_t nb = nibble(i, sj);
+            fi = i; fsj = sj;
+            emit(OP_TO1); sj--;
             st = (nb & 4u) ? ST_MATCH : ST_GAP1;
         } else {
-            out[len++] = OP_TO2; i--;
+            const uint32_t nb = nibble(i, sj);
+            fi = i; fsj = sj;
+            emit(OP_TO2); i--;
             st = (nb & 8u) ? ST_MATCH : ST_GAP2;
         }
     }
+    for (int k = 0; k < enb; k++) out[len - enb + k] = (uint8_t)(ew >> (8 * k));
     trace_len[p] = len;
     first[2 * p] = fi;
     first[2 * p + 1] = len ? fsj - (fi - 1) - lower + 1 : 0;   // band column, as bt_expand_traces expects
