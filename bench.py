@@ -250,6 +250,11 @@ def main():
 
     # ------------------------------------------------------------------ B200 arm
     from biotite_b200 import _cabi
+    numa_cpus = None
+    if world > 1:
+        # one process per GPU: stay on the GPU's NUMA node (pinned staging, planning threads)
+        from biotite_b200.distributed import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local_rank)
     lib = _cabi.load()
     if lib.bt_device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
@@ -381,6 +386,8 @@ def main():
                 "pairs_per_s": args.pairs * world * args.steps / e2e_s},
         "gpu_launches": launches, "roofline": roofline, "score_checksum_rank0": checksum,
     }
+    if numa_cpus is not None:
+        line["config"]["host_binding"] = f"rank 0 bound to the {len(numa_cpus)} CPUs of its GPU's NUMA node"
     if rank == 0 and not args.no_cpu_baseline:
         threads = cpu_threads()
         gcups, n_used, dt = time_cpu_oracle(codes1, off1, codes2, off2, matrix, args.cpu_seconds, threads)

@@ -14,7 +14,7 @@ import numpy as np
 
 from .batch import BatchResult, align_batch_arrays
 
-__all__ = ["shard_bounds", "align_batch_sharded"]
+__all__ = ["shard_bounds", "align_batch_sharded", "bind_to_gpu_numa_node"]
 
 
 def shard_bounds(off1, off2, world_size):
@@ -73,3 +73,38 @@ def align_batch_sharded(codes1, off1, codes2, off2, scoring, gap_penalty, termin
     first = np.concatenate([g[4] for g in gathered])
     ops = np.concatenate([g[5] for g in gathered])
     return BatchResult(scores, trace_len, first, ops, off1 + off2)
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """
+    Restrict this process to the CPUs next to GPU `local_rank` (its PCIe root's NUMA node), so
+    that page-locked staging buffers are allocated in, and the planning threads run on, the
+    memory the GPU's copy engines reach without crossing the socket interconnect.  One process
+    per GPU otherwise shares the first node's memory bandwidth.  Returns the CPU set, or
+    ``None`` when the topology cannot be read (nothing is changed then).
+    """
+    import subprocess
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i",
+                              str(local_rank)], capture_output=True, text=True, timeout=20).stdout.strip()
+        if not bus:
+            return None
+        # sysfs uses a 4-digit PCI domain, nvidia-smi prints 8 digits
+        domain, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{domain[-4:].lower()}:{rest.lower()}/local_cpulist"
+        with open(path) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except (OSError, ValueError, subprocess.SubprocessError):
+        return None
