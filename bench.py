@@ -206,6 +206,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its
+    # version banner on file descriptor 1), so everything but the final line goes to stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     config = {
         "workload": "C2: synthetic protein pairs ~300 aa (N(300,30) clipped [200,400], half homologous), "
                     "global affine (-10,-1) BLOSUM62, terminal_penalty=True, score + first-optimal trace",
@@ -245,7 +254,7 @@ def main():
             "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -262,8 +271,6 @@ def main():
 
     dist = None
     if world > 1:
-        # NCCL prints its version banner to stdout; the contract is ONE JSON line there
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -399,7 +406,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     return 0
 
 
