@@ -335,15 +335,21 @@ def main():
     # ---- end to end through the public batch API (host buffers in, host buffers out) ---------
     def e2e_step():
         # the public one-shot batch API: host arrays in, host arrays out
+        t_step = time.perf_counter()
         bt.align_batch_arrays(p_codes1, off1, p_codes2, off2, matrix, GAP, True, False, out=out)
+        if os.environ.get("B200ALIGN_TRACE"):
+            print(f"[bench] rank {rank}: e2e step {1e3 * (time.perf_counter() - t_step):.2f} ms", file=sys.stderr)
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
+    # every step returns with its results in host memory: the rank's clock stops here, the
+    # closing barrier (an NCCL launch that can take tens of ms after idle time) is not work
+    e2e_local = time.perf_counter() - t0
     barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = max_over_ranks(e2e_local)
     e2e_value = total_cells * args.steps / e2e_s * 1e-9
     h2d = int(sum_over_ranks(float(p_codes1.nbytes + p_codes2.nbytes + off1.nbytes + off2.nbytes + matrix.nbytes)))
     d2h = int(sum_over_ranks(float(sum(a.nbytes for a in out))))
