@@ -1,5 +1,6 @@
+"""BASELINE config 4 at full size: 10^5 pairs of 10 kb nucleotide sequences (5 % substitutions, one\nindel block), band +-128, NUC matrix, affine (-10,-1), semi-global, score + trace; device-timed."""
 import sys, json, numpy as np
-sys.path.insert(0,'.')
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent))
 import biotite_b200 as bt
 rng = np.random.default_rng(0)
 n_pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 32768

@@ -1,5 +1,6 @@
+"""Timeline of the one-shot path on config 2 (10^6 pairs): run with B200ALIGN_TRACE=1 to get the\nper-window start / input-ready / kernels-done / results-returned times of bt_align_batch."""
 import sys, time, numpy as np
-sys.path.insert(0,'.')
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent))
 import bench, biotite_b200 as bt
 from biotite_b200 import _cabi
 n=1000000
