@@ -32,6 +32,7 @@ from .pairwise import align_optimal
 from .banded import align_banded
 from .batch import (
     BatchResult,
+    CompositeBatchResult,
     DeviceBatch,
     PackedSequences,
     align_batch_arrays,

@@ -563,10 +563,86 @@ def align_optimal_batch(seqs1, seqs2, matrix, gap_penalty=-10, terminal_penalty=
     if len(p1) != len(p2):
         raise ValueError("Both lists must hold the same number of sequences")
     scoring = _resolve_scoring(matrix, p1, p2)
+    # The library routes a batch as a whole: a few pairs beyond the packed kernels' limits
+    # (a titin among 10^6 ordinary proteins) would send everything to the 32-bit kernel.  Such
+    # pairs are run as a batch of their own and the results are stitched together.
+    len1, len2 = p1.lengths, p2.lengths
+    outlier = np.maximum(len1, len2) > _PACKED_MAX_LEN
+    if not isinstance(scoring, tuple):
+        outlier |= np.minimum(len1, len2) > _packed_shorter_bound(scoring, gap_penalty)
+    if len(p1) >= 128 and outlier.any() and outlier.sum() * 8 <= len(p1):
+        parts, index = [], []
+        for mask in (~outlier, outlier):
+            ids = np.nonzero(mask)[0]
+            q1, q2 = _take(p1, ids), _take(p2, ids)
+            part = align_batch_arrays(q1.codes, q1.offsets, q2.codes, q2.offsets, scoring, gap_penalty,
+                                      terminal_penalty, local, None, score_only)
+            parts.append(part)
+            index.append(ids)
+        return CompositeBatchResult(parts, index, p1.sequences, p2.sequences)
     result = align_batch_arrays(p1.codes, p1.offsets, p2.codes, p2.offsets, scoring, gap_penalty,
                                 terminal_penalty, local, None, score_only)
     result.seqs1, result.seqs2 = p1.sequences, p2.sequences
     return result
+
+
+def _take(packed, ids):
+    """The sequences `ids` of a :class:`PackedSequences` as a new one (codes gathered)."""
+    lengths = packed.lengths[ids]
+    offsets = np.zeros(len(ids) + 1, dtype=np.int64)
+    np.cumsum(lengths, out=offsets[1:])
+    # positions of the gathered residues: start of each sequence + running index inside it
+    starts = np.repeat(packed.offsets[:-1][ids] - offsets[:-1], lengths)
+    codes = packed.codes[starts + np.arange(int(offsets[-1]), dtype=np.int64)]
+    return PackedSequences(codes, offsets, packed.alphabet, None)
+
+
+class CompositeBatchResult:
+    """
+    Results of a batch that was run in several parts (pairs outside the packed kernels' limits
+    separately from the rest); same interface as :class:`BatchResult`, pair numbering of the
+    original batch.
+    """
+
+    def __init__(self, parts, index, seqs1=None, seqs2=None):
+        self.parts, self.index = parts, index
+        n = sum(len(ids) for ids in index)
+        self.scores = np.empty(n, dtype=np.int32)
+        self._part = np.empty(n, dtype=np.int32)
+        self._local = np.empty(n, dtype=np.int64)
+        for k, (part, ids) in enumerate(zip(parts, index)):
+            self.scores[ids] = part.scores
+            self._part[ids] = k
+            self._local[ids] = np.arange(len(ids))
+        self.trace_len = None
+        if all(part.trace_len is not None for part in parts):
+            self.trace_len = np.empty(n, dtype=np.int64)
+            for part, ids in zip(parts, index):
+                self.trace_len[ids] = part.trace_len
+        self.seqs1, self.seqs2 = seqs1, seqs2
+
+    def __len__(self):
+        return len(self.scores)
+
+    def trace(self, k):
+        return self.parts[self._part[k]].trace(int(self._local[k]))
+
+    def traces(self):
+        out = [None] * len(self)
+        for part, ids in zip(self.parts, self.index):
+            for local, trace in enumerate(part.traces()):
+                out[ids[local]] = trace
+        return out
+
+    def alignment(self, k, seq1=None, seq2=None):
+        seq1 = self.seqs1[k] if seq1 is None else seq1
+        seq2 = self.seqs2[k] if seq2 is None else seq2
+        return Alignment([seq1, seq2], self.trace(k), int(self.scores[k]))
+
+    def alignments(self):
+        traces = self.traces()
+        return [Alignment([self.seqs1[k], self.seqs2[k]], traces[k], int(self.scores[k]))
+                for k in range(len(self))]
 
 
 def align_banded_batch(seqs1, seqs2, matrix, bands, gap_penalty=-10, local=False,

@@ -856,3 +856,37 @@ def test_search_scores_matches_oracle(monkeypatch):
     lo, hi = bt.database_shard([len(d) for d in database], 1, 2)
     part = bt.search_scores(queries, database, BLOSUM(), (-10, -1), chunk_size=16, db_range=(lo, hi))
     assert np.array_equal(part, got[:, lo:hi])
+
+
+def test_batch_with_outlier_pairs_is_split():
+    """A couple of pairs beyond the packed kernels' limits (8000 residues / 16-bit scores) in an
+    otherwise ordinary batch: they run as a batch of their own, results keep the batch order."""
+    rng = np.random.default_rng(123)
+    seqs1 = _random_proteins(rng, 200, 50, 250)
+    seqs2 = []
+    for s in seqs1:
+        code = s.code.copy()
+        flip = rng.random(len(code)) < 0.25
+        code[flip] = rng.integers(0, 20, int(flip.sum()))
+        t = bt.ProteinSequence()
+        t.code = np.delete(code, rng.choice(len(code), 4, replace=False))
+        seqs2.append(t)
+    long1, long2 = bt.ProteinSequence(), bt.ProteinSequence()
+    long1.code = rng.integers(0, 20, 8300).astype(np.uint8)
+    long2.code = np.delete(long1.code, rng.choice(8300, 60, replace=False))
+    rich1, rich2 = bt.ProteinSequence(), bt.ProteinSequence()
+    rich1.code = np.full(3100, 18, dtype=np.uint8)
+    rich2.code = np.full(3050, 18, dtype=np.uint8)
+    seqs1[17], seqs2[17] = long1, long2
+    seqs1[120], seqs2[120] = rich1, rich2
+    res = bt.align_optimal_batch(seqs1, seqs2, BLOSUM(), (-10, -1), terminal_penalty=False)
+    assert isinstance(res, bt.CompositeBatchResult) and len(res) == 200
+    assert res.scores[120] > 32767
+    for k in (0, 16, 17, 18, 119, 120, 121, 199):
+        ref = oracle_align_optimal(seqs1[k], seqs2[k], BLOSUM(), (-10, -1), terminal_penalty=False, max_number=1)[0]
+        assert res.scores[k] == ref.score and np.array_equal(res.trace(k), ref.trace), k
+        assert res.alignment(k) == ref
+    traces = res.traces()
+    assert all(len(traces[k]) == res.trace_len[k] for k in range(200))
+    only = bt.align_optimal_batch(seqs1, seqs2, BLOSUM(), (-10, -1), terminal_penalty=False, score_only=True)
+    assert np.array_equal(only.scores, res.scores)
