@@ -69,6 +69,8 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
     scores = np.empty((n_q, n_db), dtype=np.int32) if out is None else out
     if scores.shape != (n_q, n_db):
         raise ValueError(f"out must have shape {(n_q, n_db)}")
+    # a batch holds at most 2^31 - 1 pairs; 64 database sequences are the smallest useful chunk
+    chunk_size = int(max(1, min(chunk_size, (2**31 - 1) // max(n_q, 1))))
     chunks = [(c, min(end, c + chunk_size)) for c in range(begin, end, chunk_size)]
     total_ms, total_cells = 0.0, 0
 
