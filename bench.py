@@ -300,6 +300,8 @@ def main():
     # pinned host staging for the end-to-end path
     p_codes1 = _cabi.pinned_empty(codes1.shape, np.uint8); p_codes1[:] = codes1
     p_codes2 = _cabi.pinned_empty(codes2.shape, np.uint8); p_codes2[:] = codes2
+    p_off1 = _cabi.pinned_empty(off1.shape, np.int64); p_off1[:] = off1
+    p_off2 = _cabi.pinned_empty(off2.shape, np.int64); p_off2[:] = off2
     n = args.pairs
     out = (_cabi.pinned_empty((n,), np.int32), _cabi.pinned_empty((n,), np.int64),
            _cabi.pinned_empty((n, 2), np.int32),
@@ -336,7 +338,7 @@ def main():
     def e2e_step():
         # the public one-shot batch API: host arrays in, host arrays out
         t_step = time.perf_counter()
-        bt.align_batch_arrays(p_codes1, off1, p_codes2, off2, matrix, GAP, True, False, out=out)
+        bt.align_batch_arrays(p_codes1, p_off1, p_codes2, p_off2, matrix, GAP, True, False, out=out)
         if os.environ.get("B200ALIGN_TRACE"):
             print(f"[bench] rank {rank}: e2e step {1e3 * (time.perf_counter() - t_step):.2f} ms", file=sys.stderr)
     for _ in range(max(1, min(args.warmup, 2))):

@@ -798,14 +798,16 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     cudaEvent_t tev0 = nullptr;
     if (trace) { cudaEventCreate(&tev0); cudaEventRecord(tev0, st.h2d); }
     CUDA_TRY(cudaMemsetAsync(d_flag.ptr, 0, 4, st.h2d));
-    CUDA_TRY(cudaMemcpyAsync(d_off1.ptr, off1, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.h2d));
-    CUDA_TRY(cudaMemcpyAsync(d_off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, st.h2d));
     CUDA_TRY(cudaMemcpyAsync(d_matrix.ptr, matrix, mb, cudaMemcpyHostToDevice, st.h2d));
     // input codes of window w on the copy stream; in_ready[w] fires when they have arrived
     auto enqueue_inputs = [&](int64_t w) -> cudaError_t {
         const int64_t p0 = planner.bounds[(size_t)w], p1 = planner.bounds[(size_t)w + 1];
         const int64_t a1 = h_off1[p0], b1 = h_off1[p1], a2 = h_off2[p0], b2 = h_off2[p1];
-        cudaError_t e = cudaMemcpyAsync((char *)d_codes1.ptr + a1, (const char *)codes1 + a1, (size_t)(b1 - a1), cudaMemcpyHostToDevice, st.h2d);
+        // the window's slice of the offsets travels with its codes (a caller's pageable offset
+        // arrays make these copies synchronous: small slices keep the first window's wait short)
+        cudaError_t e = cudaMemcpyAsync(d_off1.as<int64_t>() + p0, off1 + p0, (size_t)(p1 - p0 + 1) * 8, cudaMemcpyHostToDevice, st.h2d);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off2.as<int64_t>() + p0, off2 + p0, (size_t)(p1 - p0 + 1) * 8, cudaMemcpyHostToDevice, st.h2d);
+        if (e == cudaSuccess) e = cudaMemcpyAsync((char *)d_codes1.ptr + a1, (const char *)codes1 + a1, (size_t)(b1 - a1), cudaMemcpyHostToDevice, st.h2d);
         if (e == cudaSuccess) e = cudaMemcpyAsync((char *)d_codes2.ptr + a2, (const char *)codes2 + a2, (size_t)(b2 - a2), cudaMemcpyHostToDevice, st.h2d);
         if (e == cudaSuccess) e = cudaEventRecord(st.in_ready[(size_t)w], st.h2d);
         return e;
