@@ -87,6 +87,12 @@ __global__ void banded_pack_kernel(const uint8_t *codes1, const uint8_t *codes2,
     for (int j = sub; j < d.mmax; j += nsub) colcodes[d.colcode_off + (int64_t)j * 32 + lane] = j < m ? codes2[b + j] : 0;
 }
 
+#ifndef BD_PF
+#define BD_PF 2
+#endif
+#ifndef BD_MIN_BLOCKS
+#define BD_MIN_BLOCKS 3      // 168 registers: the unrolled look-ahead does not fit 128 without spills
+#endif
 // max with one predicate: adds `c` to `acc` where the FIRST operand attains the maximum
 #define BD_MAX_PRED(out, a, b, acc, c)                                                    \
     asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %2, %3;\n\tmax.s32 %0, %2, %3;\n\t"         \
@@ -95,7 +101,7 @@ __global__ void banded_pack_kernel(const uint8_t *codes1, const uint8_t *codes2,
         : "r"(a), "r"(b), "r"(c))
 
 template <bool TRACED>
-__global__ void __launch_bounds__(BD_THREADS, 4)
+__global__ void __launch_bounds__(BD_THREADS, BD_MIN_BLOCKS)
 banded_fill_kernel(const BandConst C, const BandArgs A) {
     extern __shared__ int32_t btable[];  // [b][a][lane], one private copy per lane (no bank conflicts)
     const int lane = threadIdx.x & 31;
@@ -170,19 +176,31 @@ banded_fill_kernel(const BandConst C, const BandArgs A) {
                 um = rg_m[(int64_t)slot * 32]; uf = rg_f[(int64_t)slot * 32]; uh = rg_h[(int64_t)slot * 32];
             }
         };
-        int32_t hu_prev, nx_m, nx_f, nx_h;
+        int32_t hu_prev;
         { int32_t t0, t1; above(c_first - 1, t0, t1, hu_prev); }
-        above(c_first, nx_m, nx_f, nx_h);
         auto col_code = [&](int c) -> uint32_t {
             const int sjc = min(max(base_j + c, 0), d.mmax - 1);
             return cc[(int64_t)sjc * 32];
         };
-        uint32_t nx_code = col_code(c_first);
-        for (int c = c_first; c <= c_last; c++) {
-            int32_t up_m = nx_m, up_f2 = nx_f;
-            const int32_t hu = nx_h;
-            const uint32_t code = nx_code;
-            if (c < c_last) { above(c + 1, nx_m, nx_f, nx_h); nx_code = col_code(c + 1); }   // one column ahead
+        // The row above and the column letters are fetched BD_PF columns ahead; the column loop is
+        // unrolled BD_PF times so that the look-ahead registers need no rotation (a register
+        // move would wait for the load it forwards - the top stall site before).
+        int32_t q_m[BD_PF], q_f[BD_PF], q_h[BD_PF];
+        uint32_t q_code[BD_PF];
+#pragma unroll
+        for (int k = 0; k < BD_PF; k++) {
+            q_m[k] = q_f[k] = q_h[k] = NEG; q_code[k] = 0;
+            if (c_first + k <= c_last) { above(c_first + k, q_m[k], q_f[k], q_h[k]); q_code[k] = col_code(c_first + k); }
+        }
+        for (int c0 = c_first; c0 <= c_last; c0 += BD_PF) {
+#pragma unroll
+        for (int u = 0; u < BD_PF; u++) {
+            const int c = c0 + u;
+            if (u > 0 && c > c_last) break;
+            int32_t up_m = q_m[u], up_f2 = q_f[u];
+            const int32_t hu = q_h[u];
+            const uint32_t code = q_code[u];
+            if (c + BD_PF <= c_last) { above(c + BD_PF, q_m[u], q_f[u], q_h[u]); q_code[u] = col_code(c + BD_PF); }
             const int sj = base_j + c;
             const char *t_col = tbase + code * col_stride;
             uint32_t acc0 = 0, acc1 = 0;   // nibbles of rows 0-7 and 8-15
@@ -270,6 +288,7 @@ banded_fill_kernel(const BandConst C, const BandArgs A) {
 #pragma unroll
                 for (int r = 0; r < BD_R; r++) lastcol[(int64_t)(r0 + r) * 32] = Hl[r];
             }
+        }
         }
     }
 }
@@ -461,6 +480,19 @@ inline int banded_prepare(BandedPlan &plan, const BtParams &P, const PairMap &hm
     plan.desc.resize((size_t)plan.n_groups);
     plan.windows.clear();
     const int64_t dir_budget_words = (int64_t)(88ll << 30) / 4;   // direction nibbles resident per window
+    // A warp carries its 32 pairs through all stripes, so a window takes one "wave time" per
+    // started wave of resident warps: cut the batch into the smallest number of windows that
+    // fit the resident warps, equally large (3125 groups on 1776 slots: 2 x 1563, not 1776 + 1349
+    // or - with the budget alone - 2000 + 1125, which needs three wave times).
+    int64_t groups_per_window = plan.n_groups;
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t slots = (int64_t)sms * BD_MIN_BLOCKS * (BD_THREADS / 32);
+        const int64_t n_win = std::max<int64_t>(1, (plan.n_groups + slots - 1) / slots);
+        groups_per_window = (plan.n_groups + n_win - 1) / n_win;
+    }
     BandWindow win{};
     int64_t cells = 0, max_dir = 0, max_ring = 0, max_rowc = 0, max_colc = 0, max_lr = 0, max_lc = 0;
     auto close = [&](int64_t g_end) {
@@ -494,7 +526,7 @@ inline int banded_prepare(BandedPlan &plan, const BtParams &P, const PairMap &hm
         while (ring < BD_R + wmax + 2) ring <<= 1;
         d.ring = ring;
         const int64_t dir_words = score_only ? 0 : (int64_t)d.stripes * d.cw * 64;
-        if (win.group_begin < g && win.dir_words + dir_words > dir_budget_words) close(g);
+        if (win.group_begin < g && (win.dir_words + dir_words > dir_budget_words || g - win.group_begin >= groups_per_window)) close(g);
         d.dir_off = win.dir_words; d.ring_off = win.ring_entries;
         d.rowcode_off = win.rowcodes; d.colcode_off = win.colcodes;
         d.lastrow_off = win.lastrow; d.lastcol_off = win.lastcol;
