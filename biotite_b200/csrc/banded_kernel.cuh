@@ -494,7 +494,25 @@ inline int banded_prepare(BandedPlan &plan, const BtParams &P, const PairMap &hm
         groups_per_window = (plan.n_groups + n_win - 1) / n_win;
     }
     BandWindow win{};
-    int64_t cells = 0, max_dir = 0, max_ring = 0, max_rowc = 0, max_colc = 0, max_lr = 0, max_lc = 0;
+    // in-band, in-sequence cells of the batch (banded.rs:199-207), counted on a few threads
+    int64_t cells = 0;
+    {
+        const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(interseq_host_threads(), 16u), n_pairs / 256));
+        std::vector<int64_t> part((size_t)n_threads, 0);
+        interseq_parallel_chunks(n_pairs, n_threads, [&](int t, int64_t b, int64_t e) {
+            int64_t acc = 0;
+            for (int64_t k = b; k < e; k++) {
+                const int64_t n = hm.len1(k), m = hm.len2(k), lo = bands[2 * k], up = bands[2 * k + 1];
+                for (int64_t i = 0; i < n; i++) {
+                    const int64_t j0 = std::max<int64_t>(i + lo, 0), j1 = std::min<int64_t>(i + up + 1, m);
+                    if (j1 > j0) acc += j1 - j0;
+                }
+            }
+            part[(size_t)t] = acc;
+        });
+        for (int64_t v : part) cells += v;
+    }
+    int64_t max_dir = 0, max_ring = 0, max_rowc = 0, max_colc = 0, max_lr = 0, max_lc = 0;
     auto close = [&](int64_t g_end) {
         win.group_end = g_end;
         plan.windows.push_back(win);
@@ -513,10 +531,6 @@ inline int banded_prepare(BandedPlan &plan, const BtParams &P, const PairMap &hm
             const int64_t lo = bands[2 * k], up = bands[2 * k + 1];
             nmax = std::max<int>(nmax, (int)n); mmax = std::max<int>(mmax, (int)m);
             wmax = std::max<int>(wmax, (int)(up - lo + 1));
-            for (int64_t i = 0; i < n; i++) {   // in-band, in-sequence cells (banded.rs:199-207)
-                const int64_t j0 = std::max<int64_t>(i + lo, 0), j1 = std::min<int64_t>(i + up + 1, m);
-                if (j1 > j0) cells += j1 - j0;
-            }
         }
         BandDesc &d = plan.desc[(size_t)g];
         d.nmax = nmax; d.mmax = mmax; d.wmax = wmax;
