@@ -417,47 +417,92 @@ class _IndexedView:
 
 
 def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True, local=False,
-                      chunk_pairs=1 << 24):
+                      chunk_pairs=1 << 24, timings=None):
     """
     Symmetric ``(N, N)`` int32 matrix of optimal alignment scores of every pair ``i <= j``
     (the quantity the reference's ``align_multiple`` computes pair by pair for its guide
     tree, ``multiple.pyx:322-333``).  The triangle is enumerated in chunks of `chunk_pairs`
-    index pairs; the sequences are uploaded once per chunk call, never the pairs.
+    index pairs; the sequences are uploaded once per chunk call, never the pairs.  `timings`
+    (a dict) receives the summed CUDA-event time ``device_ms`` and the ``cells`` of the batches.
+    `sequences` may be a list of ``Sequence`` or a :class:`PackedSequences`.
     """
     _check_gap_penalty(gap_penalty)
-    pool = pack_sequences(sequences)
+    pool = sequences if hasattr(sequences, "offsets") else pack_sequences(sequences)
     scoring = _resolve_scoring(matrix, pool, pool)
     if not isinstance(scoring, tuple) and not np.array_equal(scoring, scoring.T):
         raise ValueError("all_vs_all_scores needs a symmetric substitution matrix")
     n = len(pool)
     out = np.zeros((n, n), dtype=np.int32)
     lengths = pool.lengths
-    rows_done = 0
-    while rows_done < n:
-        # rows i = rows_done .. stop-1 of the upper triangle (j >= i)
-        counts = n - np.arange(rows_done, n)
-        stop = rows_done + max(1, int(np.searchsorted(np.cumsum(counts), chunk_pairs, side="right")))
-        stop = min(stop, n)
-        i_idx = np.repeat(np.arange(rows_done, stop, dtype=np.int32), n - np.arange(rows_done, stop))
-        j_idx = np.concatenate([np.arange(i, n, dtype=np.int32) for i in range(rows_done, stop)])
-        # The packed 16-bit kernels are chosen per batch from its longest first / second
-        # sequence: orient every pair shorter-first (the matrix is symmetric, so is the score)
-        # and run the pairs whose shorter sequence keeps the scores inside the 16-bit range
-        # separately from the few that need the 32-bit kernel.
-        swap = lengths[i_idx] > lengths[j_idx]
-        first, second = np.where(swap, j_idx, i_idx), np.where(swap, i_idx, j_idx)
-        short = (lengths[first] <= _packed_shorter_bound(scoring, gap_penalty)) & (lengths[second] <= _PACKED_MAX_LEN)
-        for mask in (short, ~short):
-            if not mask.any():
-                continue
-            a, b = first[mask], second[mask]
-            with DeviceBatch(pool.codes, pool.offsets, pool.codes, pool.offsets, scoring, gap_penalty,
-                             terminal_penalty, local, None, True, idx1=a, idx2=b) as batch:
-                batch.run()
-                scores = batch.fetch().scores
-            out[a, b] = scores
-            out[b, a] = scores
-        rows_done = stop
+    bound = _packed_shorter_bound(scoring, gap_penalty)
+    total_ms, total_cells = 0.0, 0
+
+    def chunks():
+        """Index pairs (first, second) of one batch after the other."""
+        rows_done = 0
+        while rows_done < n:
+            # rows i = rows_done .. stop-1 of the upper triangle (j >= i)
+            counts = n - np.arange(rows_done, n)
+            stop = rows_done + max(1, int(np.searchsorted(np.cumsum(counts), chunk_pairs, side="right")))
+            stop = min(stop, n)
+            i_idx = np.repeat(np.arange(rows_done, stop, dtype=np.int32), n - np.arange(rows_done, stop))
+            j_idx = np.concatenate([np.arange(i, n, dtype=np.int32) for i in range(rows_done, stop)])
+            # The packed 16-bit kernels are chosen per batch from its longest first / second
+            # sequence: orient every pair shorter-first (the matrix is symmetric, so is the
+            # score) and run the pairs whose shorter sequence keeps the scores inside the 16-bit
+            # range separately from the few that need the 32-bit kernel.
+            swap = lengths[i_idx] > lengths[j_idx]
+            first, second = np.where(swap, j_idx, i_idx), np.where(swap, i_idx, j_idx)
+            short = (lengths[first] <= bound) & (lengths[second] <= _PACKED_MAX_LEN)
+            for mask in (short, ~short):
+                if mask.any():
+                    yield first[mask], second[mask]
+            rows_done = stop
+
+    def prepare(a, b):
+        return a, b, DeviceBatch(pool.codes, pool.offsets, pool.codes, pool.offsets, scoring, gap_penalty,
+                                 terminal_penalty, local, None, True, idx1=a, idx2=b)
+
+    # the next batch is built (index arrays, sort, plan, uploads) while the GPU scores this one
+    import threading
+    source = chunks()
+    slot = {}
+
+    def prepare_next(done=None):
+        try:
+            if done is not None:       # scores of the previous batch -> both triangles
+                a, b, scores = done
+                out[a, b] = scores
+                out[b, a] = scores
+            item = next(source, None)
+            slot["next"] = None if item is None else prepare(*item)
+        except BaseException as exc:   # re-raised on the consuming thread
+            slot["next"] = exc
+
+    prepare_next()
+    done = None
+    while slot["next"] is not None:
+        current = slot.pop("next")
+        if isinstance(current, BaseException):
+            raise current
+        a, b, batch = current
+        worker = threading.Thread(target=prepare_next, args=(done,))
+        worker.start()
+        try:
+            total_ms += batch.run()
+            total_cells += batch.cells
+            done = (a, b, batch.fetch().scores)
+        finally:
+            batch.close()
+            worker.join()
+    if isinstance(slot.get("next"), BaseException):
+        raise slot["next"]
+    if done is not None:
+        out[done[0], done[1]] = done[2]
+        out[done[1], done[0]] = done[2]
+    if timings is not None:
+        timings["device_ms"] = total_ms
+        timings["cells"] = total_cells
     return out
 
 
