@@ -542,10 +542,35 @@ def feng_doolittle_distances(sequences, matrix, gap_penalty=-10, terminal_penalt
     n = len(pool)
     i_idx, j_idx = np.tril_indices(n)          # i >= j, including the diagonal
     i_idx, j_idx = i_idx.astype(np.int32), j_idx.astype(np.int32)
-    with DeviceBatch(pool.codes, pool.offsets, pool.codes, pool.offsets, scoring, gap_penalty,
-                     terminal_penalty, False, None, False, idx1=i_idx, idx2=j_idx, stats=True) as batch:
-        batch.run()
-        res = batch.fetch()
+    # The orientation (sequence i first, j second, i >= j) is the reference's and is kept: the
+    # first-optimal trace, hence the gap counts, may depend on it.  The library routes a batch
+    # as a whole by its longest first / second sequence, so the pairs are run in up to three
+    # batches: first sequence inside the 16-bit bound, else second inside it, else neither
+    # (the 32-bit kernel; a handful of pairs of very long sequences).
+    lengths = pool.lengths
+    bound = _packed_shorter_bound(scoring, gap_penalty)
+    len_i, len_j = lengths[i_idx], lengths[j_idx]
+    fits = (len_i <= _PACKED_MAX_LEN) & (len_j <= _PACKED_MAX_LEN)
+    first_short = fits & (len_i <= bound)
+    second_short = fits & ~first_short & (len_j <= bound)
+    rest = ~(first_short | second_short)
+
+    class _Stats:
+        scores = np.zeros(len(i_idx), dtype=np.int32)
+        trace_len = np.zeros(len(i_idx), dtype=np.int64)
+        gap_counts = np.zeros((len(i_idx), 2), dtype=np.int32)
+    res = _Stats()
+    for mask in (first_short, second_short, rest):
+        if not mask.any():
+            continue
+        with DeviceBatch(pool.codes, pool.offsets, pool.codes, pool.offsets, scoring, gap_penalty,
+                         terminal_penalty, False, None, False, idx1=i_idx[mask], idx2=j_idx[mask],
+                         stats=True) as batch:
+            batch.run()
+            part = batch.fetch()
+        res.scores[mask] = part.scores
+        res.trace_len[mask] = part.trace_len
+        res.gap_counts[mask] = part.gap_counts
     scores = np.zeros((n, n), dtype=np.int32)
     scores[i_idx, j_idx] = res.scores
     gap_open, gap_ext = (gap_penalty if isinstance(gap_penalty, tuple) else (gap_penalty, gap_penalty))
