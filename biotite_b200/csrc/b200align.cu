@@ -727,6 +727,39 @@ extern "C" int bt_batch_fetch_gapped(BtBatch *b, const uint8_t *symbols1, int32_
     return BT_OK;
 }
 
+// Host planning of a resident packed batch, without any device work (CPU tests of the planner).
+extern "C" int bt_debug_plan(const BtParams *params, const int64_t *off1, const int64_t *off2, int64_t n_pairs,
+                             int32_t score_only, int32_t waves_per_window, int32_t *order_out, int64_t order_cap,
+                             int64_t *n_groups_out, int64_t *window_groups_out, int64_t *window_dir_bytes_out,
+                             int64_t window_cap, int64_t *n_windows_out, int64_t *cells_out) {
+    int st = check_params(params);
+    if (st) return st;
+    if (!off1 || !off2 || n_pairs < 1 || !n_groups_out || !n_windows_out)
+        return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    PairMap hm;
+    hm.off1 = off1; hm.off2 = off2;
+    const PairScan scan = interseq_scan(hm, n_pairs);
+    if (!scan.in_range) return fail(BT_ERR_RANGE, "a sequence is outside the packed kernels' length range");
+    InterseqPlan plan;
+    int64_t cells = 0;
+    interseq_plan_host(plan, *params, hm, n_pairs, score_only, 0, &cells, std::max(1, (int)waves_per_window));
+    *n_groups_out = plan.n_groups;
+    *n_windows_out = (int64_t)plan.windows.size();
+    if (cells_out) *cells_out = cells;
+    if (order_out) {
+        if ((int64_t)plan.order.size() > order_cap) return fail(BT_ERR_INVALID_ARG, "order_out is too small");
+        memcpy(order_out, plan.order.data(), plan.order.size() * 4);
+    }
+    if (window_groups_out || window_dir_bytes_out) {
+        if ((int64_t)plan.windows.size() > window_cap) return fail(BT_ERR_INVALID_ARG, "window arrays are too small");
+        for (size_t w = 0; w < plan.windows.size(); w++) {
+            if (window_groups_out) window_groups_out[w] = plan.windows[w].group_end - plan.windows[w].group_begin;
+            if (window_dir_bytes_out) window_dir_bytes_out[w] = plan.windows[w].dir_words * 4;
+        }
+    }
+    return BT_OK;
+}
+
 extern "C" int64_t bt_batch_cells(const BtBatch *b) { return b ? b->cells : 0; }
 extern "C" int64_t bt_batch_launches(const BtBatch *b) { return b ? b->launches : 0; }
 extern "C" const char *bt_batch_kernel(const BtBatch *b) {

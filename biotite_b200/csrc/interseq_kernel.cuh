@@ -939,9 +939,12 @@ __global__ void interseq_linear_traceback_kernel(const InterseqConst C, const In
 // Groups per wave of the affine fill kernel (one warp per block, IS_WARPS_PER_SM blocks per SM):
 // windows are whole numbers of waves, so that they lose little to partial waves.
 inline int64_t interseq_wave_groups() {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+        cudaGetLastError();
+        sms = 148;   // B200; only reached without a device (bt_debug_plan in the CPU tests)
+    }
     return (int64_t)sms * IS_WARPS_PER_SM;
 }
 
@@ -1081,10 +1084,10 @@ inline int interseq_setup(InterseqPlan &plan, const BtParams &P, int64_t n_pairs
     return plan.C.score_only;
 }
 
-inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap &hm, int64_t n_pairs, int score_only,
-                            int32_t min_score, int32_t max_score, int64_t *cells_out, int n_slots,
-                            int waves_per_window, cudaStream_t stream) {
-    (void)max_score;
+// Host part of the plan of a resident batch (no device work: also reachable through
+// bt_debug_plan for the CPU tests): group order, descriptors and windows.
+inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const PairMap &hm, int64_t n_pairs,
+                               int score_only, int32_t min_score, int64_t *cells_out, int waves_per_window) {
     score_only = interseq_setup(plan, P, n_pairs, score_only, min_score);
 
     const int64_t per_window = interseq_pairs_per_window(n_pairs, waves_per_window);
@@ -1117,7 +1120,7 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
             interseq_sort_pairs(hm, nullptr, 0, n_pairs, sorted);
             tp1 = now_ms();
             std::copy(sorted.rbegin(), sorted.rend(), global.begin());
-            if (n_groups_total > groups_per_window) interseq_order_groups_by_cost(hm, global);
+            interseq_order_groups_by_cost(hm, global);   // also inside a single window: longest groups first
         } else {
             // pairs of about the same size: windows of consecutive pairs, sorted one by one -
             // their results stay contiguous, which the traceback's step-byte stores like
@@ -1218,7 +1221,13 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
     if (trace_plan)
         fprintf(stderr, "[b200align] plan: sort %.1f ms, group order %.1f ms, window cut + layout %.1f ms, merge %.1f ms\n",
                 tp1 - tp0, tp2 - tp1, tp3 - tp2, now_ms() - tp3);
+}
 
+inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap &hm, int64_t n_pairs, int score_only,
+                            int32_t min_score, int32_t max_score, int64_t *cells_out, int n_slots,
+                            int waves_per_window, cudaStream_t stream) {
+    (void)max_score;
+    interseq_plan_host(plan, P, hm, n_pairs, score_only, min_score, cells_out, waves_per_window);
     cudaError_t e;
     if ((e = plan.d_order.alloc(plan.order.size() * 4)) != cudaSuccess) goto fail;
     if ((e = plan.d_desc.alloc(plan.desc.size() * sizeof(WarpDesc))) != cudaSuccess) goto fail;
