@@ -37,6 +37,21 @@ template <int KIND> __global__ void __launch_bounds__(256) k(uint32_t *out, int 
                         "setp.eq.s16 pl, x0, y0;\n\tsetp.eq.s16 ph, x1, y1;\n\t" \
                         "@pl mad.lo.u32 %1, %5, " #k ", %1;\n\t@ph mad.lo.u32 %2, %5, " #k ", %2;\n\t}" \
                         : "=&r"(out), "+r"(acc), "+r"(acc2) : "r"(x), "r"(y), "r"(one))
+#define MPU(out, x, y, k) asm volatile("{\n\t.reg .pred pl, ph;\n\t.reg .u16 x0, x1, y0, y1;\n\t" \
+                        "max.u16x2 %0, %3, %4;\n\tmov.b32 {x0, x1}, %0;\n\tmov.b32 {y0, y1}, %3;\n\t" \
+                        "setp.eq.u16 pl, x0, y0;\n\tsetp.eq.u16 ph, x1, y1;\n\t" \
+                        "@pl add.u32 %1, %1, " #k ";\n\t@ph add.u32 %2, %2, " #k ";\n\t}" \
+                        : "=&r"(out), "+r"(acc), "+r"(acc2) : "r"(x), "r"(y))
+#define MNU(out, x, y, k) asm volatile("max.u16x2 %0, %1, %2;" : "=r"(out) : "r"(x), "r"(y))
+#define CELL32(M_) { uint32_t fe, t, to; \
+                    asm volatile("add.u32 %0, %1, %2;" : "=r"(fe) : "r"(b[c]), "r"(c1)); \
+                    M_(b[c], a[c], fe, 0x4); \
+                    asm volatile("add.u32 %0, %1, %2;" : "=r"(fe) : "r"(a[c]), "r"(c1)); \
+                    M_(t, b[c], fe, 0x8); \
+                    M_(to, t, b[c], 0x2); \
+                    asm volatile("add.u32 %0, %1, %2;" : "=r"(to) : "r"(to), "r"(c1)); \
+                    asm volatile("add.u32 %0, %1, %2;" : "=r"(fe) : "r"(a[c]), "r"(t)); \
+                    M_(a[c], fe, to, 0x1); }
 #define CELL(M_) { uint32_t fe, t, to; \
                     asm volatile("add.s16x2 %0, %1, %2;" : "=r"(fe) : "r"(b[c]), "r"(c1)); \
                     M_(b[c], a[c], fe, 0x4); \
@@ -51,6 +66,9 @@ template <int KIND> __global__ void __launch_bounds__(256) k(uint32_t *out, int 
                 else if (KIND == 1) CELL(MU)
                 else if (KIND == 2) CELL(MN)
                 else if (KIND == 3) CELL(MI)
+                else if (KIND == 4) CELL32(MPU)
+                else if (KIND == 5) CELL32(MNU)
+                else if (KIND == 6) CELL32(MP)
             }
         }
     }
@@ -83,6 +101,9 @@ int main() {
         run<1>("cell: unpredicated adds", w);
         run<2>("cell: no adds (4 add16 + 4 max)", w);
         run<3>("cell: pred IMAD", w);
+        run<4>("cell32: u16x2 max + pred adds + 32-bit adds", w);
+        run<5>("cell32: no pred adds (4 add32 + 4 maxu)", w);
+        run<6>("cell32: s16x2 max + pred adds + 32-bit adds", w);
     }
     return 0;
 }
