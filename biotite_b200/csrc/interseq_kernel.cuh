@@ -302,6 +302,9 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
     const uint32_t ext2 = ((uint32_t)C.gap_ext & 0xffffu) * 0x10001u;
     const uint32_t open2 = ((uint32_t)C.gap_open & 0xffffu) * 0x10001u;
     const uint32_t neg2 = ((uint32_t)C.neg & 0xffffu) * 0x10001u;
+    // packed zero the compiler cannot see through: with a literal 0 ptxas rebuilds the operand
+    // (PRMT RZ) for every VIADDMNMX / VIMNMX3 that clamps at zero, one ALU instruction per row
+    const uint32_t zero2 = (uint32_t)C.n_cols >> 31;
     // this lane's 16 profile bytes of (half, letter b): pbase + (half * n_cols + b) * 512
     const uint32_t pbase = (uint32_t)__cvta_generic_to_shared(smem_prof) + lane * 16;
     const uint32_t pbase_hi = pbase + (uint32_t)C.n_cols * 512u;
@@ -439,7 +442,7 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
         const uint32_t fe = __vadd2(F1l[r], ext2);                                           \
         if (TRACED) { BT_MAX_PRED(F1l[r], Ml[r], fe, BT_ACC_LO(r, 2), BT_ACC_HI(r, 2), BT_BIT(r, 2)); } \
         else F1l[r] = __vmaxs2(Ml[r], fe);                                                   \
-        Ml[r] = MODE == IS_LOCAL ? __viaddmax_s16x2(diag_h, sim[r], 0u) : __vadd2(diag_h, sim[r]); \
+        Ml[r] = MODE == IS_LOCAL ? __viaddmax_s16x2(diag_h, sim[r], zero2) : __vadd2(diag_h, sim[r]); \
     }
             BT_ROW_F1_M(0, hu_prev);
             hu_prev = hu;
@@ -503,7 +506,7 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                 if (!TRACED) {
                     // score only: packed running maximum; padding rows (last stripe) and padding
                     // columns are masked to 0, which never beats the running maximum (>= 0)
-                    uint32_t cm = 0;
+                    uint32_t cm = zero2;
                     if (rows_valid) {
 #pragma unroll
                         for (int r = 0; r < IS_R; r += 2) cm = __vimax3_s16x2(cm, Ml[r], Ml[r + 1]);
@@ -724,6 +727,7 @@ interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
     if (p_hi >= 0) { n_hi = (int)A.map.len1(p_hi); m_hi = (int)A.map.len2(p_hi); }
 
     const uint32_t gap2 = ((uint32_t)C.gap_open & 0xffffu) * 0x10001u;
+    const uint32_t zero2 = (uint32_t)C.n_cols >> 31;  // packed zero in a register (see the affine kernel)
     const uint32_t col_stride = (uint32_t)C.n_rows * IS_ROWW;
     const char *tbase = (const char *)table + lane * 4;
     const uint16_t *rc = A.rowcodes + d.rowcode_off + lane;
@@ -793,7 +797,7 @@ interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                 } else {
                     sc = __viaddmax_s16x2(__vmaxs2(Sl[r], up), gap2, a[r]);
                 }
-                if (MODE == IS_LOCAL) sc = __vmaxs2(sc, 0u);  // pairwise.rs:410-413
+                if (MODE == IS_LOCAL) sc = __vmaxs2(sc, zero2);  // pairwise.rs:410-413
                 Sl[r] = sc;
                 up = sc;
             }
@@ -811,7 +815,7 @@ interseq_linear_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                 bool slow = false;
                 if (!TRACED) {
                     // score only: packed running maximum, padding rows / columns masked to 0
-                    uint32_t cm = 0;
+                    uint32_t cm = zero2;
                     if (rows_valid) {
 #pragma unroll
                         for (int r = 0; r < IS_R; r += 2) cm = __vimax3_s16x2(cm, Sl[r], Sl[r + 1]);
