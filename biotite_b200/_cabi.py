@@ -115,7 +115,7 @@ def load():
         ctypes.POINTER(BtParams), _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _i32, _i64, _vp, _vp,
         ctypes.POINTER(_vp)]
     lib.bt_debug_plan.argtypes = [
-        ctypes.POINTER(BtParams), _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]
+        ctypes.POINTER(BtParams), _vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]
     lib.bt_expand_traces.argtypes = [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.bt_pinned_alloc.restype = _vp
     lib.bt_pinned_alloc.argtypes = [ctypes.c_size_t]

@@ -731,7 +731,8 @@ extern "C" int bt_batch_fetch_gapped(BtBatch *b, const uint8_t *symbols1, int32_
 extern "C" int bt_debug_plan(const BtParams *params, const int64_t *off1, const int64_t *off2, int64_t n_pairs,
                              int32_t score_only, int32_t waves_per_window, int32_t *order_out, int64_t order_cap,
                              int64_t *n_groups_out, int64_t *window_groups_out, int64_t *window_dir_bytes_out,
-                             int64_t window_cap, int64_t *n_windows_out, int64_t *cells_out) {
+                             int64_t window_cap, int64_t *n_windows_out, int64_t *cells_out,
+                             uint64_t *layout_hash_out) {
     int st = check_params(params);
     if (st) return st;
     if (!off1 || !off2 || n_pairs < 1 || !n_groups_out || !n_windows_out)
@@ -746,6 +747,20 @@ extern "C" int bt_debug_plan(const BtParams *params, const int64_t *off1, const 
     *n_groups_out = plan.n_groups;
     *n_windows_out = (int64_t)plan.windows.size();
     if (cells_out) *cells_out = cells;
+    if (layout_hash_out) {
+        // FNV-1a over everything the kernels get from the plan besides the order: group descriptors,
+        // window records and the scratch sizes
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&h](const void *p, size_t n) {
+            const unsigned char *c = (const unsigned char *)p;
+            for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ull; }
+        };
+        if (!plan.desc.empty()) mix(plan.desc.data(), plan.desc.size() * sizeof(WarpDesc));
+        if (!plan.windows.empty()) mix(plan.windows.data(), plan.windows.size() * sizeof(Window));
+        const int64_t sizes[4] = {plan.max_dir_words, plan.max_rowbuf, plan.max_rowcodes, plan.max_colcodes};
+        mix(sizes, sizeof(sizes));
+        *layout_hash_out = h;
+    }
     if (order_out) {
         if ((int64_t)plan.order.size() > order_cap) return fail(BT_ERR_INVALID_ARG, "order_out is too small");
         memcpy(order_out, plan.order.data(), plan.order.size() * 4);

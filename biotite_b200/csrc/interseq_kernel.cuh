@@ -1033,15 +1033,107 @@ inline void interseq_order_groups_by_cost(const PairMap &hm, std::vector<int32_t
     order.swap(out);
 }
 
+// Host array without value initialisation (std::vector would memset hundreds of MB on one thread
+// before the planner's threads overwrite every element).
+template <typename T>
+struct RawBuf {
+    std::unique_ptr<T[]> p;
+    size_t n = 0;
+    void alloc(size_t count) { p.reset(new T[count]); n = count; }
+    T *data() { return p.get(); }
+    const T *data() const { return p.get(); }
+    bool empty() const { return n == 0; }
+    size_t size() const { return n; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+};
+
+// Batch-wide order of a ragged resident batch: the result of interseq_sort_pairs (ascending by
+// (len1, len2), stable), reversed into groups of 64 slots and ordered by descending group cost
+// (interseq_order_groups_by_cost) - but the lengths travel with the pair ids as 64-bit records
+// (len1 << 48 | len2 << 32 | id), so the counting passes and everything after them stream
+// through memory instead of looking the lengths of every pair up again (10^8 pairs: the
+// look-ups were most of the planning time).  Also returns the lengths per slot
+// (len1 << 16 | len2, 0 for padding) and the longest sequences per group.
+inline void interseq_order_batch(const PairMap &hm, int64_t n_pairs, RawBuf<int32_t> &order,
+                                 RawBuf<uint32_t> &order_nm, std::vector<int32_t> &group_n,
+                                 std::vector<int32_t> &group_m, double *t_sorted_ms) {
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(interseq_host_threads(), 16u), n_pairs / 262144));
+    const size_t buckets = IS_MAX_LEN + 2;
+    // uninitialised on purpose: the threads below touch (and so place) the pages themselves
+    std::unique_ptr<uint64_t[]> rec_a(new uint64_t[(size_t)n_pairs]), rec_b(new uint64_t[(size_t)n_pairs]);
+    interseq_parallel_chunks(n_pairs, n_threads, [&](int, int64_t b, int64_t e) {
+        for (int64_t q = b; q < e; q++)
+            rec_a[(size_t)q] = (uint64_t)hm.len1(q) << 48 | (uint64_t)hm.len2(q) << 32 | (uint64_t)(uint32_t)q;
+    });
+    // one stable counting pass over the records by the 16-bit field at `shift`
+    auto pass = [&](const uint64_t *in, uint64_t *out, int shift) {
+        std::vector<int64_t> hist((size_t)n_threads * buckets, 0);
+        interseq_parallel_chunks(n_pairs, n_threads, [&](int t, int64_t b, int64_t e) {
+            int64_t *h = hist.data() + (size_t)t * buckets;
+            for (int64_t q = b; q < e; q++) h[(size_t)(in[q] >> shift & 0xffffu)]++;
+        });
+        int64_t run = 0;   // bucket-major, thread-minor prefix: keeps the pass stable
+        for (size_t c = 0; c < buckets; c++)
+            for (int t = 0; t < n_threads; t++) { int64_t &h = hist[(size_t)t * buckets + c]; const int64_t v = h; h = run; run += v; }
+        interseq_parallel_chunks(n_pairs, n_threads, [&](int t, int64_t b, int64_t e) {
+            int64_t *h = hist.data() + (size_t)t * buckets;
+            for (int64_t q = b; q < e; q++) out[h[(size_t)(in[q] >> shift & 0xffffu)]++] = in[q];
+        });
+    };
+    pass(rec_a.get(), rec_b.get(), 32);   // by len2
+    pass(rec_b.get(), rec_a.get(), 48);   // then by len1
+    rec_b.reset();
+    if (t_sorted_ms) *t_sorted_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+
+    // groups of 64 slots over the descending order; cost and longest sequences per group
+    const int64_t groups = (n_pairs + 63) / 64;
+    std::vector<int64_t> cost((size_t)groups);
+    std::vector<int32_t> perm((size_t)groups), gn((size_t)groups), gm((size_t)groups);
+    const int g_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(interseq_host_threads(), 16u), groups / 8192));
+    interseq_parallel_chunks(groups, g_threads, [&](int, int64_t b, int64_t e) {
+        for (int64_t g = b; g < e; g++) {
+            int32_t nmax = 1, mmax = 1;
+            const int64_t s1 = std::min<int64_t>(n_pairs, g * 64 + 64);
+            for (int64_t slot = g * 64; slot < s1; slot++) {
+                const uint64_t r = rec_a[(size_t)(n_pairs - 1 - slot)];
+                nmax = std::max<int32_t>(nmax, (int32_t)(r >> 48)); mmax = std::max<int32_t>(mmax, (int32_t)(r >> 32 & 0xffffu));
+            }
+            gn[(size_t)g] = nmax; gm[(size_t)g] = mmax;
+            cost[(size_t)g] = (int64_t)(nmax + IS_R - 1) / IS_R * mmax;
+            perm[(size_t)g] = (int32_t)g;
+        }
+    });
+    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return cost[(size_t)a] > cost[(size_t)b]; });
+    order.alloc((size_t)groups * 64);
+    order_nm.alloc((size_t)groups * 64);
+    group_n.resize((size_t)groups); group_m.resize((size_t)groups);
+    interseq_parallel_chunks(groups, g_threads, [&](int, int64_t b, int64_t e) {
+        for (int64_t g = b; g < e; g++) {
+            const int64_t src = perm[(size_t)g];
+            group_n[(size_t)g] = gn[(size_t)src]; group_m[(size_t)g] = gm[(size_t)src];
+            const int64_t s1 = std::min<int64_t>(n_pairs, src * 64 + 64);
+            int64_t q = g * 64;
+            for (int64_t slot = src * 64; slot < s1; slot++, q++) {
+                const uint64_t r = rec_a[(size_t)(n_pairs - 1 - slot)];
+                order[(size_t)q] = (int32_t)(uint32_t)r;
+                order_nm[(size_t)q] = (uint32_t)(r >> 48) << 16 | (uint32_t)(r >> 32 & 0xffffu);
+            }
+            for (; q < g * 64 + 64; q++) { order[(size_t)q] = -1; order_nm[(size_t)q] = 0u; }   // padding slots
+        }
+    });
+}
+
 inline void interseq_plan_window(WindowPlan &wp, const PairMap &hm, int64_t w0, int64_t w1, int score_only,
-                                 int dir_words_per_lane, const int32_t *slots = nullptr, int64_t n_slot_ids = 0) {
+                                 int dir_words_per_lane, const int32_t *slots = nullptr, int64_t n_slot_ids = 0,
+                                 const uint32_t *slot_nm = nullptr) {
     Window &win = wp.win;
     win.pair_begin = w0; win.pair_end = w1;
     int64_t groups;
     if (slots) {
-        // resident batch: the groups were formed and ordered globally (interseq_prepare)
+        // resident batch: the groups were formed and ordered globally (interseq_plan_host), which
+        // also copies them into the plan; wp.order stays empty
         groups = n_slot_ids / 64;
-        wp.order.assign(slots, slots + n_slot_ids);
     } else {
         const int64_t cnt = w1 - w0;
         std::vector<int32_t> sorted;
@@ -1052,12 +1144,15 @@ inline void interseq_plan_window(WindowPlan &wp, const PairMap &hm, int64_t w0, 
         interseq_order_groups_by_cost(hm, wp.order);
     }
     wp.desc.resize((size_t)groups);
+    const int32_t *ord = slots ? slots : wp.order.data();
     for (int64_t g = 0; g < groups; g++) {
         int nmax = 1, mmax = 1;
         for (int q = 0; q < 64; q++) {
-            const int32_t k = wp.order[(size_t)(g * 64 + q)];
+            const int32_t k = ord[g * 64 + q];
             if (k < 0) continue;
-            const int64_t n = hm.len1(k), m = hm.len2(k);
+            // lengths per slot when the caller carries them (interseq_order_batch)
+            const int64_t n = slot_nm ? (int64_t)(slot_nm[g * 64 + q] >> 16) : hm.len1(k);
+            const int64_t m = slot_nm ? (int64_t)(slot_nm[g * 64 + q] & 0xffffu) : hm.len2(k);
             nmax = std::max<int>(nmax, (int)n); mmax = std::max<int>(mmax, (int)m);
             wp.cells += n * m;
         }
@@ -1114,18 +1209,18 @@ inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const Pair
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tp0 = now_ms();
     double tp1 = tp0, tp2 = tp0, tp3 = tp0;
-    std::vector<int32_t> global;
+    RawBuf<int32_t> global;
+    RawBuf<uint32_t> global_nm;                // lengths per slot of `global` (batch-wide sort only)
+    std::vector<int32_t> group_n, group_m;     // longest sequences per group (batch-wide sort only)
     std::vector<int64_t> wstart{0};            // first group of every window (+ end)
     const int64_t n_groups_total = (n_pairs + 63) / 64;
     {
-        global.assign((size_t)(n_groups_total * 64), -1);
         if (!uniform) {
-            std::vector<int32_t> sorted;
-            interseq_sort_pairs(hm, nullptr, 0, n_pairs, sorted);
-            tp1 = now_ms();
-            std::copy(sorted.rbegin(), sorted.rend(), global.begin());
-            interseq_order_groups_by_cost(hm, global);   // also inside a single window: longest groups first
+            // batch-wide sort, groups ordered by cost (also inside a single window: longest first)
+            interseq_order_batch(hm, n_pairs, global, global_nm, group_n, group_m, &tp1);
         } else {
+            global.alloc((size_t)(n_groups_total * 64));
+            std::fill(global.data(), global.data() + global.size(), -1);
             // pairs of about the same size: windows of consecutive pairs, sorted one by one -
             // their results stay contiguous, which the traceback's step-byte stores like
             for (int64_t w0 = 0; w0 < n_pairs; w0 += per_window) {
@@ -1135,7 +1230,7 @@ inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const Pair
                 std::copy(sorted.rbegin(), sorted.rend(), seg.begin());
                 interseq_order_groups_by_cost(hm, seg);
                 // per_window is a multiple of 64, so only the last segment carries padding
-                std::copy(seg.begin(), seg.end(), global.begin() + w0);
+                std::copy(seg.begin(), seg.end(), global.data() + w0);
             }
             tp1 = now_ms();
         }
@@ -1143,7 +1238,9 @@ inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const Pair
         int64_t in_window = 0, dir_bytes = 0;
         for (int64_t g = 0; g < n_groups_total; g++) {
             int64_t bytes = 0;
-            if (!score_only) {
+            if (!score_only && !group_n.empty()) {
+                bytes = (int64_t)(group_n[(size_t)g] + IS_R - 1) / IS_R * group_m[(size_t)g] * 32 * dwpl * 4;
+            } else if (!score_only) {
                 int64_t nmax = 1, mmax = 1;
                 for (int q = 0; q < 64; q++) {
                     const int32_t k = global[(size_t)(g * 64 + q)];
@@ -1172,7 +1269,8 @@ inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const Pair
                 const int64_t w = next.fetch_add(1);
                 if (w >= n_windows) break;
                 const int64_t g0 = wstart[(size_t)w] * 64, g1 = wstart[(size_t)w + 1] * 64;
-                interseq_plan_window(wps[(size_t)w], hm, 0, 0, score_only, dwpl, global.data() + g0, g1 - g0);
+                interseq_plan_window(wps[(size_t)w], hm, 0, 0, score_only, dwpl, global.data() + g0, g1 - g0,
+                                     global_nm.empty() ? nullptr : global_nm.data() + g0);
             }
         };
         std::vector<std::thread> threads;
@@ -1202,9 +1300,10 @@ inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const Pair
                 const int64_t w = next.fetch_add(1);
                 if (w >= n_windows) break;
                 WindowPlan &wp = wps[(size_t)w];
-                if (!wp.order.empty()) memcpy(plan.order.data() + wp.win.group_begin * 64, wp.order.data(), wp.order.size() * 4);
+                // window w holds groups wstart[w] .. wstart[w + 1] of the batch-wide list
+                memcpy(plan.order.data() + wp.win.group_begin * 64, global.data() + wstart[(size_t)w] * 64,
+                       (size_t)(wstart[(size_t)w + 1] - wstart[(size_t)w]) * 64 * 4);
                 if (!wp.desc.empty()) memcpy(plan.desc.data() + wp.win.group_begin, wp.desc.data(), wp.desc.size() * sizeof(WarpDesc));
-                std::vector<int32_t>().swap(wp.order);
             }
         };
         std::vector<std::thread> threads;

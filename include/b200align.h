@@ -211,13 +211,15 @@ int bt_expand_traces(int64_t n_pairs, const int64_t *trace_len, const int32_t *f
 /*
  * Test hook: the host-side plan of a resident packed batch (pair order in groups of 64 slots,
  * -1 = padding; groups and direction-table bytes per window) without any device work.  Pair k
- * has lengths off1[k+1]-off1[k] and off2[k+1]-off2[k].  Used by the CPU test-suite to check the
- * planner's invariants; not needed by callers.
+ * has lengths off1[k+1]-off1[k] and off2[k+1]-off2[k].  `layout_hash_out` (optional) receives a
+ * hash of the group descriptors, window records and scratch sizes.  Used by the CPU test-suite to
+ * check the planner's invariants; not needed by callers.
  */
 int bt_debug_plan(const BtParams *params, const int64_t *off1, const int64_t *off2, int64_t n_pairs,
                   int32_t score_only, int32_t waves_per_window, int32_t *order_out, int64_t order_cap,
                   int64_t *n_groups_out, int64_t *window_groups_out, int64_t *window_dir_bytes_out,
-                  int64_t window_cap, int64_t *n_windows_out, int64_t *cells_out);
+                  int64_t window_cap, int64_t *n_windows_out, int64_t *cells_out,
+                  uint64_t *layout_hash_out);
 
 /*
  * Roofline denominators measured on the current device: register-only loops of

@@ -26,7 +26,7 @@ def _plan(len1, len2, score_only=0, waves=4, affine=True):
     n_groups, n_windows, cells = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
     _cabi.check(lib.bt_debug_plan(ctypes.byref(params), _cabi.ptr(off1), _cabi.ptr(off2), n, score_only, waves,
                                   _cabi.ptr(order), cap, ctypes.byref(n_groups), _cabi.ptr(win_groups),
-                                  _cabi.ptr(win_bytes), 4096, ctypes.byref(n_windows), ctypes.byref(cells)))
+                                  _cabi.ptr(win_bytes), 4096, ctypes.byref(n_windows), ctypes.byref(cells), None))
     g, w = n_groups.value, n_windows.value
     return order[:g * 64].reshape(g, 64), win_groups[:w], win_bytes[:w], cells.value
 
