@@ -118,3 +118,22 @@ def test_odd_pair_counts_and_linear_mode(n):
 def test_length_range_is_checked():
     with pytest.raises(OverflowError):
         _plan(np.array([9000] * 64), np.array([100] * 64))
+
+
+@pytest.mark.parametrize("n", [1000, 300_000, 1_200_037])
+def test_ragged_order_equals_a_numpy_restatement(n):
+    """The batch-wide order is exactly: pairs sorted by (len1, len2) ascending (stable), reversed,
+    cut into groups of 64 slots, groups stably sorted by descending cost (threaded counting passes
+    over 64-bit records in the library; one thread below 262 144 pairs)."""
+    rng = np.random.default_rng(n)
+    len1 = np.clip(np.rint(rng.normal(300, 100, n)), 50, 600).astype(np.int64)
+    len2 = np.clip(np.rint(rng.lognormal(np.log(270), 0.7, n)), 30, 5000).astype(np.int64)
+    order, win_groups, _, cells = _plan(len1, len2, score_only=1, waves=1)
+    ids = np.lexsort((len2, len1))[::-1].astype(np.int32)
+    slots = np.full((n + 63) // 64 * 64, -1, dtype=np.int32)
+    slots[:n] = ids
+    slots = slots.reshape(-1, 64)
+    cost = _group_cost(slots, len1, len2)
+    expected = slots[np.argsort(-cost, kind="stable")]
+    assert np.array_equal(order, expected)
+    assert cells == int((len1 * len2).sum()) and win_groups.sum() == len(order)
