@@ -338,10 +338,17 @@ def main():
     value = total_cells * args.steps / device_s * 1e-9
 
     # ---- end to end through the public batch API (host buffers in, host buffers out) ---------
+    # results in the compact form (int32 lengths, 2-bit steps): what the reference's FFI returns,
+    # the (L, 2) traces of trace.rs:103-130, is rebuilt from it on the host (bt_expand_traces2)
+    out_c = bt.compact_out(off1, off2)
+    e2e_words = [0]
+
     def e2e_step():
         # the public one-shot batch API: host arrays in, host arrays out
         t_step = time.perf_counter()
-        bt.align_batch_arrays(p_codes1, p_off1, p_codes2, p_off2, matrix, GAP, True, False, out=out)
+        res = bt.align_batch_arrays(p_codes1, p_off1, p_codes2, p_off2, matrix, GAP, True, False,
+                                    out=out_c, compact=True)
+        e2e_words[0] = res.ops2_words
         if os.environ.get("B200ALIGN_TRACE"):
             print(f"[bench] rank {rank}: e2e step {1e3 * (time.perf_counter() - t_step):.2f} ms", file=sys.stderr)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -357,7 +364,8 @@ def main():
     e2e_s = max_over_ranks(e2e_local)
     e2e_value = total_cells * args.steps / e2e_s * 1e-9
     h2d = int(sum_over_ranks(float(p_codes1.nbytes + p_codes2.nbytes + off1.nbytes + off2.nbytes + matrix.nbytes)))
-    d2h = int(sum_over_ranks(float(sum(a.nbytes for a in out))))
+    # bytes that actually crossed the link: scores, lengths, first cells and the used step words
+    d2h = int(sum_over_ranks(float(out_c[0].nbytes + out_c[1].nbytes + out_c[2].nbytes + 4 * e2e_words[0])))
 
     # ---- roofline of the dominant kernel (DP fill) ---------------------------------------------
     peak = np.zeros(3)

@@ -36,6 +36,7 @@ from .batch import (
     DeviceBatch,
     PackedSequences,
     align_batch_arrays,
+    compact_out,
     align_indexed_batch,
     all_vs_all_scores,
     feng_doolittle_distances,

@@ -28,6 +28,7 @@ __all__ = [
     "DeviceBatch",
     "BatchResult",
     "align_batch_arrays",
+    "compact_out",
     "align_indexed_batch",
     "all_vs_all_scores",
     "feng_doolittle_distances",
@@ -76,6 +77,16 @@ def pack_sequences(sequences, dtype=None):
     return PackedSequences(codes, offsets, alphabet, sequences)
 
 
+def _as_index(idx):
+    """Pair index array as contiguous int32; values that do not fit raise instead of wrapping."""
+    idx = np.asarray(idx)
+    if idx.dtype != np.int32:
+        if idx.size and (idx.min() < 0 or idx.max() > np.iinfo(np.int32).max):
+            raise ValueError("pair index out of range")
+        idx = idx.astype(np.int32)
+    return np.ascontiguousarray(idx)
+
+
 class DeviceBatch:
     """
     Thin handle on a ``BtBatch``: inputs are copied to the GPU on construction
@@ -98,8 +109,8 @@ class DeviceBatch:
         self.codes2 = np.ascontiguousarray(codes2, dtype)
         self.off1 = np.ascontiguousarray(off1, dtype=np.int64)
         self.off2 = np.ascontiguousarray(off2, dtype=np.int64)
-        self.idx1 = None if idx1 is None else np.ascontiguousarray(idx1, dtype=np.int32)
-        self.idx2 = None if idx2 is None else np.ascontiguousarray(idx2, dtype=np.int32)
+        self.idx1 = None if idx1 is None else _as_index(idx1)
+        self.idx2 = None if idx2 is None else _as_index(idx2)
         if self.idx1 is None:
             if len(self.off1) != len(self.off2):
                 raise ValueError("Both sides of the batch must hold the same number of sequences")
@@ -109,6 +120,8 @@ class DeviceBatch:
                 raise ValueError("idx1 and idx2 must have the same length")
             self.n_pairs = len(self.idx1)
         self.bands = None if bands is None else np.ascontiguousarray(bands, dtype=np.int64)
+        if self.bands is not None and self.bands.shape != (self.n_pairs, 2):
+            raise ValueError("bands must have shape (n_pairs, 2)")
         self.score_only = bool(score_only)
         self.stats = bool(stats) and not self.score_only
         mode = 1 if self.score_only else (2 if self.stats else 0)
@@ -173,6 +186,12 @@ class DeviceBatch:
                     ops = np.empty(int(self._lib.bt_batch_ops_bytes(self._handle)), dtype=np.uint8)
         else:
             scores, trace_len, first, ops = out
+            _check_out("scores", scores, np.int32, (n,))
+            if not self.score_only:
+                _check_out("trace_len", trace_len, np.int64, (n,))
+                _check_out("first", first, np.int32, (n, 2))
+                if not self.stats:
+                    _check_out("ops", ops, np.uint8, (int(self._lib.bt_batch_ops_bytes(self._handle)),))
         _cabi.check(self._lib.bt_batch_fetch_scores(self._handle, _cabi.ptr(scores)))
         if not self.score_only:
             _cabi.check(self._lib.bt_batch_fetch_traces(
@@ -254,13 +273,41 @@ class DeviceBatch:
             pass
 
 
+def _check_out(name, array, dtype, shape):
+    """Caller-supplied result arrays go to the C ABI as raw pointers: insist on the exact layout."""
+    if not isinstance(array, np.ndarray) or array.dtype != np.dtype(dtype) or array.shape != tuple(shape) \
+            or not array.flags.c_contiguous or not array.flags.writeable:
+        raise ValueError(f"out: `{name}` must be a writeable C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}")
+
+
+def compact_out(off1, off2, pinned=True):
+    """
+    Result arrays ``(scores, trace_len, first, ops2, ops2_off)`` for the compact form of
+    :func:`align_batch_arrays`, page-locked by default so that the device-to-host copies of a
+    window overlap the kernels of the next one.  Reusable across calls of the same shape.
+    """
+    lib = _cabi.load()
+    off1 = np.ascontiguousarray(off1, dtype=np.int64)
+    off2 = np.ascontiguousarray(off2, dtype=np.int64)
+    n = len(off1) - 1
+    cap = int(lib.bt_ops2_capacity(_cabi.ptr(off1), _cabi.ptr(off2), n))
+    make = _cabi.pinned_empty if pinned else (lambda shape, dtype: np.empty(shape, dtype))
+    return (make((n,), np.int32), make((n,), np.int32), make((n, 2), np.int32), make((cap,), np.uint32),
+            make((n,), np.int64))
+
+
 def align_batch_arrays(codes1, off1, codes2, off2, scoring, gap_penalty, terminal_penalty=True,
-                       local=False, bands=None, score_only=False, out=None):
+                       local=False, bands=None, score_only=False, out=None, compact=False):
     """
     One call from host arrays to host results (``bt_align_batch``): H2D copies, kernels
     and D2H copies are pipelined inside the library.  `out` may supply preallocated
-    (ideally page-locked, see ``_cabi.pinned_empty``) result arrays
-    ``(scores, trace_len, first, ops)``.  Returns a :class:`BatchResult`.
+    (ideally page-locked, see ``_cabi.pinned_empty``; with pageable arrays every copy blocks
+    the host until it is done) result arrays ``(scores, trace_len, first, ops)``.
+
+    `compact` selects the compact trace form (``bt_align_batch_compact``): ``trace_len`` as int32
+    and the steps as 2 bits each, so that only about ``L / 4`` bytes per pair leave the device;
+    `out` is then ``(scores, trace_len, first, ops2, ops2_off)`` as made by :func:`compact_out`.
+    Returns a :class:`BatchResult`.
     """
     lib = _cabi.load()
     dtype = np.promote_types(codes1.dtype, codes2.dtype)
@@ -274,6 +321,32 @@ def align_batch_arrays(codes1, off1, codes2, off2, scoring, gap_penalty, termina
     bands = None if bands is None else np.ascontiguousarray(bands, dtype=np.int64)
     params, matrix = _cabi.make_params(scoring, gap_penalty, terminal_penalty, local,
                                        bands is not None, dtype)
+    if bands is not None and bands.shape != (n, 2):
+        raise ValueError("bands must have shape (n_pairs, 2)")
+    if compact:
+        if out is None:
+            out = compact_out(off1, off2, pinned=False)
+        scores, trace_len, first, ops2, ops2_off = out
+        cap = int(lib.bt_ops2_capacity(_cabi.ptr(off1), _cabi.ptr(off2), n))
+        _check_out("scores", scores, np.int32, (n,))
+        if not score_only:
+            _check_out("trace_len", trace_len, np.int32, (n,))
+            _check_out("first", first, np.int32, (n, 2))
+            _check_out("ops2", ops2, np.uint32, (cap,))
+            _check_out("ops2_off", ops2_off, np.int64, (n,))
+        words = ctypes.c_int64(0)
+        _cabi.check(lib.bt_align_batch_compact(
+            ctypes.byref(params), _cabi.ptr(codes1), _cabi.ptr(off1), _cabi.ptr(codes2),
+            _cabi.ptr(off2), n, _cabi.ptr(matrix), _cabi.ptr(bands), int(bool(score_only)),
+            _cabi.ptr(scores), None if score_only else _cabi.ptr(trace_len),
+            None if score_only else _cabi.ptr(first), None if score_only else _cabi.ptr(ops2), cap,
+            None if score_only else _cabi.ptr(ops2_off), ctypes.byref(words)))
+        if score_only:
+            return BatchResult(scores, None, None, None, np.zeros(0, dtype=np.int64), bands)
+        result = BatchResult(scores, trace_len, first, None, ops2_off, bands)
+        result.ops2 = ops2
+        result.ops2_words = int(words.value)
+        return result
     if out is None:
         scores = np.empty(n, dtype=np.int32)
         trace_len = first = ops = None
@@ -283,6 +356,11 @@ def align_batch_arrays(codes1, off1, codes2, off2, scoring, gap_penalty, termina
             ops = np.empty(int(off1[-1] + off2[-1]), dtype=np.uint8)
     else:
         scores, trace_len, first, ops = out
+        _check_out("scores", scores, np.int32, (n,))
+        if not score_only:
+            _check_out("trace_len", trace_len, np.int64, (n,))
+            _check_out("first", first, np.int32, (n, 2))
+            _check_out("ops", ops, np.uint8, (int(off1[-1] + off2[-1]),))
     _cabi.check(lib.bt_align_batch(
         ctypes.byref(params), _cabi.ptr(codes1), _cabi.ptr(off1), _cabi.ptr(codes2),
         _cabi.ptr(off2), n, _cabi.ptr(matrix), _cabi.ptr(bands), int(bool(score_only)),
@@ -319,6 +397,9 @@ class BatchResult:
         self.seqs1 = seqs1
         self.seqs2 = seqs2
         self.gap_counts = None   # (n, 2) gap-open / gap-extension column counts (statistics batches)
+        # compact form (bt_align_batch_compact): 2-bit steps, pair k starts at word ops_off[k]
+        self.ops2 = None
+        self.ops2_words = 0
 
     def __len__(self):
         return len(self.scores)
@@ -341,10 +422,16 @@ class BatchResult:
         rows_off = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(self.trace_len, out=rows_off[1:])
         out = np.empty((int(rows_off[-1]), 2), dtype=np.int64)
-        _cabi.check(lib.bt_expand_traces(
-            n, _cabi.ptr(self.trace_len), _cabi.ptr(np.ascontiguousarray(self.first)),
-            _cabi.ptr(self.ops), _cabi.ptr(self.ops_off), _cabi.ptr(self.bands),
-            _cabi.ptr(rows_off), _cabi.ptr(out)))
+        if self.ops2 is not None:
+            _cabi.check(lib.bt_expand_traces2(
+                n, _cabi.ptr(self.trace_len), _cabi.ptr(np.ascontiguousarray(self.first)),
+                _cabi.ptr(self.ops2), _cabi.ptr(self.ops_off), _cabi.ptr(self.bands),
+                _cabi.ptr(rows_off), _cabi.ptr(out)))
+        else:
+            _cabi.check(lib.bt_expand_traces(
+                n, _cabi.ptr(self.trace_len), _cabi.ptr(np.ascontiguousarray(self.first)),
+                _cabi.ptr(self.ops), _cabi.ptr(self.ops_off), _cabi.ptr(self.bands),
+                _cabi.ptr(rows_off), _cabi.ptr(out)))
         if self.swapped is not None and self.swapped.any():
             flip = np.repeat(self.swapped, self.trace_len)
             out[flip] = out[flip][:, ::-1]
@@ -361,9 +448,10 @@ class BatchResult:
         rows_off = np.array([0, int(length[0])], dtype=np.int64)
         out = np.empty((int(length[0]), 2), dtype=np.int64)
         band = None if self.bands is None else np.ascontiguousarray(self.bands[k:k + 1])
-        _cabi.check(lib.bt_expand_traces(
+        expand, steps = (lib.bt_expand_traces, self.ops) if self.ops2 is None else (lib.bt_expand_traces2, self.ops2)
+        _cabi.check(expand(
             1, _cabi.ptr(length), _cabi.ptr(np.ascontiguousarray(self.first[k:k + 1])),
-            _cabi.ptr(self.ops), _cabi.ptr(self.ops_off[k:k + 1]), _cabi.ptr(band),
+            _cabi.ptr(steps), _cabi.ptr(self.ops_off[k:k + 1]), _cabi.ptr(band),
             _cabi.ptr(rows_off), _cabi.ptr(out)))
         if self.swapped is not None and self.swapped[k]:
             out = np.ascontiguousarray(out[:, ::-1])

@@ -25,6 +25,7 @@
 #include "banded_kernel.cuh"
 #include "microbench.cuh"
 #include "emit_kernel.cuh"
+#include "compact_kernel.cuh"
 #include "xdrop_kernel.cuh"
 
 using namespace bt;
@@ -85,6 +86,19 @@ extern "C" void *bt_pinned_alloc(size_t bytes) {
 extern "C" void bt_pinned_free(void *ptr) {
     if (ptr) cudaFreeHost(ptr);
 }
+
+// Makes `device` current for the calling thread and restores the caller's device on scope exit
+// (a batch remembers the device it was created on; the calls that touch it may come from
+// threads whose current device is another one).
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != device && cudaSetDevice(device) == cudaSuccess) changed = true;
+    }
+    ~DeviceGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
+};
 
 // ---------------------------------------------------------------------------------------
 // device buffers
@@ -179,7 +193,10 @@ struct BtBatch {
         for (cudaEvent_t e : phase_events) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        if (stream) cudaStreamDestroy(stream);
+        // drain before the members (device buffers) return to the pool: error paths leave
+        // copies and kernels queued
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+        cudaGetLastError();
     }
 };
 
@@ -570,7 +587,7 @@ extern "C" int64_t bt_batch_ops_bytes(const BtBatch *b) { return b ? b->ops_tota
 
 extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
     if (!b) return fail(BT_ERR_INVALID_ARG, "batch is NULL");
-    CUDA_TRY(cudaSetDevice(b->device));
+    DeviceGuard device_guard(b->device);
     b->launches = 0;
     b->phase_used = 0;
     CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
@@ -632,6 +649,7 @@ extern "C" int bt_batch_timings(const BtBatch *b, float *fill_ms, float *traceba
 extern "C" int bt_batch_fetch_scores(BtBatch *b, int32_t *scores_out) {
     if (!b || !scores_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
     if (!b->ran) return fail(BT_ERR_INVALID_ARG, "bt_batch_run has not been called");
+    DeviceGuard device_guard(b->device);
     CUDA_TRY(cudaMemcpyAsync(scores_out, b->score.ptr, (size_t)b->n_pairs * 4, cudaMemcpyDeviceToHost,
                              b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
@@ -643,6 +661,7 @@ extern "C" int bt_batch_fetch_traces(BtBatch *b, int64_t *trace_len_out, int32_t
     if (!b) return fail(BT_ERR_INVALID_ARG, "batch is NULL");
     if (b->score_only) return fail(BT_ERR_INVALID_ARG, "batch was created score_only");
     if (!b->ran) return fail(BT_ERR_INVALID_ARG, "bt_batch_run has not been called");
+    DeviceGuard device_guard(b->device);
     cudaStream_t s = b->stream;
     if (trace_len_out)
         CUDA_TRY(cudaMemcpyAsync(trace_len_out, b->trace_len.ptr, (size_t)b->n_pairs * 8, cudaMemcpyDeviceToHost, s));
@@ -663,7 +682,6 @@ static int emit_args(BtBatch *b, const uint8_t *swapped, DevBuf &d_swapped, Emit
     if (!b) return fail(BT_ERR_INVALID_ARG, "batch is NULL");
     if (b->score_only || b->stats) return fail(BT_ERR_INVALID_ARG, "the batch holds no traces");
     if (!b->ran) return fail(BT_ERR_INVALID_ARG, "bt_batch_run has not been called");
-    CUDA_TRY(cudaSetDevice(b->device));
     if (swapped) {
         CUDA_TRY(d_swapped.alloc((size_t)b->n_pairs));
         CUDA_TRY(cudaMemcpyAsync(d_swapped.ptr, swapped, (size_t)b->n_pairs, cudaMemcpyHostToDevice, b->stream));
@@ -681,6 +699,7 @@ static int emit_args(BtBatch *b, const uint8_t *swapped, DevBuf &d_swapped, Emit
 extern "C" int bt_batch_fetch_cigar(BtBatch *b, int32_t flags, const uint8_t *swapped, int32_t *n_ops_out,
                                     uint32_t *cigar_out) {
     if (!n_ops_out || !cigar_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard device_guard(b ? b->device : 0);
     DevBuf d_swapped, d_nops, d_cigar;
     EmitArgs A{};
     int st = emit_args(b, swapped, d_swapped, &A);
@@ -703,6 +722,7 @@ extern "C" int bt_batch_fetch_gapped(BtBatch *b, const uint8_t *symbols1, int32_
                                      uint8_t *gapped1_out, uint8_t *gapped2_out) {
     if (!symbols1 || !symbols2 || !n_columns_out || !gapped1_out || !gapped2_out || n_symbols1 < 1 || n_symbols2 < 1)
         return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard device_guard(b ? b->device : 0);
     DevBuf d_swapped, d_sym, d_cols, d_g1, d_g2;
     EmitArgs A{};
     int st = emit_args(b, swapped, d_swapped, &A);
@@ -743,7 +763,7 @@ extern "C" int bt_debug_plan(const BtParams *params, const int64_t *off1, const 
     if (!scan.in_range) return fail(BT_ERR_RANGE, "a sequence is outside the packed kernels' length range");
     InterseqPlan plan;
     int64_t cells = 0;
-    interseq_plan_host(plan, *params, hm, n_pairs, score_only, 0, &cells, std::max(1, (int)waves_per_window));
+    interseq_plan_host(plan, *params, hm, n_pairs, score_only, 0, 0, &cells, std::max(1, (int)waves_per_window));
     *n_groups_out = plan.n_groups;
     *n_windows_out = (int64_t)plan.windows.size();
     if (cells_out) *cells_out = cells;
@@ -781,7 +801,39 @@ extern "C" const char *bt_batch_kernel(const BtBatch *b) {
     if (!b) return "";
     return b->route == ROUTE_INTERSEQ ? "interseq_s16x2" : (b->route == ROUTE_BANDED ? "banded_i32" : "general_i32");
 }
-extern "C" void bt_batch_destroy(BtBatch *b) { delete b; }
+extern "C" void bt_batch_destroy(BtBatch *b) {
+    if (!b) return;
+    DeviceGuard device_guard(b->device);   // the buffers go back to the pool of their own device
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    delete b;
+}
+
+// Where the results of a one-shot batch go.  Classic form: trace_len int64, one step byte per
+// column at off1[k] + off2[k].  Compact form (compact_kernel.cuh): trace_len int32 and 2-bit
+// steps, the words of pair k starting at ops2[ops2_off[k]].
+struct BatchOut {
+    int32_t *scores = nullptr;
+    int32_t *first = nullptr;
+    int64_t *trace_len64 = nullptr;
+    uint8_t *ops = nullptr;
+    bool compact = false;
+    int32_t *trace_len32 = nullptr;
+    uint32_t *ops2 = nullptr;
+    int64_t ops2_cap = 0;       // words
+    int64_t *ops2_off = nullptr;
+    int64_t *ops2_words = nullptr;   // words used (highest end), optional
+};
+
+// First word of the compact steps of a run of pairs starting at pair p: an upper bound of
+// sum ceil(L / 16) over the pairs before it that depends on the inputs only.
+static inline int64_t ops2_base(const int64_t *off1, const int64_t *off2, int64_t p) {
+    return (off1[p] + off2[p]) / 16 + 2 * p;
+}
+
+extern "C" int64_t bt_ops2_capacity(const int64_t *off1, const int64_t *off2, int64_t n_pairs) {
+    if (!off1 || !off2 || n_pairs < 0) return 0;
+    return ops2_base(off1, off2, n_pairs) + 16;
+}
 
 // One-shot path for the packed inter-sequence route: windows of consecutive pairs are
 // streamed through two slots (stream + scratch each), so the H2D copy of window k+1 and the
@@ -789,14 +841,16 @@ extern "C" void bt_batch_destroy(BtBatch *b) { delete b; }
 static int align_batch_pipelined(const BtParams *params, const void *codes1, const int64_t *off1,
                                  const void *codes2, const int64_t *off2, int64_t n_pairs,
                                  const int32_t *matrix, int32_t score_only, int32_t mn, int32_t mx,
-                                 const PairScan &scan, int32_t *scores_out, int64_t *trace_len_out,
-                                 int32_t *first_out, uint8_t *ops_out) {
+                                 const PairScan &scan, const BatchOut &out) {
     const int64_t *h_off1 = off1, *h_off2 = off2;   // the caller's host arrays stay valid during the call
     const int64_t total1 = h_off1[n_pairs], total2 = h_off2[n_pairs];
     const bool trace = getenv("B200ALIGN_TRACE") != nullptr;
+    const bool compact = out.compact && !score_only;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     DevBuf d_codes1, d_codes2, d_off1, d_off2, d_matrix, d_score, d_len, d_first, d_ops, d_flag, d_start;
+    DevBuf d_len32, d_packed, d_bsums[2], d_total;
+    PinnedBuf h_total;
     CUDA_TRY(d_codes1.alloc((size_t)total1));
     CUDA_TRY(d_codes2.alloc((size_t)total2));
     CUDA_TRY(d_off1.alloc((size_t)(n_pairs + 1) * 8));
@@ -815,16 +869,19 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     // the whole batch, so a window's input never waits for a scratch slot), the two compute
     // streams alternate windows / scratch slots, and `d2h` returns a window's results as soon as
     // its kernels are done - no compute stream ever waits for a copy of another window.
+    // Declared after the buffers: its destructor drains the streams before any buffer goes back
+    // to the pool, also on the error paths.
     struct Streams {
         cudaStream_t s[2] = {nullptr, nullptr}, h2d = nullptr, d2h = nullptr;
         std::vector<cudaEvent_t> in_ready, plan_ready, k_done;
         ~Streams() {
-            for (cudaStream_t x : s) if (x) cudaStreamDestroy(x);
-            if (h2d) cudaStreamDestroy(h2d);
-            if (d2h) cudaStreamDestroy(d2h);
+            for (cudaStream_t x : s) if (x) { cudaStreamSynchronize(x); cudaStreamDestroy(x); }
+            if (h2d) { cudaStreamSynchronize(h2d); cudaStreamDestroy(h2d); }
+            if (d2h) { cudaStreamSynchronize(d2h); cudaStreamDestroy(d2h); }
             for (cudaEvent_t e : in_ready) cudaEventDestroy(e);
             for (cudaEvent_t e : plan_ready) cudaEventDestroy(e);
             for (cudaEvent_t e : k_done) cudaEventDestroy(e);
+            cudaGetLastError();
         }
     } st;
     CUDA_TRY(cudaStreamCreateWithFlags(&st.s[0], cudaStreamNonBlocking));
@@ -839,10 +896,20 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     PairMap hm;
     hm.off1 = h_off1; hm.off2 = h_off2;
     interseq_setup(plan, *params, n_pairs, score_only, mn);
-    (void)mx;
+    interseq_enable_tags(plan, *params, scan, mn, mx);
     const char *waves_env = getenv("B200ALIGN_WAVES");
     const int waves = waves_env ? std::max(1, atoi(waves_env)) : 3;
     StreamingPlanner planner(plan, hm, n_pairs, waves, params->affine != 0);
+    if (compact) {
+        int64_t max_np = 0;
+        for (int64_t w = 0; w < planner.n_windows; w++)
+            max_np = std::max(max_np, planner.bounds[(size_t)w + 1] - planner.bounds[(size_t)w]);
+        CUDA_TRY(d_len32.alloc((size_t)n_pairs * 4));
+        CUDA_TRY(d_packed.alloc((size_t)(ops2_base(h_off1, h_off2, n_pairs) + 16) * 4));
+        for (DevBuf &b : d_bsums) CUDA_TRY(b.alloc((size_t)((max_np + CP_BLOCK - 1) / CP_BLOCK + 1) * 8));
+        CUDA_TRY(d_total.alloc((size_t)planner.n_windows * 8));
+        CUDA_TRY(h_total.alloc((size_t)planner.n_windows * 8));
+    }
     cudaEvent_t tev0 = nullptr;
     if (trace) { cudaEventCreate(&tev0); cudaEventRecord(tev0, st.h2d); }
     CUDA_TRY(cudaMemsetAsync(d_flag.ptr, 0, 4, st.h2d));
@@ -881,10 +948,51 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     dm.off1 = d_off1.as<int64_t>(); dm.off2 = d_off2.as<int64_t>();
     InterseqIO io{d_codes1.ptr, d_codes2.ptr, dm, d_matrix.as<int32_t>(),
                   d_score.as<int32_t>(), d_len.as<int64_t>(), d_first.as<int32_t>(), d_ops.as<uint8_t>(),
-                  d_start.as<int32_t>()};
+                  d_start.as<int32_t>(), d_flag.as<int>()};
     int64_t launches = 0;
     std::vector<cudaEvent_t> tev;   // B200ALIGN_TRACE: per window [start, h2d done, kernels done, d2h done]
     auto mark = [&](cudaStream_t s) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e); } };
+    int64_t words_end = 0;
+    // results of window w to the host: everything a window returns is a contiguous range of the
+    // output arrays.  The compact form waits (on the host) for the window's kernels, because the
+    // size of its step words is only known then; by that time the next window is already queued.
+    auto drain = [&](size_t w) -> int {
+        const Window &win = plan.windows[w];
+        const int64_t p0 = win.pair_begin, np = win.pair_end - win.pair_begin;
+        cudaStream_t r = st.d2h;
+        int64_t words = 0;
+        if (compact) {
+            CUDA_TRY(cudaEventSynchronize(st.k_done[w]));
+            words = h_total.as<int64_t>()[w];
+        } else {
+            CUDA_TRY(cudaStreamWaitEvent(r, st.k_done[w], 0));
+        }
+        if (out.scores)
+            CUDA_TRY(cudaMemcpyAsync(out.scores + p0, d_score.as<int32_t>() + p0, (size_t)np * 4, cudaMemcpyDeviceToHost, r));
+        if (!score_only) {
+            if (out.first)
+                CUDA_TRY(cudaMemcpyAsync(out.first + 2 * p0, d_first.as<int32_t>() + 2 * p0, (size_t)np * 8, cudaMemcpyDeviceToHost, r));
+            if (compact) {
+                const int64_t base = ops2_base(h_off1, h_off2, p0);
+                if (out.trace_len32)
+                    CUDA_TRY(cudaMemcpyAsync(out.trace_len32 + p0, d_len32.as<int32_t>() + p0, (size_t)np * 4, cudaMemcpyDeviceToHost, r));
+                if (out.ops2) {
+                    if (base + words > out.ops2_cap) return fail(BT_ERR_INVALID_ARG, "ops2 buffer is too small (see bt_ops2_capacity)");
+                    if (words > 0)
+                        CUDA_TRY(cudaMemcpyAsync(out.ops2 + base, d_packed.as<uint32_t>() + base, (size_t)words * 4, cudaMemcpyDeviceToHost, r));
+                }
+                words_end = std::max(words_end, base + words);
+            } else {
+                const int64_t a = h_off1[p0] + h_off2[p0], b = h_off1[win.pair_end] + h_off2[win.pair_end];
+                if (out.trace_len64)
+                    CUDA_TRY(cudaMemcpyAsync(out.trace_len64 + p0, d_len.as<int64_t>() + p0, (size_t)np * 8, cudaMemcpyDeviceToHost, r));
+                if (out.ops)
+                    CUDA_TRY(cudaMemcpyAsync(out.ops + a, d_ops.as<uint8_t>() + a, (size_t)(b - a), cudaMemcpyDeviceToHost, r));
+            }
+        }
+        mark(r);
+        return BT_OK;
+    };
     for (size_t w = 0; w < plan.windows.size(); w++) {
         const int slot = (int)(w & 1);
         cudaStream_t s = st.s[slot];
@@ -894,34 +1002,25 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
         CUDA_TRY(cudaStreamWaitEvent(s, st.plan_ready[w], 0));
         mark(s);
         const Window &win = plan.windows[w];
-        const int64_t a1 = h_off1[win.pair_begin], b1 = h_off1[win.pair_end];
-        const int64_t a2 = h_off2[win.pair_begin], b2 = h_off2[win.pair_end];
         const int64_t np = win.pair_end - win.pair_begin;
         CUDA_TRY(cudaStreamWaitEvent(s, st.in_ready[w], 0));
         mark(s);
-        validate_codes_kernel<<<(int)std::min<int64_t>(592, (b1 - a1 + 255) / 256), 256, 0, s>>>(
-            (const char *)d_codes1.ptr + a1, b1 - a1, 1, (uint64_t)params->n_rows, d_flag.as<int>());
-        validate_codes_kernel<<<(int)std::min<int64_t>(592, (b2 - a2 + 255) / 256), 256, 0, s>>>(
-            (const char *)d_codes2.ptr + a2, b2 - a2, 1, (uint64_t)params->n_cols, d_flag.as<int>());
-        CUDA_TRY(cudaGetLastError());
         CUDA_TRY(interseq_fill_window(plan, win, slot, io, s, &launches));
         CUDA_TRY(interseq_traceback_window(plan, win, slot, io, s, &launches));
+        if (compact) {
+            CompactArgs ca{d_len.as<int64_t>(), d_ops.as<uint8_t>(), dm, win.pair_begin, np, d_len32.as<int32_t>(),
+                           d_bsums[slot].as<int64_t>(),
+                           d_packed.as<uint32_t>() + ops2_base(h_off1, h_off2, win.pair_begin),
+                           d_total.as<int64_t>() + w};
+            CUDA_TRY(compact_launch(ca, s, &launches));
+            CUDA_TRY(cudaMemcpyAsync(h_total.as<int64_t>() + w, d_total.as<int64_t>() + w, 8, cudaMemcpyDeviceToHost, s));
+        }
         mark(s);
         CUDA_TRY(cudaEventRecord(st.k_done[w], s));
-        cudaStream_t r = st.d2h;
-        CUDA_TRY(cudaStreamWaitEvent(r, st.k_done[w], 0));
-        if (scores_out)
-            CUDA_TRY(cudaMemcpyAsync(scores_out + win.pair_begin, d_score.as<int32_t>() + win.pair_begin, (size_t)np * 4, cudaMemcpyDeviceToHost, r));
-        if (!score_only) {
-            if (trace_len_out)
-                CUDA_TRY(cudaMemcpyAsync(trace_len_out + win.pair_begin, d_len.as<int64_t>() + win.pair_begin, (size_t)np * 8, cudaMemcpyDeviceToHost, r));
-            if (first_out)
-                CUDA_TRY(cudaMemcpyAsync(first_out + 2 * win.pair_begin, d_first.as<int32_t>() + 2 * win.pair_begin, (size_t)np * 8, cudaMemcpyDeviceToHost, r));
-            if (ops_out)
-                CUDA_TRY(cudaMemcpyAsync(ops_out + a1 + a2, d_ops.as<uint8_t>() + a1 + a2, (size_t)(b1 - a1 + b2 - a2), cudaMemcpyDeviceToHost, r));
-        }
-        mark(r);
+        if (!compact) { int rc = drain(w); if (rc) return rc; }
+        else if (w > 0) { int rc = drain(w - 1); if (rc) return rc; }
     }
+    if (compact && !plan.windows.empty()) { int rc = drain(plan.windows.size() - 1); if (rc) return rc; }
     int flag = 0;
     const double t3 = now();
     CUDA_TRY(cudaStreamSynchronize(st.h2d));
@@ -943,14 +1042,60 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
                 t1 - t0, t2 - t1, t3 - t2, now() - t3, plan.windows.size());
     CUDA_TRY(cudaMemcpy(&flag, d_flag.ptr, 4, cudaMemcpyDeviceToHost));
     if (flag) return fail(BT_ERR_INVALID_CODE, "a sequence code is outside the substitution matrix");
+    if (compact) {
+        if (out.ops2_words) *out.ops2_words = words_end;
+        if (out.ops2_off && out.trace_len32) {
+            // first word of every pair: the window's base plus the running sum inside the window
+            for (const Window &win : plan.windows) {
+                int64_t run = ops2_base(h_off1, h_off2, win.pair_begin);
+                for (int64_t k = win.pair_begin; k < win.pair_end; k++) {
+                    out.ops2_off[k] = run;
+                    run += ops2_words(out.trace_len32[k]);
+                }
+            }
+        }
+    }
     return BT_OK;
 }
 
-extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const int64_t *off1,
-                              const void *codes2, const int64_t *off2, int64_t n_pairs,
-                              const int32_t *matrix, const int64_t *bands, int32_t score_only,
-                              int32_t *scores_out, int64_t *trace_len_out, int32_t *first_out,
-                              uint8_t *ops_out) {
+// The resident route behind the compact result form: run the batch, compact its traces as a
+// whole, copy exactly the used words.
+static int batch_fetch_compact(BtBatch *b, const BatchOut &out) {
+    if (b->score_only || b->stats) return fail(BT_ERR_INVALID_ARG, "the batch holds no traces");
+    if (!b->h_idx1.empty()) return fail(BT_ERR_INVALID_ARG, "compact traces of indexed batches are not supported");
+    const int64_t n = b->n_pairs;
+    DevBuf d_len32, d_packed, d_bsums, d_total;
+    struct Drain { cudaStream_t s; ~Drain() { cudaStreamSynchronize(s); cudaGetLastError(); } } guard{b->stream};
+    const int64_t cap = ops2_base(b->h_off1.data(), b->h_off2.data(), n) + 16;
+    CUDA_TRY(d_len32.alloc((size_t)std::max<int64_t>(n, 1) * 4));
+    CUDA_TRY(d_packed.alloc((size_t)cap * 4));
+    CUDA_TRY(d_bsums.alloc((size_t)((n + CP_BLOCK - 1) / CP_BLOCK + 1) * 8));
+    CUDA_TRY(d_total.alloc(8));
+    CompactArgs ca{b->trace_len.as<int64_t>(), b->ops.as<uint8_t>(), b->dev_map(), 0, n, d_len32.as<int32_t>(),
+                   d_bsums.as<int64_t>(), d_packed.as<uint32_t>(), d_total.as<int64_t>()};
+    CUDA_TRY(compact_launch(ca, b->stream, &b->launches));
+    int64_t words = 0;
+    CUDA_TRY(cudaMemcpyAsync(&words, d_total.ptr, 8, cudaMemcpyDeviceToHost, b->stream));
+    if (out.trace_len32) CUDA_TRY(cudaMemcpyAsync(out.trace_len32, d_len32.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (out.first) CUDA_TRY(cudaMemcpyAsync(out.first, b->first.ptr, (size_t)n * 8, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (out.ops2) {
+        if (words > out.ops2_cap) return fail(BT_ERR_INVALID_ARG, "ops2 buffer is too small (see bt_ops2_capacity)");
+        if (words > 0) CUDA_TRY(cudaMemcpyAsync(out.ops2, d_packed.ptr, (size_t)words * 4, cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    }
+    if (out.ops2_words) *out.ops2_words = words;
+    if (out.ops2_off && out.trace_len32) {
+        int64_t run = 0;
+        for (int64_t k = 0; k < n; k++) { out.ops2_off[k] = run; run += ops2_words(out.trace_len32[k]); }
+    }
+    return BT_OK;
+}
+
+static int align_batch_impl(const BtParams *params, const void *codes1, const int64_t *off1,
+                            const void *codes2, const int64_t *off2, int64_t n_pairs,
+                            const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                            const BatchOut &out) {
     int st = check_params(params);
     if (st) return st;
     if (n_pairs >= 64 && off1 && off2 && params->use_matrix && matrix && !params->banded && score_only != 2 &&
@@ -970,8 +1115,7 @@ extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const 
                                                         128.0 * (params->affine ? 4 : 2);
         if (off1[0] == 0 && off2[0] == 0 && slot_dirs <= (double)IS_DIR_BUDGET &&
             interseq_eligible(*params, hm, n_pairs, mn, mx, &scan))
-            return align_batch_pipelined(params, codes1, off1, codes2, off2, n_pairs, matrix, score_only, mn, mx, scan,
-                                         scores_out, trace_len_out, first_out, ops_out);
+            return align_batch_pipelined(params, codes1, off1, codes2, off2, n_pairs, matrix, score_only, mn, mx, scan, out);
     }
     BtBatch *raw = nullptr;
     st = bt_batch_create(params, codes1, off1, codes2, off2, n_pairs, matrix, bands, score_only, &raw);
@@ -979,10 +1123,57 @@ extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const 
     std::unique_ptr<BtBatch> b(raw);
     st = bt_batch_run(b.get(), nullptr);
     if (st) return st;
-    if (scores_out) { st = bt_batch_fetch_scores(b.get(), scores_out); if (st) return st; }
-    if (score_only != 1 && (trace_len_out || first_out || ops_out))
-        st = bt_batch_fetch_traces(b.get(), trace_len_out, first_out, score_only == 2 ? nullptr : ops_out);
+    if (out.scores) { st = bt_batch_fetch_scores(b.get(), out.scores); if (st) return st; }
+    if (score_only == 1) return BT_OK;
+    if (out.compact && score_only == 0) return batch_fetch_compact(b.get(), out);
+    if (out.trace_len64 || out.first || out.ops)
+        st = bt_batch_fetch_traces(b.get(), out.trace_len64, out.first, score_only == 2 ? nullptr : out.ops);
     return st;
+}
+
+extern "C" int bt_align_batch(const BtParams *params, const void *codes1, const int64_t *off1,
+                              const void *codes2, const int64_t *off2, int64_t n_pairs,
+                              const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                              int32_t *scores_out, int64_t *trace_len_out, int32_t *first_out,
+                              uint8_t *ops_out) {
+    BatchOut out;
+    out.scores = scores_out; out.trace_len64 = trace_len_out; out.first = first_out; out.ops = ops_out;
+    return align_batch_impl(params, codes1, off1, codes2, off2, n_pairs, matrix, bands, score_only, out);
+}
+
+extern "C" int bt_align_batch_compact(const BtParams *params, const void *codes1, const int64_t *off1,
+                                      const void *codes2, const int64_t *off2, int64_t n_pairs,
+                                      const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                                      int32_t *scores_out, int32_t *trace_len_out, int32_t *first_out,
+                                      uint32_t *ops2_out, int64_t ops2_capacity, int64_t *ops2_off_out,
+                                      int64_t *ops2_words_out) {
+    if (score_only != 0 && score_only != 1) return fail(BT_ERR_INVALID_ARG, "score_only must be 0 or 1");
+    if (!score_only && ops2_out && !trace_len_out) return fail(BT_ERR_INVALID_ARG, "trace_len_out is NULL");
+    BatchOut out;
+    out.compact = true;
+    out.scores = scores_out; out.trace_len32 = trace_len_out; out.first = first_out;
+    out.ops2 = ops2_out; out.ops2_cap = ops2_capacity; out.ops2_off = ops2_off_out; out.ops2_words = ops2_words_out;
+    return align_batch_impl(params, codes1, off1, codes2, off2, n_pairs, matrix, bands, score_only, out);
+}
+
+extern "C" int bt_expand_traces2(int64_t n_pairs, const int32_t *trace_len, const int32_t *first,
+                                 const uint32_t *ops2, const int64_t *ops2_off, const int64_t *bands,
+                                 const int64_t *rows_off, int64_t *out) {
+    if (!trace_len || !first || !ops2 || !ops2_off || !rows_off || !out)
+        return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(interseq_host_threads(), 16u), n_pairs / 4096));
+    std::vector<int64_t> bad((size_t)n_threads, -1);
+    interseq_parallel_chunks(n_pairs, n_threads, [&](int t, int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; k++) {
+            const int64_t lower = bands ? bands[2 * k] : 0;
+            const int64_t rows = expand_ops2(trace_len[k], first[2 * k], first[2 * k + 1], ops2 + ops2_off[k],
+                                             bands != nullptr, lower, out + 2 * rows_off[k]);
+            if (rows != trace_len[k] && bad[(size_t)t] < 0) bad[(size_t)t] = k;
+        }
+    });
+    for (int64_t k : bad)
+        if (k >= 0) return fail(BT_ERR_INVALID_ARG, "degenerate trace row in pair %lld", (long long)k);
+    return BT_OK;
 }
 
 extern "C" int bt_expand_traces(int64_t n_pairs, const int64_t *trace_len, const int32_t *first,
@@ -990,12 +1181,18 @@ extern "C" int bt_expand_traces(int64_t n_pairs, const int64_t *trace_len, const
                                 const int64_t *rows_off, int64_t *out) {
     if (!trace_len || !first || !ops || !ops_off || !rows_off || !out)
         return fail(BT_ERR_INVALID_ARG, "NULL argument");
-    for (int64_t k = 0; k < n_pairs; k++) {
-        const int64_t lower = bands ? bands[2 * k] : 0;
-        int64_t rows = expand_ops(trace_len[k], first[2 * k], first[2 * k + 1], ops + ops_off[k],
-                                  bands != nullptr, lower, out + 2 * rows_off[k]);
-        if (rows != trace_len[k]) return fail(BT_ERR_INVALID_ARG, "degenerate trace row in pair %lld", (long long)k);
-    }
+    const int n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(interseq_host_threads(), 16u), n_pairs / 4096));
+    std::vector<int64_t> bad((size_t)n_threads, -1);
+    interseq_parallel_chunks(n_pairs, n_threads, [&](int t, int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; k++) {
+            const int64_t lower = bands ? bands[2 * k] : 0;
+            const int64_t rows = expand_ops(trace_len[k], first[2 * k], first[2 * k + 1], ops + ops_off[k],
+                                            bands != nullptr, lower, out + 2 * rows_off[k]);
+            if (rows != trace_len[k] && bad[(size_t)t] < 0) bad[(size_t)t] = k;
+        }
+    });
+    for (int64_t k : bad)
+        if (k >= 0) return fail(BT_ERR_INVALID_ARG, "degenerate trace row in pair %lld", (long long)k);
     return BT_OK;
 }
 
@@ -1043,6 +1240,8 @@ extern "C" int bt_xdrop_regions(const BtParams *params, const void *codes1, cons
     CUDA_TRY(cudaStreamCreateWithFlags(&sg.s, cudaStreamNonBlocking));
     cudaStream_t s = sg.s;
     DevBuf d_c1, d_c2, d_o1, d_o2, d_mat, d_roll, d_roll_off, d_max, d_dims, d_status, d_flag, d_dirs, d_dir_off;
+    // destroyed before the buffers: nothing may be in flight when they return to the pool
+    struct Drain { cudaStream_t s; ~Drain() { cudaStreamSynchronize(s); cudaGetLastError(); } } drain_guard{s};
     CUDA_TRY(d_c1.alloc((size_t)total1 * cb));
     CUDA_TRY(d_c2.alloc((size_t)total2 * cb));
     CUDA_TRY(d_o1.alloc((size_t)(n_regions + 1) * 8));
@@ -1170,7 +1369,6 @@ extern "C" int bt_align_pair(const BtParams *params, const void *code1, int64_t 
     if (st) return st;
     std::unique_ptr<BtBatch> b(raw);
     const bool first_only = (max_number == 1);
-    CUDA_TRY(cudaSetDevice(b->device));
     b->phase_used = 0;
     st = run_general(b.get(), first_only);
     if (st) return st;

@@ -33,6 +33,7 @@
 #include <cstring>
 #include <memory>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/b200align.h"
@@ -81,6 +82,8 @@ struct InterseqConst {
     int32_t affine;                  // 0: linear gap penalty (gap_open)
     int32_t stats;                   // traceback emits GapStats instead of step bytes
     int32_t terminal;                // terminal gap columns count in the statistics
+    int32_t dir_layout;              // 0: predicate nibbles (interseq_fill_kernel), 1: tag nibbles
+                                     // (interseq_tag_kernel.cuh; scores scaled by 4, neg likewise)
 };
 
 // A window is a run of consecutive pairs (in input order) that is sorted, packed, filled and
@@ -118,6 +121,7 @@ struct InterseqIO {
     int32_t *first;
     uint8_t *ops;
     int32_t *start;  // local: first optimum cell per pair (2 ints), scratch of the batch
+    int *flag = nullptr;  // raised by the packer when a code lies outside the matrix
 };
 
 // ---------------------------------------------------------------------------------------
@@ -207,9 +211,14 @@ inline bool interseq_eligible(const BtParams &P, const PairMap &hm, int64_t n_pa
 // ---------------------------------------------------------------------------------------
 // batch packer: lane-interleaved codes of each group
 // ---------------------------------------------------------------------------------------
+// Codes outside the substitution matrix (the reference would panic, scoring.rs:63) raise `flag`
+// and are clamped to the last letter, so that the fill kernels' profile / table lookups stay
+// inside their shared-memory windows whatever the caller sent; the host turns the flag into
+// BT_ERR_INVALID_CODE after the batch.
 __global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes2, const PairMap map,
                                      const int32_t *order, const WarpDesc *desc,
-                                     uint16_t *rowcodes, uint16_t *colcodes, int64_t n_groups) {
+                                     uint16_t *rowcodes, uint16_t *colcodes, int64_t n_groups,
+                                     uint32_t n_rows, uint32_t n_cols, int *flag) {
     const int64_t g = blockIdx.x;
     if (g >= n_groups) return;
     const WarpDesc d = desc[g];
@@ -221,14 +230,20 @@ __global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes
     int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
     if (p_lo >= 0) { a_lo = map.beg1(p_lo); n_lo = (int)map.len1(p_lo); b_lo = map.beg2(p_lo); m_lo = (int)map.len2(p_lo); }
     if (p_hi >= 0) { a_hi = map.beg1(p_hi); n_hi = (int)map.len1(p_hi); b_hi = map.beg2(p_hi); m_hi = (int)map.len2(p_hi); }
+    bool bad = false;
     for (int i = sub; i < rows; i += nsub) {
-        const uint32_t lo = i < n_lo ? codes1[a_lo + i] : 0, hi = i < n_hi ? codes1[a_hi + i] : 0;
+        uint32_t lo = i < n_lo ? codes1[a_lo + i] : 0, hi = i < n_hi ? codes1[a_hi + i] : 0;
+        if (lo >= n_rows) { bad = true; lo = n_rows - 1; }
+        if (hi >= n_rows) { bad = true; hi = n_rows - 1; }
         rowcodes[d.rowcode_off + (int64_t)i * 32 + lane] = (uint16_t)(lo | (hi << 8));
     }
     for (int j = sub; j < d.mmax; j += nsub) {
-        const uint32_t lo = j < m_lo ? codes2[b_lo + j] : 0, hi = j < m_hi ? codes2[b_hi + j] : 0;
+        uint32_t lo = j < m_lo ? codes2[b_lo + j] : 0, hi = j < m_hi ? codes2[b_hi + j] : 0;
+        if (lo >= n_cols) { bad = true; lo = n_cols - 1; }
+        if (hi >= n_cols) { bad = true; hi = n_cols - 1; }
         colcodes[d.colcode_off + (int64_t)j * 32 + lane] = (uint16_t)(lo | (hi << 8));
     }
+    if (bad && flag) *flag = 1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -598,7 +613,8 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
     const int64_t o1 = A.map.beg1(p), o2 = A.map.beg2(p);
     const int n = (int)A.map.len1(p), m = (int)A.map.len2(p);
     const bool traced = !C.score_only;
-    const uint32_t *base = A.dirs + d.dir_off + lane * 4 + half * 2;
+    const bool tags = C.dir_layout != 0;
+    const uint32_t *base = A.dirs + d.dir_off + lane * 4 + (tags ? 0 : half * 2);
     // score-only and statistics batches carry no step bytes
     uint8_t *out = (traced && !C.stats) ? ops + A.map.ops(p) : nullptr;
     GapStats gs(C.terminal != 0);
@@ -621,6 +637,14 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
     };
     auto nibble = [&](int i, int j) -> uint32_t {  // 1-based table cell (i, j)
         const int rg = i - 1, s = rg / IS_R, r = rg % IS_R;
+        if (tags) {
+            // tag layout: word r / 4, low pair in bits 0-15, high pair in bits 16-31; bits 0-1 of
+            // a nibble name the state holding H (2 Match, 1 Gap1, 0 Gap2) -> hM / hG of this walk
+            const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 128 + (r >> 2)];
+            const uint32_t nb = (w >> (4 * (r & 3) + 16 * half)) & 0xfu;
+            const uint32_t t = nb & 3u;
+            return (nb & 0xcu) | (t == 2u ? 1u : (t == 1u ? 2u : 0u));
+        }
         const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 128 + (r >> 3)];
         return (w >> (4 * (r & 7))) & 0xfu;
     };
@@ -638,8 +662,10 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
     } else if (MODE == IS_SEMI) {
         const uint32_t *lr = A.lastrow + d.rowbuf_off * 2 + lane + (half ? (int64_t)d.mmax * 32 : 0);
         const uint32_t *lc = A.lastcol + d.rowcode_off * 2 + lane + (half ? (int64_t)d.stripes * IS_R * 32 : 0);
-        auto m_row = [&](int jj) -> int { const uint32_t w = lr[(int64_t)(jj - 1) * 32]; return (int16_t)(half ? w >> 16 : w & 0xffffu); };
-        auto m_col = [&](int ii) -> int { const uint32_t w = lc[(int64_t)(ii - 1) * 32]; return (int16_t)(half ? w >> 16 : w & 0xffffu); };
+        // the tag kernel captures 4 M + 1
+        const int sh = tags ? 2 : 0;
+        auto m_row = [&](int jj) -> int { const uint32_t w = lr[(int64_t)(jj - 1) * 32]; return (int)(int16_t)(half ? w >> 16 : w & 0xffffu) >> sh; };
+        auto m_col = [&](int ii) -> int { const uint32_t w = lc[(int64_t)(ii - 1) * 32]; return (int)(int16_t)(half ? w >> 16 : w & 0xffffu) >> sh; };
         const int mc = m_row(m);
         int g1 = C.neg, p1 = 0, g2 = C.neg, p2 = 0;
         for (int jj = 1; jj < m; jj++) { const int v = m_row(jj); if (v >= g1) { g1 = v; p1 = jj; } }
@@ -665,7 +691,7 @@ __global__ void interseq_traceback_kernel(const InterseqConst C, const InterseqA
         if (st == ST_MATCH) {
             if (MODE == IS_LOCAL) {
                 if (value <= 0) break;                              // M clamped to 0: trace ends before this cell
-                value -= mat[(int)codes1[o1 + i - 1] * C.n_cols + (int)codes2[o2 + j - 1]];
+                value -= mat[min((int)codes1[o1 + i - 1], C.n_rows - 1) * C.n_cols + min((int)codes2[o2 + j - 1], C.n_cols - 1)];
             }
             fi = i; fj = j;
             emit(OP_DIAG, len);
@@ -921,7 +947,7 @@ __global__ void interseq_linear_traceback_kernel(const InterseqConst C, const In
         const uint32_t w = base[((int64_t)s * d.mmax + (j - 1)) * 64];
         const uint32_t bits = (w >> (2 * r)) & 3u;
         if (bits & 1u) {
-            if (MODE == IS_LOCAL) value -= A.matrix[(int)codes1[o1 + i - 1] * C.n_cols + (int)codes2[o2 + j - 1]];
+            if (MODE == IS_LOCAL) value -= A.matrix[min((int)codes1[o1 + i - 1], C.n_rows - 1) * C.n_cols + min((int)codes2[o2 + j - 1], C.n_cols - 1)];
             emit(OP_DIAG, len); i--; j--;
         } else {
             if (MODE == IS_LOCAL) value -= C.gap_open;
@@ -935,6 +961,10 @@ __global__ void interseq_linear_traceback_kernel(const InterseqConst C, const In
     first[2 * p] = fi;
     first[2 * p + 1] = fj;
 }
+
+}  // namespace bt
+#include "interseq_tag_kernel.cuh"
+namespace bt {
 
 // ---------------------------------------------------------------------------------------
 // host side
@@ -1180,13 +1210,24 @@ inline int interseq_setup(InterseqPlan &plan, const BtParams &P, int64_t n_pairs
     plan.C.terminal = P.terminal_penalty;
     plan.C.score_only = trace_mode == 1;
     plan.C.mode = P.local ? IS_LOCAL : (P.terminal_penalty ? IS_GLOBAL : IS_SEMI);
+    plan.C.dir_layout = 0;
     return plan.C.score_only;
+}
+
+// Traced affine batches whose scores provably fit 13 bits run the tag kernel: scores scaled by 4,
+// so the 16-bit "minus infinity" moves to -8192 - open - ext - min(0, min sim).
+inline void interseq_enable_tags(InterseqPlan &plan, const BtParams &P, const PairScan &scan, int32_t min_score,
+                                 int32_t max_score) {
+    if (plan.C.score_only || !interseq_tag_eligible(P, scan, min_score, max_score)) return;
+    plan.C.dir_layout = 1;
+    plan.C.neg = -8192 - plan.C.gap_open - plan.C.gap_ext - std::min(min_score, 0);
 }
 
 // Host part of the plan of a resident batch (no device work: also reachable through
 // bt_debug_plan for the CPU tests): group order, descriptors and windows.
 inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const PairMap &hm, int64_t n_pairs,
-                               int score_only, int32_t min_score, int64_t *cells_out, int waves_per_window) {
+                               int score_only, int32_t min_score, int32_t max_score, int64_t *cells_out,
+                               int waves_per_window) {
     score_only = interseq_setup(plan, P, n_pairs, score_only, min_score);
 
     const int64_t per_window = interseq_pairs_per_window(n_pairs, waves_per_window);
@@ -1202,6 +1243,7 @@ inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const Pair
     bool uniform = false;
     {
         const PairScan scan = interseq_scan(hm, n_pairs);
+        interseq_enable_tags(plan, P, scan, min_score, max_score);
         uniform = scan.max_pair * (double)n_pairs <= 4.0 * scan.total;
         if (const char *f = getenv("B200ALIGN_SORT")) uniform = strcmp(f, "window") == 0;
     }
@@ -1329,8 +1371,7 @@ inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const Pair
 inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap &hm, int64_t n_pairs, int score_only,
                             int32_t min_score, int32_t max_score, int64_t *cells_out, int n_slots,
                             int waves_per_window, cudaStream_t stream) {
-    (void)max_score;
-    interseq_plan_host(plan, P, hm, n_pairs, score_only, min_score, cells_out, waves_per_window);
+    interseq_plan_host(plan, P, hm, n_pairs, score_only, min_score, max_score, cells_out, waves_per_window);
     cudaError_t e;
     if ((e = plan.d_order.alloc(plan.order.size() * 4)) != cudaSuccess) goto fail;
     if ((e = plan.d_desc.alloc(plan.desc.size() * sizeof(WarpDesc))) != cudaSuccess) goto fail;
@@ -1401,7 +1442,8 @@ inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, i
     const int64_t groups = A.n_groups;
     interseq_pack_kernel<<<(unsigned)groups, 256, 0, stream>>>(
         (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.map, A.order, A.desc,
-        plan.slots[slot].rowcodes.as<uint16_t>(), plan.slots[slot].colcodes.as<uint16_t>(), groups);
+        plan.slots[slot].rowcodes.as<uint16_t>(), plan.slots[slot].colcodes.as<uint16_t>(), groups,
+        (uint32_t)plan.C.n_rows, (uint32_t)plan.C.n_cols, io.flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     (*launches)++;
@@ -1415,6 +1457,15 @@ inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, i
         else
             e = traced ? interseq_launch_linear_fill<IS_LOCAL, true>(plan.C, A, grid, smem, stream)
                        : interseq_launch_linear_fill<IS_LOCAL, false>(plan.C, A, grid, smem, stream);
+        if (e == cudaSuccess) (*launches)++;
+        return e;
+    }
+    if (traced && plan.C.dir_layout == 1) {
+        switch (plan.C.mode) {
+        case IS_GLOBAL: e = interseq_launch_tag_fill<IS_GLOBAL>(plan.C, A, stream); break;
+        case IS_SEMI: e = interseq_launch_tag_fill<IS_SEMI>(plan.C, A, stream); break;
+        default: e = interseq_launch_tag_fill<IS_LOCAL>(plan.C, A, stream); break;
+        }
         if (e == cudaSuccess) (*launches)++;
         return e;
     }

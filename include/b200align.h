@@ -182,6 +182,29 @@ int bt_align_batch(const BtParams *params, const void *codes1, const int64_t *of
                    uint8_t *ops_out);
 
 /*
+ * The same call with the traces in compact form, which is what should cross PCIe when the
+ * batch is large: trace_len as int32, and the steps as 2 bits each (0 = both advance, 1 = gap
+ * in sequence 1, 2 = gap in sequence 2; end-to-start order like the byte form).  Step s of pair
+ * k is bits 2 (s % 16) .. 2 (s % 16) + 1 of word ops2_out[ops2_off_out[k] + s / 16].  The
+ * (L, 2) int64 trace the reference's FFI returns (src/rust/sequence/align/trace.rs:103-130) is
+ * rebuilt from first + steps by bt_expand_traces2().  ops2_out must hold
+ * bt_ops2_capacity(off1, off2, n_pairs) words (a bound from the sequence lengths); only the
+ * words in use are copied from the device (about L / 4 bytes per pair); *ops2_words_out
+ * (optional) receives the end of the used range.  score_only: 0 or 1.  Page-locked output
+ * arrays (bt_pinned_alloc) let the copies of a window overlap the kernels of the next.
+ */
+int64_t bt_ops2_capacity(const int64_t *off1, const int64_t *off2, int64_t n_pairs);
+int bt_align_batch_compact(const BtParams *params, const void *codes1, const int64_t *off1,
+                           const void *codes2, const int64_t *off2, int64_t n_pairs,
+                           const int32_t *matrix, const int64_t *bands, int32_t score_only,
+                           int32_t *scores_out, int32_t *trace_len_out, int32_t *first_out,
+                           uint32_t *ops2_out, int64_t ops2_capacity, int64_t *ops2_off_out,
+                           int64_t *ops2_words_out);
+int bt_expand_traces2(int64_t n_pairs, const int32_t *trace_len, const int32_t *first,
+                      const uint32_t *ops2, const int64_t *ops2_off, const int64_t *bands,
+                      const int64_t *rows_off, int64_t *out);
+
+/*
  * Local X-drop extension of regions: the native part of align_local_gapped, replaces
  * `align_region` (src/rust/sequence/align/localgapped.rs:57-70; called from
  * src/biotite/sequence/align/localgapped.py:235-266 once per side of the seed).  Region r

@@ -55,3 +55,33 @@ def test_composite_result_keeps_batch_order():
     got = res.traces()
     for k in range(40):
         assert np.array_equal(got[k], ref[k]) and np.array_equal(res.trace(k), ref[k]), k
+
+
+def test_compact_steps_expand_like_step_bytes():
+    """bt_expand_traces2 (2-bit steps, int32 lengths) against bt_expand_traces (step bytes) on the
+    oracle's traces: the host half of the compact result form needs no GPU."""
+    from biotite_b200.batch import BatchResult
+    codes1, off1, codes2, off2 = _make_batch(seed=5, n_pairs=60)
+    matrix = bt.SubstitutionMatrix.std_protein_matrix().score_matrix()
+    whole = _oracle_compute(codes1, off1, codes2, off2, matrix, (-10, -1), False, False, None, False)
+    n = len(whole.scores)
+    ops_off = whole.ops_off
+    words_per_pair = (whole.trace_len + 15) // 16
+    ops2_off = np.concatenate(([0], np.cumsum(words_per_pair)[:-1])).astype(np.int64) + 3   # any layout will do
+    ops2 = np.full(int(ops2_off[-1] + words_per_pair[-1]) + 2, 0xFFFFFFFF, dtype=np.uint32)
+    for k in range(n):
+        steps = whole.ops[ops_off[k]:ops_off[k] + whole.trace_len[k]].astype(np.uint64)
+        for w in range(int(words_per_pair[k])):
+            chunk = steps[16 * w:16 * w + 16]
+            ops2[ops2_off[k] + w] = np.uint32(int(sum(int(v) << (2 * b) for b, v in enumerate(chunk))))
+    compact = BatchResult(whole.scores, whole.trace_len.astype(np.int32), whole.first, None, ops2_off)
+    compact.ops2 = ops2
+    ref = whole.traces()
+    got = compact.traces()
+    for k in range(n):
+        assert np.array_equal(got[k], ref[k]) and np.array_equal(compact.trace(k), ref[k]), k
+    # capacity bound of the one-shot call: depends on the lengths only and always suffices
+    from biotite_b200 import _cabi
+    lib = _cabi.load()
+    cap = lib.bt_ops2_capacity(_cabi.ptr(off1), _cabi.ptr(off2), n)
+    assert cap >= int(((np.diff(off1) + np.diff(off2) + 15) // 16).sum())
