@@ -98,6 +98,7 @@ struct Window {
 // Scratch buffers of one in-flight window.
 struct SlotBuffers {
     DevBuf rowcodes, colcodes, dirs, rowbuf, lastrow, lastcol;
+    DevBuf ctl;   // 4 ints: largest column letter of the window, group counters of the persistent kernels
 };
 
 // Host-side plan of one batch.
@@ -218,7 +219,7 @@ inline bool interseq_eligible(const BtParams &P, const PairMap &hm, int64_t n_pa
 __global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes2, const PairMap map,
                                      const int32_t *order, const WarpDesc *desc,
                                      uint16_t *rowcodes, uint16_t *colcodes, int64_t n_groups,
-                                     uint32_t n_rows, uint32_t n_cols, int *flag) {
+                                     uint32_t n_rows, uint32_t n_cols, int *flag, int *maxcol) {
     const int64_t g = blockIdx.x;
     if (g >= n_groups) return;
     const WarpDesc d = desc[g];
@@ -237,13 +238,20 @@ __global__ void interseq_pack_kernel(const uint8_t *codes1, const uint8_t *codes
         if (hi >= n_rows) { bad = true; hi = n_rows - 1; }
         rowcodes[d.rowcode_off + (int64_t)i * 32 + lane] = (uint16_t)(lo | (hi << 8));
     }
+    uint32_t top = 0;
     for (int j = sub; j < d.mmax; j += nsub) {
         uint32_t lo = j < m_lo ? codes2[b_lo + j] : 0, hi = j < m_hi ? codes2[b_hi + j] : 0;
         if (lo >= n_cols) { bad = true; lo = n_cols - 1; }
         if (hi >= n_cols) { bad = true; hi = n_cols - 1; }
+        top = max(top, max(lo, hi));
         colcodes[d.colcode_off + (int64_t)j * 32 + lane] = (uint16_t)(lo | (hi << 8));
     }
     if (bad && flag) *flag = 1;
+    if (maxcol) {
+        // largest column letter of the window: decides how many letters the stripe profiles hold
+        top = __reduce_max_sync(0xffffffffu, top);
+        if (lane == 0 && top > 0) atomicMax(maxcol, (int)top);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1381,6 +1389,7 @@ inline int interseq_prepare(InterseqPlan &plan, const BtParams &P, const PairMap
         if ((e = b.colcodes.alloc((size_t)(plan.max_colcodes + IS_SLACK * 32) * 2)) != cudaSuccess) goto fail;
         if ((e = b.rowbuf.alloc((size_t)(plan.max_rowbuf + IS_SLACK * 32) * 12)) != cudaSuccess) goto fail;
         if ((e = b.dirs.alloc((size_t)plan.max_dir_words * 4)) != cudaSuccess) goto fail;
+        if ((e = b.ctl.alloc(16)) != cudaSuccess) goto fail;
         if (plan.C.mode == IS_SEMI) {
             if ((e = b.lastrow.alloc((size_t)plan.max_rowbuf * 8)) != cudaSuccess) goto fail;
             if ((e = b.lastcol.alloc((size_t)plan.max_rowcodes * 8)) != cudaSuccess) goto fail;
@@ -1440,11 +1449,14 @@ inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, i
                                         cudaStream_t stream, int64_t *launches) {
     const InterseqArgs A = interseq_args(plan, win, slot, io);
     const int64_t groups = A.n_groups;
+    int *const ctl = plan.slots[slot].ctl.as<int>();
+    cudaError_t e = cudaMemsetAsync(ctl, 0, 16, stream);
+    if (e != cudaSuccess) return e;
     interseq_pack_kernel<<<(unsigned)groups, 256, 0, stream>>>(
         (const uint8_t *)io.codes1, (const uint8_t *)io.codes2, io.map, A.order, A.desc,
         plan.slots[slot].rowcodes.as<uint16_t>(), plan.slots[slot].colcodes.as<uint16_t>(), groups,
-        (uint32_t)plan.C.n_rows, (uint32_t)plan.C.n_cols, io.flag);
-    cudaError_t e = cudaGetLastError();
+        (uint32_t)plan.C.n_rows, (uint32_t)plan.C.n_cols, io.flag, ctl);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     (*launches)++;
     const size_t smem = (size_t)plan.C.n_rows * plan.C.n_cols * IS_ROWW;
@@ -1461,12 +1473,12 @@ inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, i
         return e;
     }
     if (traced && plan.C.dir_layout == 1) {
+        const int sms = (int)(interseq_wave_groups() / IS_WARPS_PER_SM);
         switch (plan.C.mode) {
-        case IS_GLOBAL: e = interseq_launch_tag_fill<IS_GLOBAL>(plan.C, A, stream); break;
-        case IS_SEMI: e = interseq_launch_tag_fill<IS_SEMI>(plan.C, A, stream); break;
-        default: e = interseq_launch_tag_fill<IS_LOCAL>(plan.C, A, stream); break;
+        case IS_GLOBAL: e = interseq_launch_tag_fill<IS_GLOBAL>(plan.C, A, ctl, sms, stream, launches); break;
+        case IS_SEMI: e = interseq_launch_tag_fill<IS_SEMI>(plan.C, A, ctl, sms, stream, launches); break;
+        default: e = interseq_launch_tag_fill<IS_LOCAL>(plan.C, A, ctl, sms, stream, launches); break;
         }
-        if (e == cudaSuccess) (*launches)++;
         return e;
     }
     switch (plan.C.mode) {
@@ -1581,6 +1593,7 @@ struct StreamingPlanner {
             if ((e = b.colcodes.alloc((size_t)(plan.max_colcodes + IS_SLACK * 32) * 2)) != cudaSuccess) return e;
             if ((e = b.rowbuf.alloc((size_t)(plan.max_rowbuf + IS_SLACK * 32) * 12)) != cudaSuccess) return e;
             if ((e = b.dirs.alloc((size_t)plan.max_dir_words * 4)) != cudaSuccess) return e;
+            if ((e = b.ctl.alloc(16)) != cudaSuccess) return e;
             if (plan.C.mode == IS_SEMI) {
                 if ((e = b.lastrow.alloc((size_t)plan.max_rowbuf * 8)) != cudaSuccess) return e;
                 if ((e = b.lastcol.alloc((size_t)plan.max_rowcodes * 8)) != cudaSuccess) return e;

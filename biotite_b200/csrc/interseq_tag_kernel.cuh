@@ -53,18 +53,27 @@ inline bool interseq_tag_eligible(const BtParams &P, const PairScan &scan, int32
 __device__ __forceinline__ int tg_lo(uint32_t x) { return (int)(int16_t)(x & 0xffffu) >> 2; }
 __device__ __forceinline__ int tg_hi(uint32_t x) { return (int)(int16_t)(x >> 16) >> 2; }
 
-template <int MODE, int PF, int WARPS>
-__global__ void __launch_bounds__(32, WARPS)
-interseq_tag_fill_kernel(const InterseqConst C, const InterseqArgs A) {
-    extern __shared__ uint4 smem_prof[];
-    const int lane = threadIdx.x;
-    const int64_t g = blockIdx.x;
-    const WarpDesc d = A.desc[g];
-    const int32_t p_lo = A.order[g * 64 + 2 * lane], p_hi = A.order[g * 64 + 2 * lane + 1];
-    int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
-    if (p_lo >= 0) { n_lo = (int)A.map.len1(p_lo); m_lo = (int)A.map.len2(p_lo); }
-    if (p_hi >= 0) { n_hi = (int)A.map.len1(p_hi); m_hi = (int)A.map.len2(p_hi); }
-
+// Persistent: one block per SM, `blockDim.x / 32` warps per block, every warp takes the next
+// group of 64 pairs from a counter until none is left (no partial last wave, and the 1 KiB of
+// shared memory the system reserves per block is paid once per SM instead of once per warp).
+// The stripe profile of a warp holds the first `n_eff` column letters only: the launcher picks
+// n_eff and the number of warps that then fit (interseq_launch_tag_fill); `ctl` carries the
+// largest column letter the packer saw in this window, so that a variant built for fewer letters
+// than the matrix has steps aside when a rarer letter turns up (the variant for all letters,
+// launched right after it, then does the work).
+template <int MODE, int PF, int MAXW>
+__global__ void __launch_bounds__(32 * MAXW, 1)
+interseq_tag_fill_kernel(const InterseqConst C, const InterseqArgs A, const int n_eff, const int small_letters,
+                         int *const ctl, const int counter_slot) {
+    extern __shared__ uint4 smem_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        // ctl[0]: largest column letter of the window.  A variant whose profile is shorter than the
+        // matrix runs only if every letter fits; the full variant only if the short one did not run.
+        const int maxcol = ctl[0];
+        if (n_eff < C.n_cols ? maxcol >= n_eff : (small_letters > 0 && maxcol < small_letters)) return;
+    }
+    uint4 *const smem_prof = smem_all + (size_t)warp * 2 * n_eff * 32;
     const uint32_t ext4 = ((uint32_t)(4 * C.gap_ext) & 0xffffu) * 0x10001u;
     const uint32_t open4 = ((uint32_t)(4 * C.gap_open) & 0xffffu) * 0x10001u;
     const uint32_t neg4 = ((uint32_t)(4 * C.neg) & 0xffffu) * 0x10001u;
@@ -73,7 +82,17 @@ interseq_tag_fill_kernel(const InterseqConst C, const InterseqArgs A) {
     const uint32_t opaque = (uint32_t)C.n_cols >> 31;            // 0
     const uint32_t one2 = TG_ONE + opaque, clr = TG_CLR - opaque, msk = TG_MASK + opaque;
     const uint32_t pbase = (uint32_t)__cvta_generic_to_shared(smem_prof) + lane * 16;
-    const uint32_t pbase_hi = pbase + (uint32_t)C.n_cols * 512u;
+    const uint32_t pbase_hi = pbase + (uint32_t)n_eff * 512u;
+  for (;;) {
+    int64_t g = 0;
+    if (lane == 0) g = atomicAdd(ctl + counter_slot, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= A.n_groups) break;
+    const WarpDesc d = A.desc[g];
+    const int32_t p_lo = A.order[g * 64 + 2 * lane], p_hi = A.order[g * 64 + 2 * lane + 1];
+    int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
+    if (p_lo >= 0) { n_lo = (int)A.map.len1(p_lo); m_lo = (int)A.map.len2(p_lo); }
+    if (p_hi >= 0) { n_hi = (int)A.map.len1(p_hi); m_hi = (int)A.map.len2(p_hi); }
 
     const uint16_t *rc = A.rowcodes + d.rowcode_off + lane;
     const uint16_t *cc = A.colcodes + d.colcode_off + lane;
@@ -114,7 +133,7 @@ interseq_tag_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                 a_hi[r] = (v >> 8) * (uint32_t)C.n_cols;
             }
             __syncwarp();
-            for (int b = 0; b < C.n_cols; b++) {
+            for (int b = 0; b < n_eff; b++) {
                 const int32_t *col = A.matrix + b;
                 uint32_t w_lo[4], w_hi[4];
 #pragma unroll
@@ -127,7 +146,7 @@ interseq_tag_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                     }
                 }
                 smem_prof[b * 32 + lane] = make_uint4(w_lo[0], w_lo[1], w_lo[2], w_lo[3]);
-                smem_prof[(C.n_cols + b) * 32 + lane] = make_uint4(w_hi[0], w_hi[1], w_hi[2], w_hi[3]);
+                smem_prof[(n_eff + b) * 32 + lane] = make_uint4(w_hi[0], w_hi[1], w_hi[2], w_hi[3]);
             }
             __syncwarp();
         }
@@ -297,21 +316,54 @@ interseq_tag_fill_kernel(const InterseqConst C, const InterseqArgs A) {
         if (p_lo >= 0) { A.start[2 * p_lo] = bidx_lo / (m_lo + 1); A.start[2 * p_lo + 1] = bidx_lo % (m_lo + 1); }
         if (p_hi >= 0) { A.start[2 * p_hi] = bidx_hi / (m_hi + 1); A.start[2 * p_hi + 1] = bidx_hi % (m_hi + 1); }
     }
+    __syncwarp();   // the next group's profile overwrites this one's
+  }
 }
 
-#ifndef TAGW
-#define TAGW 9
-#endif
+constexpr int TG_SMEM_BYTES = 226 * 1024;   // per SM: 227 KiB less the block's reserved KiB
+constexpr int TG_SMALL_LETTERS = 20;        // the standard amino acids: 11 warps per SM instead of 9
+
+// warps per SM whose stripe profiles of n_eff letters fit
+inline int interseq_tag_warps(int n_eff) { return std::max(1, std::min(16, TG_SMEM_BYTES / (2 * n_eff * 512))); }
+
 template <int MODE>
-inline cudaError_t interseq_launch_tag_fill(const InterseqConst &C, const InterseqArgs &A, cudaStream_t stream) {
-    const size_t smem = (size_t)2 * C.n_cols * 512;
-    auto kernel = interseq_tag_fill_kernel<MODE, BT_PF_TRACED, TAGW>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    kernel<<<(unsigned)A.n_groups, 32, smem, stream>>>(C, A);
+inline cudaError_t interseq_launch_tag_variant(const InterseqConst &C, const InterseqArgs &A, int n_eff,
+                                               int small_letters, int *ctl, int counter_slot, int sms,
+                                               cudaStream_t stream) {
+    const int warps = interseq_tag_warps(n_eff);
+    const size_t smem = (size_t)warps * 2 * n_eff * 512;
+    const unsigned grid = (unsigned)std::min<int64_t>(sms, (A.n_groups + warps - 1) / warps);
+    cudaError_t e;
+    if (warps > 11) {   // small alphabets: up to 16 warps, 128 registers each
+        auto kernel = interseq_tag_fill_kernel<MODE, BT_PF_TRACED, 16>;
+        if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        kernel<<<grid, 32 * warps, smem, stream>>>(C, A, n_eff, small_letters, ctl, counter_slot);
+    } else {
+        auto kernel = interseq_tag_fill_kernel<MODE, BT_PF_TRACED, 11>;
+        if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        kernel<<<grid, 32 * warps, smem, stream>>>(C, A, n_eff, small_letters, ctl, counter_slot);
+    }
     return cudaGetLastError();
+}
+
+// ctl: three ints of the window's slot - [0] largest column letter (written by the packer),
+// [1], [2] group counters of the two variants (zeroed with [0] before the packer runs).
+template <int MODE>
+inline cudaError_t interseq_launch_tag_fill(const InterseqConst &C, const InterseqArgs &A, int *ctl, int sms,
+                                            cudaStream_t stream, int64_t *launches) {
+    cudaError_t e = cudaSuccess;
+    int small_letters = 0;
+    if (C.n_cols > TG_SMALL_LETTERS && interseq_tag_warps(TG_SMALL_LETTERS) > interseq_tag_warps(C.n_cols)) {
+        // matrices with more letters than the 20 standard amino acids (B, Z, X, * of the protein
+        // alphabet): windows that use only those get the larger number of warps
+        small_letters = TG_SMALL_LETTERS;
+        e = interseq_launch_tag_variant<MODE>(C, A, small_letters, small_letters, ctl, 1, sms, stream);
+        if (e != cudaSuccess) return e;
+        (*launches)++;
+    }
+    e = interseq_launch_tag_variant<MODE>(C, A, C.n_cols, small_letters, ctl, 2, sms, stream);
+    if (e == cudaSuccess) (*launches)++;
+    return e;
 }
 
 }  // namespace bt
