@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "pool.cuh"
 #include "general_kernel.cuh"
+#include "wavefront_kernel.cuh"
 #include "host_trace.hpp"
 #include "interseq_kernel.cuh"
 #include "banded_kernel.cuh"
@@ -146,6 +147,7 @@ struct BtBatch {
     int stats = 0;        // traceback emits gap statistics, no step bytes
     int device = 0;
     Route route = ROUTE_GENERAL;
+    bool wavefront = false;   // general route: intra-pair wavefront kernel (else the anti-diagonal kernel)
     int64_t cells = 0, launches = 0;
     int64_t total1 = 0, total2 = 0;
     int min_score = 0, max_score = 0;
@@ -258,6 +260,18 @@ static cudaError_t dispatch_general_fill(const DevParams &D, const BatchView &V,
 
 static cudaError_t dispatch_general_traceback(const DevParams &D, const BatchView &V, int64_t count,
                                               cudaStream_t s) {
+    if (D.dir_pad) {
+        // padded tables (wavefront route): one warp per pair walks a cached tile
+        const int grid = (int)((count + 3) / 4);
+        if (D.affine) {
+            if (D.banded) wavefront_traceback_kernel<true, true><<<grid, 128, 0, s>>>(D, V);
+            else wavefront_traceback_kernel<true, false><<<grid, 128, 0, s>>>(D, V);
+        } else {
+            if (D.banded) wavefront_traceback_kernel<false, true><<<grid, 128, 0, s>>>(D, V);
+            else wavefront_traceback_kernel<false, false><<<grid, 128, 0, s>>>(D, V);
+        }
+        return cudaGetLastError();
+    }
     const int threads = 128;
     const int grid = (int)((count + threads - 1) / threads);
     if (D.affine) {
@@ -270,6 +284,81 @@ static cudaError_t dispatch_general_traceback(const DevParams &D, const BatchVie
     return cudaGetLastError();
 }
 
+template <bool AFFINE, bool BANDED, int MODE, bool TRACED>
+static cudaError_t launch_wavefront_fill(const DevParams &D, const BatchView &V, const WfArgs &A, int grid, int threads,
+                                         size_t smem, cudaStream_t s) {
+    // rows per lane: 2 under a band (its windows move two columns per lane), 4 on full tables
+    auto kernel = wavefront_fill_kernel<AFFINE, BANDED, MODE, TRACED, BANDED ? 2 : 4>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kernel<<<grid, threads, smem, s>>>(D, V, A);
+    return cudaGetLastError();
+}
+
+template <bool AFFINE, bool BANDED>
+static cudaError_t dispatch_wavefront_mode(const DevParams &D, const BatchView &V, const WfArgs &A, int grid,
+                                           int threads, size_t smem, cudaStream_t s) {
+    if (D.local)
+        return D.score_only ? launch_wavefront_fill<AFFINE, BANDED, WF_LOCAL, false>(D, V, A, grid, threads, smem, s)
+                            : launch_wavefront_fill<AFFINE, BANDED, WF_LOCAL, true>(D, V, A, grid, threads, smem, s);
+    if (!BANDED && !D.terminal)
+        return D.score_only ? launch_wavefront_fill<AFFINE, false, WF_SEMI, false>(D, V, A, grid, threads, smem, s)
+                            : launch_wavefront_fill<AFFINE, false, WF_SEMI, true>(D, V, A, grid, threads, smem, s);
+    return D.score_only ? launch_wavefront_fill<AFFINE, BANDED, WF_GLOBAL, false>(D, V, A, grid, threads, smem, s)
+                        : launch_wavefront_fill<AFFINE, BANDED, WF_GLOBAL, true>(D, V, A, grid, threads, smem, s);
+}
+
+static cudaError_t dispatch_wavefront_fill(const DevParams &D, const BatchView &V, const WfArgs &A, int grid,
+                                           int threads, size_t smem, cudaStream_t s) {
+    if (D.affine) {
+        return D.banded ? dispatch_wavefront_mode<true, true>(D, V, A, grid, threads, smem, s)
+                        : dispatch_wavefront_mode<true, false>(D, V, A, grid, threads, smem, s);
+    }
+    return D.banded ? dispatch_wavefront_mode<false, true>(D, V, A, grid, threads, smem, s)
+                    : dispatch_wavefront_mode<false, false>(D, V, A, grid, threads, smem, s);
+}
+
+// Fill of pairs [begin, end) with the intra-pair wavefront kernel.  `max_n`, `max_m`: longest
+// sequences among them; `gscratch` holds the stripe boundaries when they do not fit shared memory.
+static int wavefront_launch(const BtParams &P, const DevParams &D, BatchView V, int64_t begin, int64_t end,
+                            int max_n, int max_m, DevBuf &gscratch, cudaStream_t stream, int64_t *launches) {
+    const int NS = P.affine ? 3 : 1;
+    const int mat_ints = P.use_matrix ? P.n_rows * P.n_cols : 0;
+    const int R = P.banded ? 2 : 4;   // rows per lane (launch_wavefront_fill)
+    const int rows = 32 * R;
+    const int nw = std::max(1, std::min(WF_MAX_WARPS, (max_n + rows - 1) / rows));
+    WfArgs A{};
+    A.bnd_cols = max_m + 8;
+    A.mat_smem = (mat_ints > 0 && mat_ints <= 4096) ? 1 : 0;
+    const int64_t bnd_ints = (int64_t)nw * A.bnd_cols * NS;
+    const int64_t smem_ints = (A.mat_smem ? mat_ints : 0) + bnd_ints;
+    int64_t per_launch = end - begin;
+    size_t smem = 0;
+    if (smem_ints <= 24 * 1024) {
+        smem = (size_t)smem_ints * 4;            // boundaries in shared memory (up to 96 KB)
+    } else {
+        smem = (size_t)(A.mat_smem ? mat_ints : 0) * 4;
+        A.bnd_block = bnd_ints;
+        per_launch = std::max<int64_t>(1, std::min<int64_t>(per_launch, (2ll << 30) / (bnd_ints * 4)));
+        if (gscratch.bytes < (size_t)(per_launch * bnd_ints * 4))
+            CUDA_TRY(gscratch.alloc((size_t)(per_launch * bnd_ints * 4)));
+        A.bnd = gscratch.as<int32_t>();
+    }
+    for (int64_t p0 = begin; p0 < end; p0 += per_launch) {
+        V.pair_begin = p0; V.pair_end = std::min(end, p0 + per_launch);
+        const int grid = (int)(V.pair_end - V.pair_begin);
+        CUDA_TRY(dispatch_wavefront_fill(D, V, A, grid, 32 * nw, smem, stream));
+        if (launches) (*launches)++;
+    }
+    return BT_OK;
+}
+
+static int run_wavefront_chunk(BtBatch *b, const Chunk &c, const DevParams &D, BatchView V) {
+    return wavefront_launch(b->P, D, V, c.begin, c.end, c.max_n, c.max_m, b->gscratch, b->stream, &b->launches);
+}
+
 // Runs fill (+ first-optimal traceback) of the general route for every chunk.
 static int run_general(BtBatch *b, bool traceback) {
     const bool affine = b->P.affine != 0;
@@ -278,6 +367,21 @@ static int run_general(BtBatch *b, bool traceback) {
     for (const Chunk &c : b->chunks) {
         BatchView V = make_view(b);
         DevParams D = b->D;
+        if (b->wavefront) {
+            // never-filled band cells and the padding behind every row read as "no direction"
+            if (!b->score_only) CUDA_TRY(cudaMemsetAsync(b->dirs.ptr, 0, (size_t)c.dir_bytes, b->stream));
+            CUDA_TRY(b->mark_phase());
+            int st = run_wavefront_chunk(b, c, D, V);
+            if (st) return st;
+            CUDA_TRY(b->mark_phase());
+            if (traceback && !b->score_only) {
+                V.pair_begin = c.begin; V.pair_end = c.end;
+                CUDA_TRY(dispatch_general_traceback(D, V, c.end - c.begin, b->stream));
+                b->launches++;
+            }
+            CUDA_TRY(b->mark_phase());
+            continue;
+        }
         const int slots = b->P.banded ? c.max_w + 2 : c.max_n + 1;
         const int64_t wave_ints = 3ll * slots * NS;
         D.matrix_in_smem = (mat_ints > 0 && mat_ints <= 4096) ? 1 : 0;
@@ -339,7 +443,7 @@ static int build_chunks(BtBatch *b) {
             if (w < 1) return fail(BT_ERR_INVALID_ARG, "The width of the band is 0");
             if (lo < -l1 || up > l2)
                 return fail(BT_ERR_INVALID_ARG, "Alignment band is out of range (crop it to the sequences)");
-            bytes = (l1 + 1) * (w + 2);
+            bytes = (l1 + 1) * table_stride(b->D.dir_pad, w + 2);
             // cells: in-band, in-sequence positions (banded.rs:199-207)
             for (int64_t i = 0; i < l1; i++) {
                 int64_t j0 = std::max<int64_t>(i + lo, 0), j1 = std::min<int64_t>(i + up + 1, l2);
@@ -348,7 +452,7 @@ static int build_chunks(BtBatch *b) {
             b->h_cand_off[k] = cand_total;
             cand_total += 3 * (w + 2);
         } else {
-            bytes = (l1 + 1) * (l2 + 1);
+            bytes = (l1 + 1) * table_stride(b->D.dir_pad, l2 + 1);
             b->cells += l1 * l2;
         }
         if (b->score_only) bytes = 0;
@@ -529,6 +633,17 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
         if (st == BT_ERR_OOM) return fail(st, "out of device memory (banded plan)");
         if (st) return fail(st, "banded plan failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
+        // The wavefront kernel takes row 0 / column 0 from closed forms, which equal the
+        // reference's running sums as long as no sum can wrap: a bound on every |value|.
+        {
+            int64_t span = 0;
+            for (int64_t k = 0; k < n_pairs; k++) span = std::max(span, hm.len1(k) + hm.len2(k));
+            const int64_t step = std::max<int64_t>({std::abs((int64_t)mn), std::abs((int64_t)mx),
+                                                    std::abs((int64_t)params->gap_open), std::abs((int64_t)params->gap_ext)});
+            const char *forced = getenv("B200ALIGN_GENERAL");
+            b->wavefront = step * (span + 4) < (1ll << 30) && !(forced && strcmp(forced, "antidiag") == 0);
+            D.dir_pad = b->wavefront ? 1 : 0;
+        }
         st = build_chunks(b.get());
         if (st) return st;
         CUDA_TRY(b->dir_off.alloc((size_t)n_pairs * 8));
@@ -940,7 +1055,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     // of a window (uploaded as soon as it is planned), then the next window's input codes, ...
     // (the host enqueues all of this within the first few milliseconds)
     CUDA_TRY(enqueue_inputs(0));
-    CUDA_TRY(planner.allocate(2, scan.nmax, scan.mmax));
+    CUDA_TRY(planner.allocate(1, scan.nmax, scan.mmax));
     planner.start();
     const double t2 = now();
 
@@ -950,9 +1065,13 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
                   d_score.as<int32_t>(), d_len.as<int64_t>(), d_first.as<int32_t>(), d_ops.as<uint8_t>(),
                   d_start.as<int32_t>(), d_flag.as<int>()};
     int64_t launches = 0;
-    std::vector<cudaEvent_t> tev;   // B200ALIGN_TRACE: per window [start, h2d done, kernels done, d2h done]
-    auto mark = [&](cudaStream_t s) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e); } };
+    // B200ALIGN_TRACE: per window [start, h2d done, kernels done, d2h done]
+    std::vector<cudaEvent_t> tev(trace ? (size_t)planner.n_windows * 4 : 0, nullptr);
+    auto mark = [&](size_t w, int what, cudaStream_t s) {
+        if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev[w * 4 + what] = e; }
+    };
     int64_t words_end = 0;
+    std::vector<double> host_t(trace ? (size_t)planner.n_windows * 3 : 0, 0.0);   // host clock: planned, enqueued, drained
     // results of window w to the host: everything a window returns is a contiguous range of the
     // output arrays.  The compact form waits (on the host) for the window's kernels, because the
     // size of its step words is only known then; by that time the next window is already queued.
@@ -990,21 +1109,25 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
                     CUDA_TRY(cudaMemcpyAsync(out.ops + a, d_ops.as<uint8_t>() + a, (size_t)(b - a), cudaMemcpyDeviceToHost, r));
             }
         }
-        mark(r);
+        mark(w, 3, r);
+        if (trace) host_t[w * 3 + 2] = now() - t0;
         return BT_OK;
     };
     for (size_t w = 0; w < plan.windows.size(); w++) {
-        const int slot = (int)(w & 1);
-        cudaStream_t s = st.s[slot];
+        // one compute stream: the persistent fill kernels fill the machine, and a traceback beside
+        // the next window's fill slows that fill by as much as it saves (measured)
+        const int slot = 0;
+        cudaStream_t s = st.s[0];
         CUDA_TRY(planner.take((int64_t)w, st.h2d));
+        if (trace) host_t[w * 3] = now() - t0;
         CUDA_TRY(cudaEventRecord(st.plan_ready[w], st.h2d));
         if ((int64_t)w + 1 < planner.n_windows) CUDA_TRY(enqueue_inputs((int64_t)w + 1));
         CUDA_TRY(cudaStreamWaitEvent(s, st.plan_ready[w], 0));
-        mark(s);
+        mark(w, 0, s);
         const Window &win = plan.windows[w];
         const int64_t np = win.pair_end - win.pair_begin;
         CUDA_TRY(cudaStreamWaitEvent(s, st.in_ready[w], 0));
-        mark(s);
+        mark(w, 1, s);
         CUDA_TRY(interseq_fill_window(plan, win, slot, io, s, &launches));
         CUDA_TRY(interseq_traceback_window(plan, win, slot, io, s, &launches));
         if (compact) {
@@ -1015,8 +1138,9 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
             CUDA_TRY(compact_launch(ca, s, &launches));
             CUDA_TRY(cudaMemcpyAsync(h_total.as<int64_t>() + w, d_total.as<int64_t>() + w, 8, cudaMemcpyDeviceToHost, s));
         }
-        mark(s);
+        mark(w, 2, s);
         CUDA_TRY(cudaEventRecord(st.k_done[w], s));
+        if (trace) host_t[w * 3 + 1] = now() - t0;
         if (!compact) { int rc = drain(w); if (rc) return rc; }
         else if (w > 0) { int rc = drain(w - 1); if (rc) return rc; }
     }
@@ -1029,12 +1153,14 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     CUDA_TRY(cudaStreamSynchronize(st.d2h));
     if (trace) {
         for (size_t w = 0; w * 4 + 3 < tev.size(); w++) {
+            if (!tev[w * 4] || !tev[w * 4 + 1] || !tev[w * 4 + 2] || !tev[w * 4 + 3]) continue;
             float a = 0, b = 0, c = 0, d = 0;
             cudaEventElapsedTime(&a, tev0, tev[w * 4]); cudaEventElapsedTime(&b, tev0, tev[w * 4 + 1]);
             cudaEventElapsedTime(&c, tev0, tev[w * 4 + 2]); cudaEventElapsedTime(&d, tev0, tev[w * 4 + 3]);
-            fprintf(stderr, "[b200align]   window %zu: start %.2f  h2d done %.2f  kernels done %.2f  d2h done %.2f ms\n", w, a, b, c, d);
+            fprintf(stderr, "[b200align]   window %zu: start %.2f  h2d done %.2f  kernels done %.2f  d2h done %.2f ms | host: planned %.2f enqueued %.2f drained %.2f\n",
+                    w, a, b, c, d, host_t[w * 3], host_t[w * 3 + 1], host_t[w * 3 + 2]);
         }
-        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        for (cudaEvent_t e : tev) if (e) cudaEventDestroy(e);
         cudaEventDestroy(tev0);
     }
     if (trace)
@@ -1110,7 +1236,7 @@ static int align_batch_impl(const BtParams *params, const void *codes1, const in
         // the streaming path sizes its two scratch slots from the longest sequences of the batch;
         // batches with very long pairs go through the resident path, whose windows follow the
         // actual direction-table sizes
-        const double slot_dirs = score_only ? 0.0 : (double)(interseq_pairs_per_window(n_pairs, 3) / 64) *
+        const double slot_dirs = score_only ? 0.0 : (double)(interseq_pairs_per_window(n_pairs, 3, 12) / 64) *
                                                         (double)((scan.nmax + IS_R - 1) / IS_R) * (double)scan.mmax *
                                                         128.0 * (params->affine ? 4 : 2);
         if (off1[0] == 0 && off2[0] == 0 && slot_dirs <= (double)IS_DIR_BUDGET &&
@@ -1350,74 +1476,14 @@ extern "C" int bt_tracelist_copy(const BtTraceList *l, int64_t k, int64_t *out) 
 }
 extern "C" void bt_tracelist_free(BtTraceList *l) { delete l; }
 
-extern "C" int bt_align_pair(const BtParams *params, const void *code1, int64_t len1, const void *code2,
-                             int64_t len2, const int32_t *matrix, int64_t lower_diag, int64_t upper_diag,
-                             int32_t score_only, int64_t max_number, int32_t *score_out,
-                             BtTraceList **traces_out) {
-    if (!score_out) return fail(BT_ERR_INVALID_ARG, "score_out is NULL");
-    if (traces_out) *traces_out = nullptr;
-    score_only = score_only ? 1 : 0;
-    if (!score_only && !traces_out) return fail(BT_ERR_INVALID_ARG, "traces_out is NULL");
-    if (max_number < 1) return fail(BT_ERR_INVALID_ARG, "Maximum number of returned alignments must be at least 1");
-    const int64_t off1[2] = {0, len1}, off2[2] = {0, len2};
-    const int64_t band[2] = {lower_diag, upper_diag};
-    // the single-pair path always uses full direction sets (general route)
-    BtParams P = *params;
-    BtBatch *raw = nullptr;
-    int st = batch_create_impl(&P, code1, off1, 1, code2, off2, 1, nullptr, nullptr, 1, matrix,
-                               P.banded ? band : nullptr, score_only, true, &raw);
-    if (st) return st;
-    std::unique_ptr<BtBatch> b(raw);
-    const bool first_only = (max_number == 1);
-    b->phase_used = 0;
-    st = run_general(b.get(), first_only);
-    if (st) return st;
-    b->ran = true;
-    int32_t score = 0;
-    CUDA_TRY(cudaMemcpyAsync(&score, b->score.ptr, 4, cudaMemcpyDeviceToHost, b->stream));
-    CUDA_TRY(cudaStreamSynchronize(b->stream));
-    *score_out = score;
-    if (score_only) return BT_OK;
-
-    std::unique_ptr<BtTraceList> list(new BtTraceList());
+// Co-optimal enumeration on the host over a direction table copied back from the GPU
+// (trace.rs:21-92; starts: pairwise.rs:532-559, :845-881, banded.rs:377-414, :550-593).
+static void enumerate_traces(const BtParams &P, const uint8_t *dir, const int32_t *cand, const int32_t endv[3],
+                             int32_t score, int64_t len1, int64_t len2, int64_t lower_diag, int64_t upper_diag,
+                             int64_t rs, int64_t max_number, BtTraceList &list) {
     const bool banded = P.banded != 0, affine = P.affine != 0;
     const int64_t W = upper_diag - lower_diag + 1;
-    const int64_t rs = banded ? W + 2 : len2 + 1;
-    if (first_only) {
-        int64_t len = 0; int32_t first[2] = {0, 0};
-        CUDA_TRY(cudaMemcpyAsync(&len, b->trace_len.ptr, 8, cudaMemcpyDeviceToHost, b->stream));
-        CUDA_TRY(cudaMemcpyAsync(first, b->first.ptr, 8, cudaMemcpyDeviceToHost, b->stream));
-        CUDA_TRY(cudaStreamSynchronize(b->stream));
-        std::vector<uint8_t> ops((size_t)std::max<int64_t>(len, 1));
-        if (len > 0) CUDA_TRY(cudaMemcpy(ops.data(), b->ops.ptr, (size_t)len, cudaMemcpyDeviceToHost));
-        std::vector<int64_t> rows((size_t)(2 * len));
-        int64_t nrows = expand_ops(len, first[0], first[1], ops.data(), banded, lower_diag, rows.data());
-        rows.resize((size_t)(2 * nrows));
-        list->traces.push_back(std::move(rows));
-        *traces_out = list.release();
-        return BT_OK;
-    }
-
-    // ---- co-optimal enumeration on the host over the direction table ------------------
-    if (P.local) {
-        // second pass tags every cell whose M equals the optimum (pairwise.rs:536-551)
-        b->D.mark = 1; b->D.mark_value = score;
-        b->phase_used = 0;
-        st = run_general(b.get(), false);
-        if (st) return st;
-    }
     const int64_t table = (len1 + 1) * rs;
-    std::vector<uint8_t> dir((size_t)table);
-    CUDA_TRY(cudaMemcpyAsync(dir.data(), b->dirs.ptr, (size_t)table, cudaMemcpyDeviceToHost, b->stream));
-    std::vector<int32_t> cand;
-    int32_t endv[3] = {0, 0, 0};
-    if (banded && !P.local) {
-        cand.resize((size_t)(3 * (W + 2)));
-        CUDA_TRY(cudaMemcpyAsync(cand.data(), b->cand.ptr, cand.size() * 4, cudaMemcpyDeviceToHost, b->stream));
-    }
-    CUDA_TRY(cudaMemcpyAsync(endv, b->end_vals.ptr, 12, cudaMemcpyDeviceToHost, b->stream));
-    CUDA_TRY(cudaStreamSynchronize(b->stream));
-
     std::vector<Start> starts;
     if (P.local) {
         for (int64_t idx = 0; idx < table && (int64_t)starts.size() < max_number; idx++) {
@@ -1454,15 +1520,297 @@ extern "C" int bt_align_pair(const BtParams *params, const void *code1, int64_t 
     const int64_t off[3] = {banded ? -rs : -(rs + 1), -1, banded ? -rs + 1 : -rs};
     std::vector<Path> paths;
     for (const Start &s0 : starts) {
-        enumerate_from(dir.data(), affine, off, s0, max_number, max_number, paths);
+        enumerate_from(dir, affine, off, s0, max_number, max_number, paths);
         if ((int64_t)paths.size() >= max_number) break;
     }
     if ((int64_t)paths.size() > max_number) paths.resize((size_t)max_number);
     std::vector<int64_t> rows;
     for (const Path &path : paths) {
         path_to_trace(path, rs, banded, lower_diag, rows);
-        list->traces.push_back(rows);
+        list.traces.push_back(rows);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Single pair, low latency.  A call of align_optimal / align_banded on one pair is dominated by
+// the trips around the kernel, not by the kernel: this path keeps one stream, one page-locked
+// staging buffer each way and its device buffers per host thread, sends parameters, offsets,
+// matrix and both sequences in ONE host-to-device copy, launches fill (+ traceback) and reads
+// score, start and steps back in ONE device-to-host copy.  Codes are validated on the host (a
+// few hundred bytes).  Returns 1 when the pair must take the general batch path instead (sums
+// that could wrap, tables beyond the cached buffers' limit).
+// ---------------------------------------------------------------------------------------
+struct PairCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *d_dirs = nullptr, *h_dirs = nullptr;
+    size_t h_in_cap = 0, h_out_cap = 0, d_in_cap = 0, d_out_cap = 0, d_dirs_cap = 0, h_dirs_cap = 0;
+    DevBuf bnd;
+    void release() {
+        if (stream) cudaStreamDestroy(stream);
+        if (h_in) cudaFreeHost(h_in);
+        if (h_out) cudaFreeHost(h_out);
+        if (h_dirs) cudaFreeHost(h_dirs);
+        if (d_in) cudaFree(d_in);
+        if (d_out) cudaFree(d_out);
+        if (d_dirs) cudaFree(d_dirs);
+        bnd.release();
+        cudaGetLastError();
+        *this = PairCtx();
+    }
+    ~PairCtx() {
+        // at thread / process exit the runtime may be gone already: errors are ignored
+        if (device >= 0) { int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess) { cudaSetDevice(device); release(); if (cur >= 0) cudaSetDevice(cur); } }
+        cudaGetLastError();
+    }
+    PairCtx() = default;
+    PairCtx(const PairCtx &) = delete;
+    PairCtx &operator=(PairCtx &&o) {
+        device = o.device; stream = o.stream; h_in = o.h_in; h_out = o.h_out; d_in = o.d_in; d_out = o.d_out;
+        d_dirs = o.d_dirs; h_dirs = o.h_dirs; h_in_cap = o.h_in_cap; h_out_cap = o.h_out_cap; d_in_cap = o.d_in_cap;
+        d_out_cap = o.d_out_cap; d_dirs_cap = o.d_dirs_cap; h_dirs_cap = o.h_dirs_cap;
+        return *this;
+    }
+};
+static thread_local PairCtx g_pair_ctx;
+
+template <bool HOST>
+static cudaError_t pair_ensure(void **ptr, size_t *cap, size_t need) {
+    if (*cap >= need) return cudaSuccess;
+    if (*ptr) { if (HOST) cudaFreeHost(*ptr); else cudaFree(*ptr); }
+    *ptr = nullptr; *cap = 0;
+    const size_t want = std::max<size_t>(need + need / 2, 64 * 1024);
+    cudaError_t e = HOST ? cudaHostAlloc(ptr, want, cudaHostAllocDefault) : cudaMalloc(ptr, want);
+    if (e == cudaSuccess) *cap = want;
+    return e;
+}
+
+static const int64_t kPairTableLimit = 4ll << 30;   // direction bytes the cached buffers may hold
+
+static int align_pair_fast(const BtParams &P, const void *code1, int64_t len1, const void *code2, int64_t len2,
+                           const int32_t *matrix, int64_t lower_diag, int64_t upper_diag, int32_t score_only,
+                           int64_t max_number, int32_t *score_out, BtTraceList **traces_out) {
+    if (len1 < 0 || len2 < 0 || len1 > INT32_MAX / 2 - 2 || len2 > INT32_MAX / 2 - 2) return 1;
+    if (P.use_matrix && !matrix) return 1;
+    const bool banded = P.banded != 0;
+    const int64_t W = upper_diag - lower_diag + 1;
+    if (banded && (W < 1 || lower_diag < -len1 || upper_diag > len2)) return 1;   // the batch path reports it
+    // scoring range: the closed forms of the first row / column need sums that cannot wrap
+    int32_t mn = 0, mx = 0;
+    if (P.use_matrix) {
+        const int64_t cnt = (int64_t)P.n_rows * P.n_cols;
+        mn = mx = matrix[0];
+        for (int64_t k = 1; k < cnt; k++) { mn = std::min(mn, matrix[k]); mx = std::max(mx, matrix[k]); }
+    } else {
+        mn = std::min(P.match_score, P.mismatch_score); mx = std::max(P.match_score, P.mismatch_score);
+    }
+    const int64_t step = std::max<int64_t>({std::abs((int64_t)mn), std::abs((int64_t)mx), std::abs((int64_t)P.gap_open),
+                                            std::abs((int64_t)P.gap_ext)});
+    if (step * (len1 + len2 + 4) >= (1ll << 30)) return 1;
+    if (const char *forced = getenv("B200ALIGN_GENERAL")) { if (strcmp(forced, "antidiag") == 0) return 1; }
+    const int64_t rs = table_stride(1, banded ? W + 2 : len2 + 1);
+    const int64_t table = (len1 + 1) * rs;
+    if (!score_only && table > kPairTableLimit) return 1;
+    if (bt_device_count() <= 0) return fail(BT_ERR_CUDA, "no CUDA device available (libb200align has no CPU fallback)");
+    // codes outside the matrix: the reference would panic (scoring.rs:63)
+    const int cb = P.code_bytes;
+    if (P.use_matrix) {
+        auto bad = [cb](const void *c, int64_t n, uint64_t limit) {
+            for (int64_t k = 0; k < n; k++) {
+                uint64_t v;
+                switch (cb) {
+                case 1: v = ((const uint8_t *)c)[k]; break;
+                case 2: v = ((const uint16_t *)c)[k]; break;
+                case 4: v = ((const uint32_t *)c)[k]; break;
+                default: v = ((const uint64_t *)c)[k]; break;
+                }
+                if (v >= limit) return true;
+            }
+            return false;
+        };
+        if (bad(code1, len1, (uint64_t)P.n_rows) || bad(code2, len2, (uint64_t)P.n_cols))
+            return fail(BT_ERR_INVALID_CODE, "a sequence code is outside the substitution matrix");
+    }
+
+    PairCtx &C = g_pair_ctx;
+    const int dev = bt_get_device();
+    if (C.device != dev) {
+        if (C.device >= 0) { DeviceGuard g(C.device); C.release(); }
+        C.device = dev;
+        CUDA_TRY(cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking));
+    }
+    cudaStream_t s = C.stream;
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    // ---- input block: 8 int64 (offsets, band, table offsets) | matrix | codes1 | codes2
+    const size_t mat_bytes = P.use_matrix ? (size_t)P.n_rows * P.n_cols * 4 : 0;
+    const size_t in_mat = 64, in_c1 = in_mat + up16(mat_bytes), in_c2 = in_c1 + up16((size_t)len1 * cb);
+    const size_t in_bytes = in_c2 + up16((size_t)len2 * cb);
+    // ---- output block: results (64 bytes) | step bytes | end candidates of a band
+    const size_t out_ops = 64, out_cand = out_ops + up16((size_t)(len1 + len2));
+    const size_t out_bytes = out_cand + (banded ? (size_t)(3 * (W + 2)) * 4 : 0);
+    CUDA_TRY(pair_ensure<true>(&C.h_in, &C.h_in_cap, in_bytes));
+    CUDA_TRY(pair_ensure<false>(&C.d_in, &C.d_in_cap, in_bytes));
+    CUDA_TRY(pair_ensure<true>(&C.h_out, &C.h_out_cap, out_bytes));
+    CUDA_TRY(pair_ensure<false>(&C.d_out, &C.d_out_cap, out_bytes));
+    if (!score_only) CUDA_TRY(pair_ensure<false>(&C.d_dirs, &C.d_dirs_cap, (size_t)table));
+    {
+        int64_t *hdr = (int64_t *)C.h_in;
+        hdr[0] = 0; hdr[1] = len1; hdr[2] = 0; hdr[3] = len2; hdr[4] = lower_diag; hdr[5] = upper_diag; hdr[6] = 0; hdr[7] = 0;
+        if (mat_bytes) memcpy((char *)C.h_in + in_mat, matrix, mat_bytes);
+        if (len1) memcpy((char *)C.h_in + in_c1, code1, (size_t)len1 * cb);
+        if (len2) memcpy((char *)C.h_in + in_c2, code2, (size_t)len2 * cb);
+    }
+    CUDA_TRY(cudaMemcpyAsync(C.d_in, C.h_in, in_bytes, cudaMemcpyHostToDevice, s));
+
+    DevParams D{};
+    D.affine = P.affine; D.local = P.local; D.terminal = banded ? 1 : P.terminal_penalty;
+    D.use_matrix = P.use_matrix; D.banded = P.banded; D.score_only = score_only;
+    D.gap_open = P.gap_open; D.gap_ext = P.affine ? P.gap_ext : P.gap_open;
+    D.match = P.match_score; D.mismatch = P.mismatch_score;
+    D.neg_inf = reference_neg_inf(P, mn);
+    D.n_rows = P.n_rows; D.n_cols = P.n_cols; D.code_bytes = P.code_bytes;
+    D.dir_pad = 1;
+    char *din = (char *)C.d_in, *dout = (char *)C.d_out;
+    BatchView V{};
+    V.codes1 = din + in_c1; V.codes2 = din + in_c2;
+    V.map.off1 = (const int64_t *)din; V.map.off2 = (const int64_t *)din + 2;
+    V.bands = banded ? (const int64_t *)din + 4 : nullptr;
+    V.matrix = P.use_matrix ? (const int32_t *)(din + in_mat) : nullptr;
+    V.dirs = (uint8_t *)C.d_dirs;
+    V.dir_off = (const int64_t *)din + 6;
+    V.cand = (int32_t *)(dout + out_cand);
+    V.cand_off = (const int64_t *)din + 7;
+    V.score = (int32_t *)dout; V.start_state = (int32_t *)(dout + 4); V.start_idx = (int64_t *)(dout + 8);
+    V.end_vals = (int32_t *)(dout + 16); V.trace_len = (int64_t *)(dout + 32); V.first = (int32_t *)(dout + 40);
+    V.ops = (uint8_t *)(dout + out_ops);
+    V.pair_begin = 0; V.pair_end = 1;
+    const bool first_only = max_number == 1;
+    auto fill = [&]() -> int {
+        if (!score_only) CUDA_TRY(cudaMemsetAsync(C.d_dirs, 0, (size_t)table, s));
+        return wavefront_launch(P, D, V, 0, 1, (int)len1, (int)len2, C.bnd, s, nullptr);
+    };
+    int st = fill();
+    if (st) return st;
+    const char *hout = (const char *)C.h_out;
+    if (score_only || first_only) {
+        size_t back = 64;
+        if (first_only && !score_only) {
+            CUDA_TRY(dispatch_general_traceback(D, V, 1, s));
+            back = out_ops + (size_t)(len1 + len2);
+        }
+        CUDA_TRY(cudaMemcpyAsync(C.h_out, C.d_out, back, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        *score_out = *(const int32_t *)hout;
+        if (score_only) return BT_OK;
+        std::unique_ptr<BtTraceList> list(new BtTraceList());
+        const int64_t len = *(const int64_t *)(hout + 32);
+        const int32_t *first = (const int32_t *)(hout + 40);
+        std::vector<int64_t> rows((size_t)(2 * len));
+        const int64_t nrows = expand_ops(len, first[0], first[1], (const uint8_t *)hout + out_ops, banded, lower_diag, rows.data());
+        rows.resize((size_t)(2 * nrows));
+        list->traces.push_back(std::move(rows));
+        *traces_out = list.release();
+        return BT_OK;
+    }
+    // ---- co-optimal enumeration: the whole direction table comes back
+    int32_t score = 0;
+    if (P.local) {
+        // the optimum first, then a second fill that tags every cell holding it (pairwise.rs:536-551)
+        CUDA_TRY(cudaMemcpyAsync(C.h_out, C.d_out, 64, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        score = *(const int32_t *)hout;
+        D.mark = 1; D.mark_value = score;
+        st = fill();
+        if (st) return st;
+    }
+    CUDA_TRY(pair_ensure<true>(&C.h_dirs, &C.h_dirs_cap, (size_t)table));
+    CUDA_TRY(cudaMemcpyAsync(C.h_dirs, C.d_dirs, (size_t)table, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(C.h_out, C.d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    score = *(const int32_t *)hout;
+    *score_out = score;
+    std::unique_ptr<BtTraceList> list(new BtTraceList());
+    enumerate_traces(P, (const uint8_t *)C.h_dirs, (const int32_t *)(hout + out_cand), (const int32_t *)(hout + 16), score,
+                     len1, len2, lower_diag, upper_diag, rs, max_number, *list);
+    *traces_out = list.release();
+    return BT_OK;
+}
+
+extern "C" int bt_align_pair(const BtParams *params, const void *code1, int64_t len1, const void *code2,
+                             int64_t len2, const int32_t *matrix, int64_t lower_diag, int64_t upper_diag,
+                             int32_t score_only, int64_t max_number, int32_t *score_out,
+                             BtTraceList **traces_out) {
+    if (!score_out) return fail(BT_ERR_INVALID_ARG, "score_out is NULL");
+    if (traces_out) *traces_out = nullptr;
+    score_only = score_only ? 1 : 0;
+    if (!score_only && !traces_out) return fail(BT_ERR_INVALID_ARG, "traces_out is NULL");
+    if (max_number < 1) return fail(BT_ERR_INVALID_ARG, "Maximum number of returned alignments must be at least 1");
+    {
+        int stc = check_params(params);
+        if (stc) return stc;
+        const int fast = align_pair_fast(*params, code1, len1, code2, len2, matrix, lower_diag, upper_diag, score_only,
+                                         max_number, score_out, traces_out);
+        if (fast != 1) return fast;
+    }
+    const int64_t off1[2] = {0, len1}, off2[2] = {0, len2};
+    const int64_t band[2] = {lower_diag, upper_diag};
+    // the general batch path (anti-diagonal kernel where sums could wrap, chunked tables)
+    BtParams P = *params;
+    BtBatch *raw = nullptr;
+    int st = batch_create_impl(&P, code1, off1, 1, code2, off2, 1, nullptr, nullptr, 1, matrix,
+                               P.banded ? band : nullptr, score_only, true, &raw);
+    if (st) return st;
+    std::unique_ptr<BtBatch> b(raw);
+    const bool first_only = (max_number == 1);
+    b->phase_used = 0;
+    st = run_general(b.get(), first_only);
+    if (st) return st;
+    b->ran = true;
+    int32_t score = 0;
+    CUDA_TRY(cudaMemcpyAsync(&score, b->score.ptr, 4, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    *score_out = score;
+    if (score_only) return BT_OK;
+
+    std::unique_ptr<BtTraceList> list(new BtTraceList());
+    const bool banded = P.banded != 0;
+    const int64_t W = upper_diag - lower_diag + 1;
+    const int64_t rs = table_stride(b->D.dir_pad, banded ? W + 2 : len2 + 1);
+    if (first_only) {
+        int64_t len = 0; int32_t first[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(&len, b->trace_len.ptr, 8, cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaMemcpyAsync(first, b->first.ptr, 8, cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        std::vector<uint8_t> ops((size_t)std::max<int64_t>(len, 1));
+        if (len > 0) CUDA_TRY(cudaMemcpy(ops.data(), b->ops.ptr, (size_t)len, cudaMemcpyDeviceToHost));
+        std::vector<int64_t> rows((size_t)(2 * len));
+        int64_t nrows = expand_ops(len, first[0], first[1], ops.data(), banded, lower_diag, rows.data());
+        rows.resize((size_t)(2 * nrows));
+        list->traces.push_back(std::move(rows));
+        *traces_out = list.release();
+        return BT_OK;
+    }
+
+    // ---- co-optimal enumeration on the host over the direction table ------------------
+    if (P.local) {
+        // second pass tags every cell whose M equals the optimum (pairwise.rs:536-551)
+        b->D.mark = 1; b->D.mark_value = score;
+        b->phase_used = 0;
+        st = run_general(b.get(), false);
+        if (st) return st;
+    }
+    const int64_t table = (len1 + 1) * rs;
+    std::vector<uint8_t> dir((size_t)table);
+    CUDA_TRY(cudaMemcpyAsync(dir.data(), b->dirs.ptr, (size_t)table, cudaMemcpyDeviceToHost, b->stream));
+    std::vector<int32_t> cand;
+    int32_t endv[3] = {0, 0, 0};
+    if (banded && !P.local) {
+        cand.resize((size_t)(3 * (W + 2)));
+        CUDA_TRY(cudaMemcpyAsync(cand.data(), b->cand.ptr, cand.size() * 4, cudaMemcpyDeviceToHost, b->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(endv, b->end_vals.ptr, 12, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    enumerate_traces(P, dir.data(), cand.data(), endv, score, len1, len2, lower_diag, upper_diag, rs, max_number, *list);
     *traces_out = list.release();
     return BT_OK;
 }

@@ -25,7 +25,13 @@ struct DevParams {
     int32_t mark_value;
     int matrix_in_smem;  // matrix staged in shared memory
     int stats;           // traceback emits GapStats (in `first`) instead of step bytes
+    int dir_pad;         // direction tables have their row stride rounded up to 16 (wavefront kernel)
 };
+
+// row stride of a direction table with `cols` columns
+__host__ __device__ __forceinline__ int64_t table_stride(int dir_pad, int64_t cols) {
+    return dir_pad ? (cols + 15) & ~(int64_t)15 : cols;
+}
 
 // Which sequences pair p aligns.  off1/off2 are the offsets of two sequence pools; idx1/idx2
 // map a pair to its sequences (nullptr = identity: pair p aligns sequence p of either pool,

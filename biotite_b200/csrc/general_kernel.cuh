@@ -324,8 +324,8 @@ __global__ void general_traceback_kernel(const DevParams P, const BatchView V) {
     const int64_t p = V.pair_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= V.pair_end) return;
     const int64_t n = V.map.len1(p), m = V.map.len2(p);
-    int64_t rs = m + 1;
-    if (BANDED) rs = V.bands[2 * p + 1] - V.bands[2 * p] + 3;
+    int64_t rs = table_stride(P.dir_pad, m + 1);
+    if (BANDED) rs = table_stride(P.dir_pad, V.bands[2 * p + 1] - V.bands[2 * p] + 3);
     const int64_t step[3] = {BANDED ? -rs : -(rs + 1), -1, BANDED ? -rs + 1 : -rs};
     const uint8_t *dir = V.dirs + V.dir_off[p];
     uint8_t *ops = P.stats ? nullptr : V.ops + V.map.ops(p);

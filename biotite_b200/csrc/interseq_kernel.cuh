@@ -105,6 +105,7 @@ struct SlotBuffers {
 struct InterseqPlan {
     int64_t n_pairs = 0, n_groups = 0;
     int64_t max_dir_words = 0, max_rowbuf = 0, max_rowcodes = 0, max_colcodes = 0;
+    int warps_per_sm = IS_WARPS_PER_SM;   // resident warps of the fill kernel that will run (window sizing)
     InterseqConst C{};
     std::vector<int32_t> order;        // group slot -> pair id (-1 = padding), window by window
     std::vector<WarpDesc> desc;        // offsets are relative to the window's scratch
@@ -980,19 +981,19 @@ namespace bt {
 
 // Groups per wave of the affine fill kernel (one warp per block, IS_WARPS_PER_SM blocks per SM):
 // windows are whole numbers of waves, so that they lose little to partial waves.
-inline int64_t interseq_wave_groups() {
+inline int64_t interseq_wave_groups(int warps_per_sm = IS_WARPS_PER_SM) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
         cudaGetLastError();
         sms = 148;   // B200; only reached without a device (bt_debug_plan in the CPU tests)
     }
-    return (int64_t)sms * IS_WARPS_PER_SM;
+    return (int64_t)sms * warps_per_sm;
 }
 
 // Pairs per window for a batch of n_pairs when a window should span `waves` full waves.
-inline int64_t interseq_pairs_per_window(int64_t n_pairs, int waves) {
-    int64_t win_pairs = interseq_wave_groups() * waves * 64;
+inline int64_t interseq_pairs_per_window(int64_t n_pairs, int waves, int warps_per_sm = IS_WARPS_PER_SM) {
+    int64_t win_pairs = interseq_wave_groups(warps_per_sm) * waves * 64;
     if (const char *g = getenv("B200ALIGN_WIN_GROUPS")) win_pairs = std::max<int64_t>(64, atoll(g) * 64);
     const int64_t n_windows = std::max<int64_t>(1, (n_pairs + win_pairs - 1) / win_pairs);
     return ((n_pairs + n_windows - 1) / n_windows + 63) / 64 * 64;  // balanced windows
@@ -1228,6 +1229,9 @@ inline void interseq_enable_tags(InterseqPlan &plan, const BtParams &P, const Pa
                                  int32_t max_score) {
     if (plan.C.score_only || !interseq_tag_eligible(P, scan, min_score, max_score)) return;
     plan.C.dir_layout = 1;
+    // persistent tag kernel: windows without the rare letters (B, Z, X, * of the protein alphabet)
+    // are the rule, size the waves for them
+    plan.warps_per_sm = interseq_tag_warps(std::min<int>(P.n_cols, TG_SMALL_LETTERS));
     plan.C.neg = -8192 - plan.C.gap_open - plan.C.gap_ext - std::min(min_score, 0);
 }
 
@@ -1237,8 +1241,10 @@ inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const Pair
                                int score_only, int32_t min_score, int32_t max_score, int64_t *cells_out,
                                int waves_per_window) {
     score_only = interseq_setup(plan, P, n_pairs, score_only, min_score);
+    const PairScan batch_scan = interseq_scan(hm, n_pairs);
+    interseq_enable_tags(plan, P, batch_scan, min_score, max_score);
 
-    const int64_t per_window = interseq_pairs_per_window(n_pairs, waves_per_window);
+    const int64_t per_window = interseq_pairs_per_window(n_pairs, waves_per_window, plan.warps_per_sm);
     const int64_t groups_per_window = per_window / 64;
     const int dwpl = P.affine ? 4 : 2;
     // The whole batch is resident: sort it globally by (len1, len2), form the groups of 64, order
@@ -1250,8 +1256,7 @@ inline void interseq_plan_host(InterseqPlan &plan, const BtParams &P, const Pair
     // stragglers cannot dominate a window and the batch-wide sort buys nothing
     bool uniform = false;
     {
-        const PairScan scan = interseq_scan(hm, n_pairs);
-        interseq_enable_tags(plan, P, scan, min_score, max_score);
+        const PairScan &scan = batch_scan;
         uniform = scan.max_pair * (double)n_pairs <= 4.0 * scan.total;
         if (const char *f = getenv("B200ALIGN_SORT")) uniform = strcmp(f, "window") == 0;
     }
@@ -1544,17 +1549,18 @@ struct StreamingPlanner {
 
     StreamingPlanner(InterseqPlan &p, const PairMap &map, int64_t n, int waves, bool affine)
         : plan(p), hm(map), n_pairs(n), no_dirs(p.C.score_only), dir_words_per_lane(affine ? 4 : 2) {
-        per_window = interseq_pairs_per_window(n_pairs, waves);
-        // A short first window lets the kernels start while most of the input is still on its
-        // way, a short last window shortens the final device-to-host copy nobody overlaps.
+        per_window = interseq_pairs_per_window(n_pairs, waves, p.warps_per_sm);
+        // Windows are whole waves of the fill kernel (a partial wave leaves warps idle for the
+        // 3 - 4 ms a group takes).  The first window is a single wave, so that the kernels start
+        // while most of the input is still on its way; the rest is cut into equally many waves.
         bounds.push_back(0);
-        if (n_pairs > 3 * per_window) {
-            const int64_t edge = (per_window / 4 + 63) / 64 * 64;
-            bounds.push_back(edge);
-            const int64_t inner = n_pairs - 2 * edge, k = std::max<int64_t>(1, (inner + per_window - 1) / per_window);
-            const int64_t step = ((inner + k - 1) / k + 63) / 64 * 64;
-            for (int64_t q = 1; q < k; q++) bounds.push_back(edge + q * step);
-            bounds.push_back(n_pairs - edge);
+        const int64_t wave = interseq_wave_groups(p.warps_per_sm) * 64;
+        if (n_pairs > 2 * wave && !getenv("B200ALIGN_WIN_GROUPS")) {
+            bounds.push_back(wave);
+            const int64_t rest = n_pairs - wave;
+            const int64_t k = std::max<int64_t>(1, (rest + waves * wave - 1) / (waves * wave));
+            const int64_t per = ((rest + k - 1) / k + wave - 1) / wave * wave;
+            for (int64_t q = 1; q < k && wave + q * per < n_pairs; q++) bounds.push_back(wave + q * per);
         } else {
             for (int64_t q = per_window; q < n_pairs; q += per_window) bounds.push_back(q);
         }
