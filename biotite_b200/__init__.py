@@ -37,6 +37,7 @@ from .batch import (
     PackedSequences,
     align_batch_arrays,
     compact_out,
+    align_batch_multi,
     align_indexed_batch,
     all_vs_all_scores,
     feng_doolittle_distances,

@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "bt_tracelist_free", "bt_batch_create", "bt_batch_create_indexed", "bt_batch_ops_bytes", "bt_batch_run", "bt_batch_fetch_scores",
     "bt_batch_fetch_traces", "bt_batch_fetch_cigar", "bt_batch_fetch_gapped", "bt_batch_timings", "bt_microbench", "bt_batch_cells", "bt_batch_launches", "bt_batch_kernel",
     "bt_batch_destroy", "bt_align_batch", "bt_xdrop_regions", "bt_debug_plan", "bt_expand_traces", "bt_pinned_alloc",
-    "bt_pinned_free", "bt_pool_trim", "bt_ops2_capacity", "bt_align_batch_compact", "bt_expand_traces2",
+    "bt_pinned_free", "bt_pool_trim", "bt_ops2_capacity", "bt_align_batch_compact", "bt_expand_traces2", "bt_align_batch_multi",
 ]
 
 
@@ -117,6 +117,9 @@ def load():
         ctypes.POINTER(BtParams), _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp,
         ctypes.POINTER(_i64)]
     lib.bt_expand_traces2.argtypes = [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.bt_align_batch_multi.argtypes = [
+        _vp, _i32, ctypes.POINTER(BtParams), _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp,
+        ctypes.POINTER(_i64), _vp]
     lib.bt_xdrop_regions.argtypes = [
         ctypes.POINTER(BtParams), _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i64, _i32, _i64, _vp, _vp,
         ctypes.POINTER(_vp)]

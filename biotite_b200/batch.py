@@ -29,6 +29,7 @@ __all__ = [
     "BatchResult",
     "align_batch_arrays",
     "compact_out",
+    "align_batch_multi",
     "align_indexed_batch",
     "all_vs_all_scores",
     "feng_doolittle_distances",
@@ -280,7 +281,7 @@ def _check_out(name, array, dtype, shape):
         raise ValueError(f"out: `{name}` must be a writeable C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}")
 
 
-def compact_out(off1, off2, pinned=True):
+def compact_out(off1, off2, pinned=True, n_devices=1):
     """
     Result arrays ``(scores, trace_len, first, ops2, ops2_off)`` for the compact form of
     :func:`align_batch_arrays`, page-locked by default so that the device-to-host copies of a
@@ -290,7 +291,7 @@ def compact_out(off1, off2, pinned=True):
     off1 = np.ascontiguousarray(off1, dtype=np.int64)
     off2 = np.ascontiguousarray(off2, dtype=np.int64)
     n = len(off1) - 1
-    cap = int(lib.bt_ops2_capacity(_cabi.ptr(off1), _cabi.ptr(off2), n))
+    cap = int(lib.bt_ops2_capacity(_cabi.ptr(off1), _cabi.ptr(off2), n)) + (16 * int(n_devices) if int(n_devices) > 1 else 0)
     make = _cabi.pinned_empty if pinned else (lambda shape, dtype: np.empty(shape, dtype))
     return (make((n,), np.int32), make((n,), np.int32), make((n, 2), np.int32), make((cap,), np.uint32),
             make((n,), np.int64))
@@ -366,6 +367,61 @@ def align_batch_arrays(codes1, off1, codes2, off2, scoring, gap_penalty, termina
         _cabi.ptr(off2), n, _cabi.ptr(matrix), _cabi.ptr(bands), int(bool(score_only)),
         _cabi.ptr(scores), _cabi.ptr(trace_len), _cabi.ptr(first), _cabi.ptr(ops)))
     return BatchResult(scores, trace_len, first, ops, (off1, off2), bands)
+
+
+def align_batch_multi(codes1, off1, codes2, off2, scoring, gap_penalty, terminal_penalty=True, local=False,
+                      bands=None, score_only=False, devices=None, out=None):
+    """
+    :func:`align_batch_arrays` (compact result form) over several GPUs of the node from this one
+    process (``bt_align_batch_multi``): the pairs are cut into contiguous shards of equal DP cells,
+    one host thread per device, results written straight into disjoint slices of the result arrays.
+    `devices`: list of CUDA device ordinals (default: all).  `out`: arrays from
+    ``compact_out(off1, off2, n_devices=max(2, len(devices)))``.  Returns a :class:`BatchResult` whose
+    ``shards`` attribute holds the first pair of every device's shard.
+    """
+    lib = _cabi.load()
+    dtype = np.promote_types(codes1.dtype, codes2.dtype)
+    codes1 = np.ascontiguousarray(codes1, dtype)
+    codes2 = np.ascontiguousarray(codes2, dtype)
+    off1 = np.ascontiguousarray(off1, dtype=np.int64)
+    off2 = np.ascontiguousarray(off2, dtype=np.int64)
+    if len(off1) != len(off2):
+        raise ValueError("Both sides of the batch must hold the same number of sequences")
+    n = len(off1) - 1
+    bands = None if bands is None else np.ascontiguousarray(bands, dtype=np.int64)
+    if bands is not None and bands.shape != (n, 2):
+        raise ValueError("bands must have shape (n_pairs, 2)")
+    if devices is None:
+        devices = list(range(lib.bt_device_count()))
+    devs = np.ascontiguousarray(devices, dtype=np.int32)
+    params, matrix = _cabi.make_params(scoring, gap_penalty, terminal_penalty, local, bands is not None, dtype)
+    if out is None:
+        out = compact_out(off1, off2, pinned=False, n_devices=max(2, len(devs)))
+    scores, trace_len, first, ops2, ops2_off = out
+    cap = int(lib.bt_ops2_capacity(_cabi.ptr(off1), _cabi.ptr(off2), n)) + 16 * len(devs)
+    _check_out("scores", scores, np.int32, (n,))
+    if not score_only:
+        _check_out("trace_len", trace_len, np.int32, (n,))
+        _check_out("first", first, np.int32, (n, 2))
+        if ops2.dtype != np.uint32 or ops2.ndim != 1 or len(ops2) < cap or not ops2.flags.c_contiguous:
+            raise ValueError(f"out: `ops2` must be a C-contiguous uint32 array of at least {cap} words")
+        _check_out("ops2_off", ops2_off, np.int64, (n,))
+    words = ctypes.c_int64(0)
+    shards = np.zeros(len(devs) + 1, dtype=np.int64)
+    _cabi.check(lib.bt_align_batch_multi(
+        _cabi.ptr(devs), len(devs), ctypes.byref(params), _cabi.ptr(codes1), _cabi.ptr(off1), _cabi.ptr(codes2),
+        _cabi.ptr(off2), n, _cabi.ptr(matrix), _cabi.ptr(bands), int(bool(score_only)), _cabi.ptr(scores),
+        None if score_only else _cabi.ptr(trace_len), None if score_only else _cabi.ptr(first),
+        None if score_only else _cabi.ptr(ops2), len(ops2) if not score_only else 0,
+        None if score_only else _cabi.ptr(ops2_off), ctypes.byref(words), _cabi.ptr(shards)))
+    if score_only:
+        result = BatchResult(scores, None, None, None, np.zeros(0, dtype=np.int64), bands)
+    else:
+        result = BatchResult(scores, trace_len, first, None, ops2_off, bands)
+        result.ops2 = ops2
+        result.ops2_words = int(words.value)
+    result.shards = shards
+    return result
 
 
 class BatchResult:
@@ -556,8 +612,13 @@ def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True,
     source = chunks()
     slot = {}
 
+    device = _cabi.load().bt_get_device()
+
     def prepare_next(done=None):
         try:
+            # a new host thread starts on device 0: take the caller's device
+            if device >= 0:
+                _cabi.check(_cabi.load().bt_set_device(device))
             if done is not None:       # scores of the previous batch -> both triangles
                 a, b, scores = done
                 out[a, b] = scores

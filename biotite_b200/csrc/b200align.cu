@@ -988,7 +988,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     // to the pool, also on the error paths.
     struct Streams {
         cudaStream_t s[2] = {nullptr, nullptr}, h2d = nullptr, d2h = nullptr;
-        std::vector<cudaEvent_t> in_ready, plan_ready, k_done;
+        std::vector<cudaEvent_t> in_ready, plan_ready, k_done, d2h_done;
         ~Streams() {
             for (cudaStream_t x : s) if (x) { cudaStreamSynchronize(x); cudaStreamDestroy(x); }
             if (h2d) { cudaStreamSynchronize(h2d); cudaStreamDestroy(h2d); }
@@ -996,6 +996,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
             for (cudaEvent_t e : in_ready) cudaEventDestroy(e);
             for (cudaEvent_t e : plan_ready) cudaEventDestroy(e);
             for (cudaEvent_t e : k_done) cudaEventDestroy(e);
+            for (cudaEvent_t e : d2h_done) cudaEventDestroy(e);
             cudaGetLastError();
         }
     } st;
@@ -1050,6 +1051,9 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
         st.plan_ready.push_back(e2);
         CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
         st.k_done.push_back(e1);
+        cudaEvent_t e3 = nullptr;
+        CUDA_TRY(cudaEventCreateWithFlags(&e3, cudaEventDisableTiming));
+        st.d2h_done.push_back(e3);
     }
     // the copy engine serves its queue in order: input codes, then group order / descriptors
     // of a window (uploaded as soon as it is planned), then the next window's input codes, ...
@@ -1075,6 +1079,15 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     // results of window w to the host: everything a window returns is a contiguous range of the
     // output arrays.  The compact form waits (on the host) for the window's kernels, because the
     // size of its step words is only known then; by that time the next window is already queued.
+    auto fill_ops2_off = [&](size_t w) {
+        if (!out.ops2_off || !out.trace_len32) return;
+        const Window &win = plan.windows[w];
+        int64_t run = ops2_base(h_off1, h_off2, win.pair_begin);
+        for (int64_t k = win.pair_begin; k < win.pair_end; k++) {
+            out.ops2_off[k] = run;
+            run += ops2_words(out.trace_len32[k]);
+        }
+    };
     auto drain = [&](size_t w) -> int {
         const Window &win = plan.windows[w];
         const int64_t p0 = win.pair_begin, np = win.pair_end - win.pair_begin;
@@ -1110,6 +1123,15 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
             }
         }
         mark(w, 3, r);
+        if (compact) {
+            CUDA_TRY(cudaEventRecord(st.d2h_done[w], r));
+            // first word of every pair of the window BEFORE this one, whose lengths have arrived by
+            // now: the window's base plus the running sum (keeps this pass off the end of the call)
+            if (w > 0) {
+                CUDA_TRY(cudaEventSynchronize(st.d2h_done[w - 1]));
+                fill_ops2_off(w - 1);
+            }
+        }
         if (trace) host_t[w * 3 + 2] = now() - t0;
         return BT_OK;
     };
@@ -1170,16 +1192,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     if (flag) return fail(BT_ERR_INVALID_CODE, "a sequence code is outside the substitution matrix");
     if (compact) {
         if (out.ops2_words) *out.ops2_words = words_end;
-        if (out.ops2_off && out.trace_len32) {
-            // first word of every pair: the window's base plus the running sum inside the window
-            for (const Window &win : plan.windows) {
-                int64_t run = ops2_base(h_off1, h_off2, win.pair_begin);
-                for (int64_t k = win.pair_begin; k < win.pair_end; k++) {
-                    out.ops2_off[k] = run;
-                    run += ops2_words(out.trace_len32[k]);
-                }
-            }
-        }
+        if (!plan.windows.empty()) fill_ops2_off(plan.windows.size() - 1);
     }
     return BT_OK;
 }
@@ -1280,6 +1293,107 @@ extern "C" int bt_align_batch_compact(const BtParams *params, const void *codes1
     out.scores = scores_out; out.trace_len32 = trace_len_out; out.first = first_out;
     out.ops2 = ops2_out; out.ops2_cap = ops2_capacity; out.ops2_off = ops2_off_out; out.ops2_words = ops2_words_out;
     return align_batch_impl(params, codes1, off1, codes2, off2, n_pairs, matrix, bands, score_only, out);
+}
+
+// ---------------------------------------------------------------------------------------
+// One batch over several GPUs of the node, from one process: the pairs
+// are cut into contiguous shards of equal DP cells, one host thread per device runs its shard
+// through the one-shot path (own streams, own pooled buffers) and writes the results straight
+// into disjoint slices of the caller's arrays.  No data-path collective: pairs are independent
+// (pairwise.rs:161 takes one pair).  The step words of shard d start at the input-only bound
+// ops2_base(first pair of d) + 16 d, so the shards cannot overlap.
+// ---------------------------------------------------------------------------------------
+extern "C" int bt_align_batch_multi(const int32_t *devices, int32_t n_devices, const BtParams *params,
+                                    const void *codes1, const int64_t *off1, const void *codes2,
+                                    const int64_t *off2, int64_t n_pairs, const int32_t *matrix,
+                                    const int64_t *bands, int32_t score_only, int32_t *scores_out,
+                                    int32_t *trace_len_out, int32_t *first_out, uint32_t *ops2_out,
+                                    int64_t ops2_capacity, int64_t *ops2_off_out, int64_t *ops2_words_out,
+                                    int64_t *shard_begin_out) {
+    int st = check_params(params);
+    if (st) return st;
+    if (!off1 || !off2 || n_pairs < 0) return fail(BT_ERR_INVALID_ARG, "bad pair offsets");
+    if (score_only != 0 && score_only != 1) return fail(BT_ERR_INVALID_ARG, "score_only must be 0 or 1");
+    const int available = bt_device_count();
+    if (available <= 0) return fail(BT_ERR_CUDA, "no CUDA device available (libb200align has no CPU fallback)");
+    std::vector<int32_t> devs;
+    if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+    else for (int d = 0; d < available; d++) devs.push_back(d);
+    for (int32_t d : devs)
+        if (d < 0 || d >= available) return fail(BT_ERR_INVALID_ARG, "device %d does not exist (%d devices)", d, available);
+    const int nd = (int)devs.size();
+    if (off1[0] != 0 || off2[0] != 0) return fail(BT_ERR_INVALID_ARG, "offsets must start at 0");
+    for (int64_t k = 0; k < n_pairs; k++)
+        if (off1[k + 1] < off1[k] || off2[k + 1] < off2[k]) return fail(BT_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    if (!score_only && ops2_out && ops2_capacity < bt_ops2_capacity(off1, off2, n_pairs) + 16 * nd)
+        return fail(BT_ERR_INVALID_ARG, "ops2 buffer is too small (bt_ops2_capacity + 16 words per device)");
+    // shards of equal DP cells (band: rows x width)
+    std::vector<int64_t> cut((size_t)nd + 1, n_pairs);
+    cut[0] = 0;
+    {
+        double total = 0.0;
+        auto cells = [&](int64_t k) {
+            const double n = (double)(off1[k + 1] - off1[k]), m = (double)(off2[k + 1] - off2[k]);
+            return params->banded && bands ? n * (double)(bands[2 * k + 1] - bands[2 * k] + 1) : n * m;
+        };
+        for (int64_t k = 0; k < n_pairs; k++) total += cells(k);
+        double run = 0.0;
+        int d = 1;
+        for (int64_t k = 0; k < n_pairs && d < nd; k++) {
+            run += cells(k);
+            while (d < nd && run >= total * d / nd) cut[(size_t)d++] = k + 1;
+        }
+    }
+    if (shard_begin_out) for (int d = 0; d <= nd; d++) shard_begin_out[d] = cut[(size_t)d];
+    const size_t cb = (size_t)params->code_bytes;
+    std::vector<int> status((size_t)nd, BT_OK);
+    std::vector<std::string> message((size_t)nd);
+    std::vector<int64_t> words_end((size_t)nd, 0);
+    auto work = [&](int d) {
+        const int64_t p0 = cut[(size_t)d], p1 = cut[(size_t)d + 1], np = p1 - p0;
+        if (np <= 0) return;
+        if (cudaSetDevice(devs[(size_t)d]) != cudaSuccess) {
+            cudaGetLastError();
+            status[(size_t)d] = BT_ERR_CUDA; message[(size_t)d] = "cudaSetDevice failed";
+            return;
+        }
+        // offsets of the shard, rebased to its first pair
+        std::vector<int64_t> o1((size_t)np + 1), o2((size_t)np + 1);
+        for (int64_t k = 0; k <= np; k++) { o1[(size_t)k] = off1[p0 + k] - off1[p0]; o2[(size_t)k] = off2[p0 + k] - off2[p0]; }
+        const int64_t base = ops2_base(off1, off2, p0) + 16 * d;
+        BatchOut out;
+        out.compact = true;
+        out.scores = scores_out ? scores_out + p0 : nullptr;
+        if (!score_only) {
+            out.trace_len32 = trace_len_out ? trace_len_out + p0 : nullptr;
+            out.first = first_out ? first_out + 2 * p0 : nullptr;
+            out.ops2 = ops2_out ? ops2_out + base : nullptr;
+            out.ops2_cap = ops2_base(off1, off2, p1) + 16 * (d + 1) - base;
+            out.ops2_off = ops2_off_out ? ops2_off_out + p0 : nullptr;
+            out.ops2_words = &words_end[(size_t)d];
+        }
+        const int rc = align_batch_impl(params, (const char *)codes1 + (size_t)off1[p0] * cb, o1.data(),
+                                        (const char *)codes2 + (size_t)off2[p0] * cb, o2.data(), np, matrix,
+                                        bands ? bands + 2 * p0 : nullptr, score_only, out);
+        if (rc) { status[(size_t)d] = rc; message[(size_t)d] = g_error; return; }
+        if (out.ops2_off) for (int64_t k = 0; k < np; k++) out.ops2_off[k] += base;   // word index in the caller's array
+        words_end[(size_t)d] += base;
+    };
+    {
+        DeviceGuard keep(bt_get_device() >= 0 ? bt_get_device() : 0);   // the calling thread keeps its device
+        std::vector<std::thread> threads;
+        for (int d = 1; d < nd; d++) threads.emplace_back(work, d);
+        work(0);
+        for (std::thread &t : threads) t.join();
+    }
+    for (int d = 0; d < nd; d++)
+        if (status[(size_t)d]) return fail(status[(size_t)d], "device %d: %s", devs[(size_t)d], message[(size_t)d].c_str());
+    if (ops2_words_out) {
+        int64_t end = 0;
+        for (int64_t w : words_end) end = std::max(end, w);
+        *ops2_words_out = end;
+    }
+    return BT_OK;
 }
 
 extern "C" int bt_expand_traces2(int64_t n_pairs, const int32_t *trace_len, const int32_t *first,

@@ -1207,6 +1207,69 @@ inline void interseq_plan_window(WindowPlan &wp, const PairMap &hm, int64_t w0, 
     }
 }
 
+// Plan of one window of consecutive pairs [w0, w1) for the streaming path: same result as
+// interseq_plan_window (sort by (len1, len2), reversed into groups of 64, groups by descending
+// cost), but the lengths travel with the pair ids as 64-bit records (len1 << 48 | len2 << 32 |
+// id) through two counting passes, so that nothing looks a length up twice: the per-pair
+// look-ups of the offsets were most of the 25 - 65 ns per pair the first version took, and with
+// one process per GPU the host has four cores per rank for it.
+inline void interseq_plan_window_records(WindowPlan &wp, const PairMap &hm, int64_t w0, int64_t w1, int score_only,
+                                         int dir_words_per_lane) {
+    Window &win = wp.win;
+    win.pair_begin = w0; win.pair_end = w1;
+    const int64_t cnt = w1 - w0;
+    const size_t buckets = IS_MAX_LEN + 2;
+    std::unique_ptr<uint64_t[]> rec_a(new uint64_t[(size_t)cnt]), rec_b(new uint64_t[(size_t)cnt]);
+    std::vector<int32_t> hist1(buckets, 0), hist2(buckets, 0);
+    for (int64_t q = 0; q < cnt; q++) {
+        const int64_t n = hm.len1(w0 + q), m = hm.len2(w0 + q);
+        rec_a[(size_t)q] = (uint64_t)n << 48 | (uint64_t)m << 32 | (uint64_t)(uint32_t)(w0 + q);
+        hist1[(size_t)n]++; hist2[(size_t)m]++;
+    }
+    auto exclusive = [&](std::vector<int32_t> &h) { int32_t run = 0; for (int32_t &v : h) { const int32_t c = v; v = run; run += c; } };
+    exclusive(hist1); exclusive(hist2);
+    for (int64_t q = 0; q < cnt; q++) rec_b[(size_t)hist2[(size_t)(rec_a[(size_t)q] >> 32 & 0xffffu)]++] = rec_a[(size_t)q];   // by len2
+    for (int64_t q = 0; q < cnt; q++) rec_a[(size_t)hist1[(size_t)(rec_b[(size_t)q] >> 48)]++] = rec_b[(size_t)q];             // then by len1 (stable)
+    rec_b.reset();
+    // groups of 64 over the descending order, their longest sequences and cost
+    const int64_t groups = (cnt + 63) / 64;
+    std::vector<int64_t> cost((size_t)groups);
+    std::vector<int32_t> perm((size_t)groups), gn((size_t)groups), gm((size_t)groups);
+    for (int64_t g = 0; g < groups; g++) {
+        int32_t nmax = 1, mmax = 1;
+        const int64_t s1 = std::min<int64_t>(cnt, g * 64 + 64);
+        for (int64_t slot = g * 64; slot < s1; slot++) {
+            const uint64_t r = rec_a[(size_t)(cnt - 1 - slot)];
+            nmax = std::max<int32_t>(nmax, (int32_t)(r >> 48)); mmax = std::max<int32_t>(mmax, (int32_t)(r >> 32 & 0xffffu));
+        }
+        gn[(size_t)g] = nmax; gm[(size_t)g] = mmax;
+        cost[(size_t)g] = (int64_t)(nmax + IS_R - 1) / IS_R * mmax;
+        perm[(size_t)g] = (int32_t)g;
+    }
+    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return cost[(size_t)a] > cost[(size_t)b]; });
+    wp.order.assign((size_t)groups * 64, -1);
+    wp.desc.resize((size_t)groups);
+    for (int64_t g = 0; g < groups; g++) {
+        const int64_t src = perm[(size_t)g];
+        const int64_t s1 = std::min<int64_t>(cnt, src * 64 + 64);
+        int64_t q = g * 64;
+        for (int64_t slot = src * 64; slot < s1; slot++, q++) {
+            const uint64_t r = rec_a[(size_t)(cnt - 1 - slot)];
+            wp.order[(size_t)q] = (int32_t)(uint32_t)r;
+            wp.cells += (int64_t)(r >> 48) * (int64_t)(r >> 32 & 0xffffu);
+        }
+        const int nmax = gn[(size_t)src], mmax = gm[(size_t)src];
+        WarpDesc &d = wp.desc[(size_t)g];
+        d.nmax = nmax; d.mmax = mmax; d.stripes = (nmax + IS_R - 1) / IS_R; d.pad = 0;
+        d.dir_off = win.dir_words; d.rowbuf_off = win.rowbuf_entries;
+        d.rowcode_off = win.rowcodes; d.colcode_off = win.colcodes;
+        if (!score_only) win.dir_words += (int64_t)d.stripes * mmax * 32 * dir_words_per_lane;
+        win.rowbuf_entries += (int64_t)mmax * 32;
+        win.rowcodes += (int64_t)d.stripes * IS_R * 32;
+        win.colcodes += (int64_t)mmax * 32;
+    }
+}
+
 // Kernel constants of a plan; returns the "no direction nibbles" flag of the trace mode
 // (0 = traces, 1 = score only, 2 = statistics).
 inline int interseq_setup(InterseqPlan &plan, const BtParams &P, int64_t n_pairs, int trace_mode, int32_t min_score) {
@@ -1617,7 +1680,7 @@ struct StreamingPlanner {
                     if (w >= n_windows) break;
                     const int64_t w0 = bounds[(size_t)w], w1 = bounds[(size_t)w + 1];
                     WindowPlan &wp = wps[(size_t)w];
-                    interseq_plan_window(wp, hm, w0, w1, no_dirs, dir_words_per_lane);
+                    interseq_plan_window_records(wp, hm, w0, w1, no_dirs, dir_words_per_lane);
                     memcpy(stage_order() + group_begin[(size_t)w] * 64, wp.order.data(), wp.order.size() * 4);
                     memcpy(stage_desc() + group_begin[(size_t)w], wp.desc.data(), wp.desc.size() * sizeof(WarpDesc));
                     ready[(size_t)w].store(1, std::memory_order_release);

@@ -1,9 +1,12 @@
 """
-Multi-GPU use of the batch path: one process per GPU (``torchrun``), the pairs of a batch
+Multi-GPU use of the batch path with one process per GPU (``torchrun``): the pairs of a batch
 are split into contiguous shards of equal DP work, every rank aligns its shard on its own
-device, and the only communication is the final gather of scores and compact traces.
-Pairs are independent (the reference's ``align_optimal_generic`` takes one pair,
-``src/rust/sequence/align/pairwise.rs:161``), so there is no collective on the data path.
+device, and the only communication is the final gather of scores and compact traces - a
+``torch.distributed.gather`` of plain int32 / uint32 tensors (NCCL over NVLink when the group's
+backend is NCCL, gloo on the CPU), no pickling.  Pairs are independent (the reference's
+``align_optimal_generic`` takes one pair, ``src/rust/sequence/align/pairwise.rs:161``), so there
+is no collective on the data path.  Within ONE process use ``align_batch_multi`` instead
+(``bt_align_batch_multi``: one host thread per device, results straight into the caller's arrays).
 """
 
 from __future__ import annotations
@@ -14,7 +17,7 @@ import numpy as np
 
 from .batch import BatchResult, align_batch_arrays
 
-__all__ = ["shard_bounds", "align_batch_sharded", "bind_to_gpu_numa_node"]
+__all__ = ["shard_bounds", "gather_arrays", "align_batch_sharded", "bind_to_gpu_numa_node"]
 
 
 def shard_bounds(off1, off2, world_size):
@@ -33,13 +36,44 @@ def shard_bounds(off1, off2, world_size):
     return np.maximum.accumulate(bounds)
 
 
+def gather_arrays(array, dst=0, group=None):
+    """
+    Gather one 1-D NumPy array per rank on rank `dst` (other ranks get ``None``): the lengths
+    first, then the payload padded to the longest one, as tensors on the device the group's
+    backend moves (CUDA for NCCL, CPU for gloo).  Returns the list of per-rank arrays.
+    """
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    array = np.ascontiguousarray(array).reshape(-1)
+    dtype = array.dtype
+    # torch has no uint32 arithmetic, but a gather only moves bytes: reinterpret as int32
+    wire = array.view(np.int32) if dtype == np.uint32 else array
+    size = torch.tensor([len(wire)], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, size, group=group)
+    sizes = [int(t.item()) for t in sizes]
+    longest = max(sizes) if sizes else 0
+    padded = torch.zeros(max(longest, 1), dtype=torch.from_numpy(wire[:0]).dtype, device=device)
+    if len(wire):
+        padded[:len(wire)] = torch.from_numpy(wire).to(device)
+    bucket = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bucket, dst=dst, group=group)
+    if rank != dst:
+        return None
+    parts = [t[:n].cpu().numpy() for t, n in zip(bucket, sizes)]
+    return [p.view(np.uint32) if dtype == np.uint32 else p for p in parts]
+
+
 def align_batch_sharded(codes1, off1, codes2, off2, scoring, gap_penalty, terminal_penalty=True,
                         local=False, score_only=False, group=None, compute=None, dst=0):
     """
     Collective call: every rank passes the same batch (or at least its own shard's codes),
     aligns shard ``rank`` and rank `dst` receives the :class:`BatchResult` of the whole
-    batch (other ranks get ``None``).  `compute` defaults to the GPU batch entry point; the
-    CPU test-suite injects the oracle here.
+    batch (other ranks get ``None``).  `compute` defaults to the GPU batch entry point in its
+    compact result form; the CPU test-suite injects a stand-in with the same result layout.
     """
     import torch.distributed as dist
 
@@ -56,23 +90,47 @@ def align_batch_sharded(codes1, off1, codes2, off2, scoring, gap_penalty, termin
         from . import _cabi
         lib = _cabi.load()
         _cabi.check(lib.bt_set_device(int(os.environ.get("LOCAL_RANK", rank))))
-        compute = align_batch_arrays
-    local_result = compute(l_codes1, l_off1, l_codes2, l_off2, scoring, gap_penalty,
-                           terminal_penalty, local, None, score_only)
-    payload = (lo, hi, local_result.scores, local_result.trace_len, local_result.first,
-               local_result.ops)
-    gathered = [None] * world if rank == dst else None
-    dist.gather_object(payload, gathered, dst=dst, group=group)
+
+        def compute(*args):
+            return align_batch_arrays(*args, compact=True)
+    part = compute(l_codes1, l_off1, l_codes2, l_off2, scoring, gap_penalty, terminal_penalty, local, None,
+                   score_only)
+    scores = gather_arrays(part.scores.astype(np.int32, copy=False), dst, group)
+    if score_only:
+        return None if rank != dst else BatchResult(np.concatenate(scores), None, None, None, np.zeros(0, dtype=np.int64))
+    # compact traces: int32 lengths, first cells and the used 2-bit step words of every shard
+    if part.ops2 is None:
+        # byte form (injected compute): pack it like the device does, 16 steps per word
+        words_per_pair = (part.trace_len.astype(np.int64) + 15) // 16
+        ops2_off = np.concatenate(([0], np.cumsum(words_per_pair)[:-1])).astype(np.int64)
+        ops2 = np.zeros(int(words_per_pair.sum()), dtype=np.uint32)
+        ops_off = part.ops_off
+        for k in range(len(part.scores)):
+            steps = part.ops[ops_off[k]:ops_off[k] + part.trace_len[k]].astype(np.uint64)
+            for w in range(int(words_per_pair[k])):
+                chunk = steps[16 * w:16 * w + 16]
+                ops2[ops2_off[k] + w] = np.uint32(int(sum(int(v) << (2 * b) for b, v in enumerate(chunk))))
+        used = ops2
+    else:
+        # the shard's words are contiguous per window but windows leave gaps: send pair by pair order
+        words_per_pair = (part.trace_len.astype(np.int64) + 15) // 16
+        take = np.repeat(part.ops_off, words_per_pair) + (np.arange(int(words_per_pair.sum()))
+                                                          - np.repeat(np.cumsum(words_per_pair) - words_per_pair, words_per_pair))
+        used = part.ops2[take]
+    lens = gather_arrays(part.trace_len.astype(np.int32), dst, group)
+    firsts = gather_arrays(np.ascontiguousarray(part.first, dtype=np.int32), dst, group)
+    words = gather_arrays(used, dst, group)
     if rank != dst:
         return None
-    gathered.sort(key=lambda item: item[0])
-    scores = np.concatenate([g[2] for g in gathered])
-    if score_only:
-        return BatchResult(scores, None, None, None, off1 + off2)
-    trace_len = np.concatenate([g[3] for g in gathered])
-    first = np.concatenate([g[4] for g in gathered])
-    ops = np.concatenate([g[5] for g in gathered])
-    return BatchResult(scores, trace_len, first, ops, off1 + off2)
+    trace_len = np.concatenate(lens)
+    per_pair = (trace_len.astype(np.int64) + 15) // 16
+    ops2_off = np.concatenate(([0], np.cumsum(per_pair)[:-1])).astype(np.int64)
+    result = BatchResult(np.concatenate(scores), trace_len, np.concatenate(firsts).reshape(-1, 2), None, ops2_off)
+    result.ops2 = np.concatenate(words) if len(words) else np.zeros(0, dtype=np.uint32)
+    if len(result.ops2) == 0:
+        result.ops2 = np.zeros(1, dtype=np.uint32)
+    result.ops2_words = len(result.ops2)
+    return result
 
 
 def bind_to_gpu_numa_node(local_rank):

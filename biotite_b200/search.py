@@ -38,7 +38,7 @@ def database_shard(db_lengths, rank, world_size):
 
 
 def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, terminal_penalty=True,
-                  chunk_size=100_000, db_range=None, out=None, timings=None):
+                  chunk_size=100_000, db_range=None, out=None, timings=None, devices=None):
     """
     Optimal alignment score of every query against every database sequence.
 
@@ -55,6 +55,10 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
         Preallocated ``(len(queries), n_db)`` int32 result.
     timings : dict, optional
         Receives ``device_ms`` (sum of the CUDA-event times of the batches) and ``cells``.
+    devices : list of int, optional
+        Several GPUs of the node from this one process: the database slice is cut into
+        :func:`database_shard` parts, one host thread per device scores its part into its own
+        columns of the result (no exchange between devices).
 
     Returns
     -------
@@ -69,6 +73,38 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
     scores = np.empty((n_q, n_db), dtype=np.int32) if out is None else out
     if scores.shape != (n_q, n_db):
         raise ValueError(f"out must have shape {(n_q, n_db)}")
+    if devices is not None and len(devices) > 1:
+        from . import _cabi
+        lib = _cabi.load()
+        world = len(devices)
+        parts = [database_shard(d.lengths[begin:end], r, world) for r in range(world)]
+        results, errors = [None] * world, [None] * world
+
+        def run(r):
+            try:
+                _cabi.check(lib.bt_set_device(int(devices[r])))
+                lo, hi = begin + parts[r][0], begin + parts[r][1]
+                t = {}
+                if hi > lo:
+                    search_scores(q, d, scoring, gap_penalty, local, terminal_penalty, chunk_size, (lo, hi),
+                                  scores[:, lo - begin:hi - begin], t)
+                results[r] = t
+            except BaseException as exc:   # re-raised on the calling thread
+                errors[r] = exc
+
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for exc in errors:
+            if exc is not None:
+                raise exc
+        if timings is not None:
+            # the devices work side by side: the batch takes as long as the slowest of them
+            timings["device_ms"] = max((t.get("device_ms", 0.0) for t in results), default=0.0)
+            timings["cells"] = sum(t.get("cells", 0) for t in results)
+        return scores
     # a batch holds at most 2^31 - 1 pairs; 64 database sequences are the smallest useful chunk
     chunk_size = int(max(1, min(chunk_size, (2**31 - 1) // max(n_q, 1))))
     chunks = [(c, min(end, c + chunk_size)) for c in range(begin, end, chunk_size)]
@@ -89,8 +125,13 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
     staging = _cabi.pinned_empty((n_q * min(chunk_size, max(n_db, 1)),), np.int32)
     pending = {}
 
+    device = _cabi.load().bt_get_device()
+
     def prepare_into(k):
         try:
+            # a new host thread starts on device 0: take the caller's device
+            if device >= 0:
+                _cabi.check(_cabi.load().bt_set_device(device))
             pending[k] = prepare(*chunks[k])
         except BaseException as exc:   # re-raised on the consuming thread
             pending[k] = exc
@@ -148,9 +189,10 @@ def search_scores_sharded(queries, database, matrix, gap_penalty=(-10, -1), loca
         _cabi.check(_cabi.load().bt_set_device(int(os.environ.get("LOCAL_RANK", rank))))
         compute = search_scores
     part = compute(queries, d, matrix, gap_penalty, local, terminal_penalty, chunk_size, (lo, hi))
-    gathered = [None] * world if rank == dst else None
-    dist.gather_object((lo, part), gathered, dst=dst, group=group)
+    # the only exchange: the score columns of every rank's database slice, as int32 tensors
+    from .distributed import gather_arrays
+    n_q = part.shape[0]
+    parts = gather_arrays(np.ascontiguousarray(part, dtype=np.int32), dst, group)
     if rank != dst:
         return None
-    gathered.sort(key=lambda item: item[0])
-    return np.concatenate([g[1] for g in gathered], axis=1)
+    return np.concatenate([p.reshape(n_q, -1) for p in parts], axis=1)

@@ -200,6 +200,22 @@ int bt_align_batch_compact(const BtParams *params, const void *codes1, const int
                            int32_t *scores_out, int32_t *trace_len_out, int32_t *first_out,
                            uint32_t *ops2_out, int64_t ops2_capacity, int64_t *ops2_off_out,
                            int64_t *ops2_words_out);
+/*
+ * The same batch over several GPUs of the node from ONE process: `devices` lists n_devices CUDA
+ * device ordinals (NULL: all of bt_device_count()).  The pairs are cut into contiguous shards of
+ * equal DP cells; one host thread per device runs its shard with its own streams and writes
+ * straight into disjoint slices of the caller's arrays - no collective, pairs are independent
+ * (src/rust/sequence/align/pairwise.rs:161 aligns one pair).  Results as in
+ * bt_align_batch_compact; ops2_out needs bt_ops2_capacity() + 16 * n_devices words.
+ * shard_begin_out (optional, n_devices + 1 entries) receives the first pair of every shard.
+ */
+int bt_align_batch_multi(const int32_t *devices, int32_t n_devices, const BtParams *params,
+                         const void *codes1, const int64_t *off1, const void *codes2,
+                         const int64_t *off2, int64_t n_pairs, const int32_t *matrix,
+                         const int64_t *bands, int32_t score_only, int32_t *scores_out,
+                         int32_t *trace_len_out, int32_t *first_out, uint32_t *ops2_out,
+                         int64_t ops2_capacity, int64_t *ops2_off_out, int64_t *ops2_words_out,
+                         int64_t *shard_begin_out);
 int bt_expand_traces2(int64_t n_pairs, const int32_t *trace_len, const int32_t *first,
                       const uint32_t *ops2, const int64_t *ops2_off, const int64_t *bands,
                       const int64_t *rows_off, int64_t *out);

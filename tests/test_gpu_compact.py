@@ -165,3 +165,39 @@ def test_out_arrays_are_validated():
         out[k] = wrong
         with pytest.raises(ValueError, match="out:"):
             bt.align_batch_arrays(codes1, off1, codes2, off2, matrix, (-10, -1), out=tuple(out))
+
+
+def test_multi_device_call_matches_single_device():
+    """bt_align_batch_multi over every device of the box (and over the same device listed twice:
+    two shards, two host threads) against the one-device result and the oracle."""
+    from biotite_b200 import _cabi
+    lib = _cabi.load()
+    rng = np.random.default_rng(21)
+    n = 1500
+    codes1, off1, codes2, off2 = _batch(rng, n, 30, 200)
+    matrix = BLOSUM().score_matrix()
+    single = bt.align_batch_arrays(codes1, off1, codes2, off2, matrix, (-10, -1), True, False, compact=True)
+    ref = single.traces()
+    device_lists = [list(range(lib.bt_device_count())), [0, 0], [0, 0, 0]]
+    for devices in device_lists:
+        out = bt.compact_out(off1, off2, n_devices=max(2, len(devices)))
+        res = bt.align_batch_multi(codes1, off1, codes2, off2, matrix, (-10, -1), True, False, devices=devices, out=out)
+        assert np.array_equal(res.scores, single.scores)
+        assert np.array_equal(res.trace_len, single.trace_len)
+        got = res.traces()
+        for k in range(n):
+            assert np.array_equal(got[k], ref[k]), (devices, k)
+        # shards are contiguous, cover the batch and hold about the same number of DP cells
+        shards = res.shards
+        assert shards[0] == 0 and shards[-1] == n and np.all(np.diff(shards) >= 0)
+        cells = np.diff(off1) * np.diff(off2)
+        per = np.add.reduceat(cells, shards[:-1][np.diff(shards) > 0])
+        assert per.max() - per.min() <= 2 * cells.max()
+    _check(single, codes1, off1, codes2, off2, matrix, (-10, -1), True, False, range(0, n, 97))
+    # score only, semi-global, small batch (general route in every shard)
+    res = bt.align_batch_multi(codes1[:off1[40]], off1[:41], codes2[:off2[40]], off2[:41], matrix, (-10, -1), False, False,
+                               score_only=True, devices=[0, 0])
+    ref_scores, _ = oracle.batch(codes1[:off1[40]], off1[:41], codes2[:off2[40]], off2[:41], matrix, (-10, -1), False, False)
+    assert np.array_equal(res.scores, ref_scores)
+    with pytest.raises(ValueError, match="does not exist"):
+        bt.align_batch_multi(codes1, off1, codes2, off2, matrix, (-10, -1), devices=[99])
