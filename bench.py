@@ -54,9 +54,9 @@ def draw_residues(rng, count):
 GAP = (-10, -1)
 ALGO_LANE_INSTR_PER_CELL = 3.0  # affine 3-state recurrence, s16x2 DPX: 6 instr / 2 cells
 DIR_BYTES_PER_CELL = 0.5        # 4-bit first-optimal directions
-# dram__bytes_read.sum + dram__bytes_write.sum of one interseq_fill_kernel<GLOBAL,traced> launch over
-# 3.015e10 cells: 11.25 GB + 22.71 GB (profiles/r01_interseq_fill_v3_ncu_full.txt, ncu --set full)
-NCU_DRAM_BYTES_PER_CELL = (11.250585e9 + 22.706602e9) / 3.015e10
+# dram__bytes_read.sum + dram__bytes_write.sum per cell of the dominant fill kernel comes from the
+# ncu --set full capture named in this file (written by tools/ncu_traffic.py from the .ncu-rep)
+TRAFFIC_FILE = ROOT / "profiles" / "fill_traffic.json"
 
 def make_c2(n_pairs, seed):
     """BASELINE config 2: lengths N(300,30^2) clipped to [200,400]; the second sequence is a
@@ -204,6 +204,11 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU (config 2: 10^6)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="all", choices=["all", "none"],
+                    help="also run C1 / Cas9 latencies, C3, C4, C5 (JSON key `configs`)")
+    ap.add_argument("--c3-db", type=int, default=200_000, help="database sequences of the C3 entry")
+    ap.add_argument("--c4-pairs", type=int, default=100_000, help="pairs of the C4 entry (full size: 10^5)")
+    ap.add_argument("--c5-seqs", type=int, default=6000, help="proteins of the C5 entry")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -326,6 +331,7 @@ def main():
         fill_ms += f
         back_ms += b
         launches += batch.launches
+    n_windows = batch.windows
     barrier()
     t_end = time.perf_counter()
     clocks = sampler.stop(t_begin, t_end)
@@ -341,14 +347,14 @@ def main():
     # results in the compact form (int32 lengths, 2-bit steps): what the reference's FFI returns,
     # the (L, 2) traces of trace.rs:103-130, is rebuilt from it on the host (bt_expand_traces2)
     out_c = bt.compact_out(off1, off2)
-    e2e_words = [0]
+    e2e_last = [None]
 
     def e2e_step():
         # the public one-shot batch API: host arrays in, host arrays out
         t_step = time.perf_counter()
         res = bt.align_batch_arrays(p_codes1, p_off1, p_codes2, p_off2, matrix, GAP, True, False,
                                     out=out_c, compact=True)
-        e2e_words[0] = res.ops2_words
+        e2e_last[0] = res
         if os.environ.get("B200ALIGN_TRACE"):
             print(f"[bench] rank {rank}: e2e step {1e3 * (time.perf_counter() - t_step):.2f} ms", file=sys.stderr)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -364,8 +370,30 @@ def main():
     e2e_s = max_over_ranks(e2e_local)
     e2e_value = total_cells * args.steps / e2e_s * 1e-9
     h2d = int(sum_over_ranks(float(p_codes1.nbytes + p_codes2.nbytes + off1.nbytes + off2.nbytes + matrix.nbytes)))
-    # bytes that actually crossed the link: scores, lengths, first cells and the used step words
-    d2h = int(sum_over_ranks(float(out_c[0].nbytes + out_c[1].nbytes + out_c[2].nbytes + 4 * e2e_words[0])))
+    # bytes that actually crossed the link: scores, lengths, first cells and the step words in use
+    # (every window copies exactly its compacted words: ceil(L / 16) per pair)
+    step_words = int(((out_c[1].astype(np.int64) + 15) // 16).sum())
+    d2h = int(sum_over_ranks(float(out_c[0].nbytes + out_c[1].nbytes + out_c[2].nbytes + 4 * step_words)))
+
+    # the same call followed by the expansion to the (L, 2) int64 traces the reference's FFI returns
+    # (trace.rs:103-130; bt_expand_traces2 on the host threads): `e2e_expanded`
+    barrier()
+    t0 = time.perf_counter()
+    exp_steps = max(1, min(args.steps, 3))
+    for _ in range(exp_steps):
+        e2e_step()
+        flat, rows_off = e2e_last[0].traces_flat()
+    exp_local = time.perf_counter() - t0
+    expanded_bytes = int(flat.nbytes)
+    del flat
+    barrier()
+    exp_s = max_over_ranks(exp_local)
+    # self-check of the timed workload: sampled pairs of the last end-to-end result against the oracle
+    parity_n, parity_ok = 0, True
+    if rank == 0:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import bench_configs
+        parity_n, parity_ok = bench_configs.parity_c2(e2e_last[0], codes1, off1, codes2, off2, matrix, cpu_threads())
 
     # ---- roofline of the dominant kernel (DP fill) ---------------------------------------------
     peak = np.zeros(3)
@@ -374,7 +402,15 @@ def main():
         _cabi.check(lib.bt_microbench(kind, _cabi.ctypes.byref(v)))
         peak[kind] = v.value
     fill_s = fill_ms * 1e-3 / args.steps          # all fill launches of one step (rank 0)
-    n_fill_launches = max(1, (launches // args.steps) // 3)  # pack + fill + traceback per window
+    n_fill_launches = max(1, n_windows)           # one fill launch per window (bt_batch_windows)
+    traffic, traffic_src = None, None
+    if TRAFFIC_FILE.exists():
+        import hashlib
+        tf = json.loads(TRAFFIC_FILE.read_text())
+        src = ROOT / tf["source"]
+        traffic = tf["dram_bytes_per_cell"] * cells / n_fill_launches
+        traffic_src = {"file": tf["source"], "kernel": tf["kernel"], "dram_bytes_per_cell": tf["dram_bytes_per_cell"],
+                       "sha256": hashlib.sha256(src.read_bytes()).hexdigest() if src.exists() else None}
     achieved = cells * ALGO_LANE_INSTR_PER_CELL / fill_s
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     hbm_peak, hbm_src = 6650.0, "fallback"
@@ -391,9 +427,10 @@ def main():
         "traceback_ms_per_step": back_ms / args.steps,
         "fill_share_of_step": fill_ms / device_ms if device_ms else None,
         "peak_s32_dpx": peak[1] * 1e-12, "peak_dual_issue": peak[2] * 1e-12,
-        "traffic": NCU_DRAM_BYTES_PER_CELL * cells / n_fill_launches,
-        "traffic_note": "bytes per fill launch scaled from the ncu --set full capture in profiles/ "
-                        "(1.13 B/cell: 0.5 direction nibbles + row buffer write/read + packed codes)",
+        "traffic": traffic,
+        "traffic_source": traffic_src,
+        "traffic_note": "dram bytes per fill launch = bytes per cell of the ncu --set full capture named in "
+                        "traffic_source x the cells of one launch of this run",
         "hbm": {"bound": "hbm", "achieved": cells * DIR_BYTES_PER_CELL / fill_s * 1e-9,
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
                 "frac": cells * DIR_BYTES_PER_CELL / fill_s * 1e-9 / hbm_peak,
@@ -409,7 +446,14 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3 / args.steps,
-                "pairs_per_s": args.pairs * world * args.steps / e2e_s},
+                "pairs_per_s": args.pairs * world * args.steps / e2e_s,
+                "result": "scores + first-optimal traces in compact form (int32 lengths, first cell, 2-bit steps)"},
+        "e2e_expanded": {"value": total_cells * exp_steps / exp_s * 1e-9, "unit": "GCUPS",
+                         "ms_per_step": exp_s * 1e3 / exp_steps, "steps": exp_steps,
+                         "expanded_bytes_per_step_rank0": expanded_bytes,
+                         "result": "the same call + bt_expand_traces2: (L, 2) int64 traces as the reference's FFI "
+                                   "returns them (trace.rs:103-130), in pageable host memory"},
+        "parity_checked": parity_n, "parity_ok": parity_ok,
         "gpu_launches": launches, "roofline": roofline, "score_checksum_rank0": checksum,
     }
     if numa_cpus is not None:
@@ -421,6 +465,24 @@ def main():
             "value": gcups, "unit": "GCUPS", "cores": threads, "kind": "port",
             "sample": f"first {n_used} pairs of rank 0's C2 workload ({dt:.1f} s), "
                       f"oracle/align_oracle.c on {threads} host threads"}
+    if args.configs == "all":
+        sys.path.insert(0, str(ROOT / "tools"))
+        import bench_configs
+        out = out_c = batch = None
+        lib.bt_pool_trim()
+        configs = {}
+        threads = cpu_threads()
+        entry = bench_configs.config_c3(args.c3_db, 100_000, peak, threads, dist, rank, world)
+        if rank == 0:
+            configs["c3"] = entry
+            configs["latency"] = bench_configs.single_pair_latencies(threads)
+            configs["c4"] = bench_configs.config_c4(args.c4_pairs, peak, threads)
+            lib.bt_pool_trim()
+            configs["c5"] = bench_configs.config_c5(args.c5_seqs, peak, threads)
+            configs["note"] = ("C3 runs on all ranks (database-sharded), the other entries on rank 0's GPU; "
+                               "roofline_frac = lane-instructions of the recurrence per cell x device-timed cells/s / "
+                               "the DPX issue rate bt_microbench measured in this run")
+            line["configs"] = configs
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

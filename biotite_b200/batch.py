@@ -144,6 +144,46 @@ class DeviceBatch:
                 ctypes.byref(handle)))
         self._handle = handle
 
+    @classmethod
+    def generated(cls, codes1, off1, codes2, off2, scoring, gap_penalty, terminal_penalty=True, local=False,
+                  kind="cross"):
+        """
+        Score-only batch whose pairs are enumerated, planned and packed on the GPU
+        (``bt_batch_create_generated``): ``kind="cross"`` aligns every sequence of pool 1 with
+        every sequence of pool 2 (pair ``i * n2 + j``), ``kind="triangle"`` every pair ``i <= j``
+        of one pool (pass it twice; symmetric matrix).  Raises ``ValueError`` for modes outside
+        the packed kernels; callers then fall back to index arrays.
+        """
+        self = cls.__new__(cls)
+        self._lib = _cabi.load()
+        self._handle = None
+        dtype = np.promote_types(codes1.dtype, codes2.dtype)
+        self.codes1 = np.ascontiguousarray(codes1, dtype)
+        self.codes2 = np.ascontiguousarray(codes2, dtype)
+        self.off1 = np.ascontiguousarray(off1, dtype=np.int64)
+        self.off2 = np.ascontiguousarray(off2, dtype=np.int64)
+        self.idx1 = self.idx2 = self.bands = None
+        n1, n2 = len(self.off1) - 1, len(self.off2) - 1
+        self.kind = {"cross": 0, "triangle": 1}[kind]
+        self.n_pairs = n1 * n2 if self.kind == 0 else n1 * (n1 + 1) // 2
+        self.score_only, self.stats = True, False
+        self._params, self._matrix = _cabi.make_params(scoring, gap_penalty, terminal_penalty, local, False, dtype)
+        handle = ctypes.c_void_p(None)
+        _cabi.check(self._lib.bt_batch_create_generated(
+            ctypes.byref(self._params), _cabi.ptr(self.codes1), _cabi.ptr(self.off1), n1, _cabi.ptr(self.codes2),
+            _cabi.ptr(self.off2), n2, self.kind, _cabi.ptr(self._matrix), 1, ctypes.byref(handle)))
+        self._handle = handle
+        return self
+
+    def score_matrix(self, out=None):
+        """Symmetric ``(n, n)`` score matrix of a ``kind="triangle"`` generated batch after :meth:`run`."""
+        n = len(self.off1) - 1
+        if out is None:
+            out = np.empty((n, n), dtype=np.int32)
+        _check_out("out", out, np.int32, (n, n))
+        _cabi.check(self._lib.bt_batch_fetch_score_matrix(self._handle, _cabi.ptr(out)))
+        return out
+
     def _ops_offsets(self):
         if self.idx1 is None:
             return self.off1 + self.off2
@@ -157,6 +197,11 @@ class DeviceBatch:
     @property
     def launches(self):
         return int(self._lib.bt_batch_launches(self._handle))
+
+    @property
+    def windows(self):
+        """Fill launches of the last :meth:`run` (one per window)."""
+        return int(self._lib.bt_batch_windows(self._handle))
 
     @property
     def kernel(self):
@@ -561,12 +606,14 @@ class _IndexedView:
 
 
 def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True, local=False,
-                      chunk_pairs=1 << 24, timings=None):
+                      chunk_pairs=1 << 24, timings=None, chunk_limit=2**31 - 1):
     """
     Symmetric ``(N, N)`` int32 matrix of optimal alignment scores of every pair ``i <= j``
     (the quantity the reference's ``align_multiple`` computes pair by pair for its guide
     tree, ``multiple.pyx:322-333``).  The triangle is enumerated in chunks of `chunk_pairs`
-    index pairs; the sequences are uploaded once per chunk call, never the pairs.  `timings`
+    index pairs; the sequences are uploaded once per chunk call, never the pairs.  Protein-sized
+    jobs (up to `chunk_limit` pairs, 8-bit codes, a matrix the packed kernels can stage) skip all
+    of that: the GPU enumerates the triangle itself (``bt_batch_create_generated``).  `timings`
     (a dict) receives the summed CUDA-event time ``device_ms`` and the ``cells`` of the batches.
     `sequences` may be a list of ``Sequence`` or a :class:`PackedSequences`.
     """
@@ -576,10 +623,23 @@ def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True,
     if not isinstance(scoring, tuple) and not np.array_equal(scoring, scoring.T):
         raise ValueError("all_vs_all_scores needs a symmetric substitution matrix")
     n = len(pool)
+    if not isinstance(scoring, tuple) and pool.codes.dtype == np.uint8 and 0 < n and n * (n + 1) // 2 <= chunk_limit:
+        # the whole triangle as one batch, enumerated / sorted / packed on the GPU
+        try:
+            batch = DeviceBatch.generated(pool.codes, pool.offsets, pool.codes, pool.offsets, scoring, gap_penalty,
+                                          terminal_penalty, local, kind="triangle")
+        except ValueError:
+            batch = None   # a mode outside the packed kernels: index arrays below
+        if batch is not None:
+            with batch:
+                ms = batch.run()
+                if timings is not None:
+                    timings["device_ms"], timings["cells"], timings["kernel"] = ms, batch.cells, batch.kernel
+                return batch.score_matrix()
     out = np.zeros((n, n), dtype=np.int32)
     lengths = pool.lengths
     bound = _packed_shorter_bound(scoring, gap_penalty)
-    total_ms, total_cells = 0.0, 0
+    total_ms, total_cells, kernels = 0.0, 0, set()
 
     def chunks():
         """Index pairs (first, second) of one batch after the other."""
@@ -640,6 +700,7 @@ def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True,
         try:
             total_ms += batch.run()
             total_cells += batch.cells
+            kernels.add(batch.kernel)
             done = (a, b, batch.fetch().scores)
         finally:
             batch.close()
@@ -652,6 +713,7 @@ def all_vs_all_scores(sequences, matrix, gap_penalty=-10, terminal_penalty=True,
     if timings is not None:
         timings["device_ms"] = total_ms
         timings["cells"] = total_cells
+        timings["kernel"] = "+".join(sorted(kernels))
     return out
 
 

@@ -28,6 +28,7 @@
 #include "emit_kernel.cuh"
 #include "compact_kernel.cuh"
 #include "xdrop_kernel.cuh"
+#include "device_plan.cuh"
 
 using namespace bt;
 
@@ -167,8 +168,8 @@ struct BtBatch {
     PairMap dev_map() const {
         PairMap m;
         m.off1 = off1.as<int64_t>(); m.off2 = off2.as<int64_t>();
-        m.idx1 = h_idx1.empty() ? nullptr : idx1.as<int32_t>();
-        m.idx2 = h_idx2.empty() ? nullptr : idx2.as<int32_t>();
+        m.idx1 = (h_idx1.empty() && !dev_indexed) ? nullptr : idx1.as<int32_t>();
+        m.idx2 = (h_idx2.empty() && !dev_indexed) ? nullptr : idx2.as<int32_t>();
         m.ops_off = h_ops_off.empty() ? nullptr : ops_off.as<int64_t>();
         return m;
     }
@@ -178,6 +179,12 @@ struct BtBatch {
     InterseqPlan interseq;  // state of the packed 16-bit route
     BandedPlan banded;      // state of the banded inter-sequence route
     bool ran = false;
+    // generated batches (bt_batch_create_generated): the index arrays exist on the device only;
+    // pairs outside the packed kernels' range run in `other` (pair other_ids[k] = its pair k)
+    bool dev_indexed = false;
+    int pair_kind = -1;
+    std::unique_ptr<BtBatch> other;
+    std::vector<int32_t> other_ids;
     // per-phase device timing: events[3k..3k+2] bracket fill and traceback of step k
     std::vector<cudaEvent_t> phase_events;
     size_t phase_used = 0;
@@ -496,6 +503,7 @@ static int batch_create_impl(const BtParams *params, const void *codes1, const i
     if (bt_device_count() <= 0)
         return fail(BT_ERR_CUDA, "no CUDA device available (libb200align has no CPU fallback)");
 
+    NvtxRange nvtx_create("bt_batch_create: checks, plan, H2D");
     std::unique_ptr<BtBatch> b(new BtBatch());
     b->P = *params;
     b->n_pairs = n_pairs;
@@ -703,6 +711,7 @@ extern "C" int64_t bt_batch_ops_bytes(const BtBatch *b) { return b ? b->ops_tota
 extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
     if (!b) return fail(BT_ERR_INVALID_ARG, "batch is NULL");
     DeviceGuard device_guard(b->device);
+    NvtxRange nvtx_run("bt_batch_run");
     b->launches = 0;
     b->phase_used = 0;
     CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
@@ -715,9 +724,9 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
             cudaError_t e = cudaSuccess;
             for (const Window &win : b->interseq.windows) {
                 if (e == cudaSuccess) e = b->mark_phase();
-                if (e == cudaSuccess) e = interseq_fill_window(b->interseq, win, 0, io, b->stream, &b->launches);
+                if (e == cudaSuccess) { NvtxRange r("pack + fill"); e = interseq_fill_window(b->interseq, win, 0, io, b->stream, &b->launches); }
                 if (e == cudaSuccess) e = b->mark_phase();
-                if (e == cudaSuccess) e = interseq_traceback_window(b->interseq, win, 0, io, b->stream, &b->launches);
+                if (e == cudaSuccess) { NvtxRange r("traceback"); e = interseq_traceback_window(b->interseq, win, 0, io, b->stream, &b->launches); }
                 if (e == cudaSuccess) e = b->mark_phase();
             }
             if (e != cudaSuccess) st = fail(BT_ERR_CUDA, "inter-sequence kernels: %s", cudaGetErrorString(e));
@@ -728,9 +737,9 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
             cudaError_t e = cudaSuccess;
             for (const BandWindow &win : b->banded.windows) {
                 if (e == cudaSuccess) e = b->mark_phase();
-                if (e == cudaSuccess) e = banded_fill_window(b->banded, win, io, b->stream, &b->launches);
+                if (e == cudaSuccess) { NvtxRange r("banded fill"); e = banded_fill_window(b->banded, win, io, b->stream, &b->launches); }
                 if (e == cudaSuccess) e = b->mark_phase();
-                if (e == cudaSuccess) e = banded_traceback_window(b->banded, win, io, b->stream, &b->launches);
+                if (e == cudaSuccess) { NvtxRange r("banded traceback"); e = banded_traceback_window(b->banded, win, io, b->stream, &b->launches); }
                 if (e == cudaSuccess) e = b->mark_phase();
             }
             if (e != cudaSuccess) st = fail(BT_ERR_CUDA, "banded kernels: %s", cudaGetErrorString(e));
@@ -750,6 +759,14 @@ extern "C" int bt_batch_run(BtBatch *b, float *device_ms) {
         b->fill_ms += f;
         b->traceback_ms += t;
     }
+    if (b->other) {   // the few pairs of a generated batch that need the 32-bit kernels
+        float ms = 0.f;
+        st = bt_batch_run(b->other.get(), &ms);
+        if (st) return st;
+        if (device_ms) *device_ms += ms;
+        b->fill_ms += b->other->fill_ms; b->traceback_ms += b->other->traceback_ms;
+        b->launches += b->other->launches;
+    }
     b->ran = true;
     return BT_OK;
 }
@@ -768,6 +785,267 @@ extern "C" int bt_batch_fetch_scores(BtBatch *b, int32_t *scores_out) {
     CUDA_TRY(cudaMemcpyAsync(scores_out, b->score.ptr, (size_t)b->n_pairs * 4, cudaMemcpyDeviceToHost,
                              b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (b->other) {
+        std::vector<int32_t> part(b->other_ids.size());
+        int st = bt_batch_fetch_scores(b->other.get(), part.data());
+        if (st) return st;
+        for (size_t k = 0; k < part.size(); k++) scores_out[b->other_ids[k]] = part[k];
+    }
+    return BT_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Generated batches: the pairs of a cross product / of the upper triangle of one pool are
+// enumerated, planned and packed on the device (device_plan.cuh); the host never holds a
+// per-pair array.  Score-only batches of the packed 16-bit route; the (few) pairs whose scores
+// could leave 16 bits are collected by the generator and run as an indexed batch of the 32-bit
+// kernels.
+// ---------------------------------------------------------------------------------------
+__global__ void symmetrize_kernel(const int32_t *scores, const int32_t *idx1, const int32_t *idx2, int64_t n_pairs,
+                                  int64_t n, int32_t *matrix) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
+        const int64_t a = idx1[p], b = idx2[p];
+        const int32_t v = scores[p];
+        matrix[a * n + b] = v;
+        matrix[b * n + a] = v;
+    }
+}
+
+extern "C" int bt_batch_create_generated(const BtParams *params, const void *codes1, const int64_t *off1,
+                                         int64_t n_seq1, const void *codes2, const int64_t *off2, int64_t n_seq2,
+                                         int32_t pair_kind, const int32_t *matrix, int32_t score_only,
+                                         BtBatch **batch_out) {
+    if (!batch_out) return fail(BT_ERR_INVALID_ARG, "batch_out is NULL");
+    *batch_out = nullptr;
+    int st = check_params(params);
+    if (st) return st;
+    NvtxRange nvtx_create("bt_batch_create_generated: H2D, device plan");
+    if (pair_kind != DP_PAIRS_CROSS && pair_kind != DP_PAIRS_TRIANGLE) return fail(BT_ERR_INVALID_ARG, "unknown pair_kind");
+    if (score_only != 1) return fail(BT_ERR_INVALID_ARG, "generated batches are score-only (score_only = 1)");
+    if (!off1 || !off2 || n_seq1 < 0 || n_seq2 < 0) return fail(BT_ERR_INVALID_ARG, "bad pool offsets");
+    if (pair_kind == DP_PAIRS_TRIANGLE && n_seq1 != n_seq2) return fail(BT_ERR_INVALID_ARG, "a triangular batch takes one pool (twice)");
+    if (n_seq1 > INT32_MAX || n_seq2 > INT32_MAX) return fail(BT_ERR_INVALID_ARG, "too many sequences");
+    const double pairs_d = pair_kind == DP_PAIRS_CROSS ? (double)n_seq1 * (double)n_seq2 : (double)n_seq1 * ((double)n_seq1 + 1.0) / 2.0;
+    if (pairs_d > (double)INT32_MAX) return fail(BT_ERR_INVALID_ARG, "too many pairs for one batch (split it)");
+    const int64_t n_pairs = pair_kind == DP_PAIRS_CROSS ? n_seq1 * n_seq2 : n_seq1 * (n_seq1 + 1) / 2;
+    // the modes the packed kernels serve (interseq_eligible); everything else: the indexed entry points
+    if (params->banded || !params->use_matrix || !matrix || params->code_bytes != 1 || params->n_rows > 255 ||
+        params->n_cols > 255 || (!params->affine && !params->local && !params->terminal_penalty))
+        return fail(BT_ERR_INVALID_ARG, "generated batches need the packed kernels' modes (matrix scoring, 8-bit codes)");
+    if (off1[0] != 0 || off2[0] != 0) return fail(BT_ERR_INVALID_ARG, "offsets must start at 0");
+    for (int64_t k = 0; k < n_seq1; k++) if (off1[k + 1] < off1[k]) return fail(BT_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    for (int64_t k = 0; k < n_seq2; k++) if (off2[k + 1] < off2[k]) return fail(BT_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    int32_t mn = matrix[0], mx = matrix[0];
+    for (int64_t k = 1; k < (int64_t)params->n_rows * params->n_cols; k++) { mn = std::min(mn, matrix[k]); mx = std::max(mx, matrix[k]); }
+    if (params->affine ? (mn < -128 || mx > 127 || params->n_cols > 128)
+                       : ((int64_t)params->n_rows * params->n_cols * IS_ROWW > 96 * 1024))
+        return fail(BT_ERR_INVALID_ARG, "generated batches need a matrix the packed kernels can stage");
+    if (bt_device_count() <= 0) return fail(BT_ERR_CUDA, "no CUDA device available (libb200align has no CPU fallback)");
+    // exact 16-bit range (the proof of interseq_eligible, per pair): the longer sequence at most
+    // IS_MAX_LEN, the shorter one small enough for the highest finite value
+    int32_t long_max = IS_MAX_LEN, short_max = IS_MAX_LEN;
+    {
+        const int64_t open = params->gap_open, ext = params->affine ? params->gap_ext : params->gap_open;
+        const int64_t lo_s = std::min<int64_t>(mn, 0), hi_s = std::max<int64_t>(mx, 0);
+        const int64_t neg = -32768 - open - ext - lo_s;
+        while (long_max > 0 && !(3 * open + (2 * (int64_t)long_max + 2 + IS_R) * ext + 2 * lo_s > neg + 1)) long_max /= 2;
+        if (hi_s > 0) short_max = (int32_t)std::min<int64_t>(long_max, std::max<int64_t>(0, (32766 + open - hi_s) / hi_s - 1));
+        else short_max = long_max;
+    }
+
+    std::unique_ptr<BtBatch> b(new BtBatch());
+    b->P = *params; b->n_pairs = n_pairs; b->score_only = 1; b->stats = 0;
+    b->device = bt_get_device();
+    b->n_seq1 = n_seq1; b->n_seq2 = n_seq2;
+    b->h_off1.assign(off1, off1 + n_seq1 + 1);
+    b->h_off2.assign(off2, off2 + n_seq2 + 1);
+    b->total1 = off1[n_seq1]; b->total2 = off2[n_seq2];
+    b->min_score = mn; b->max_score = mx;
+    b->dev_indexed = true; b->pair_kind = pair_kind;
+    b->route = ROUTE_INTERSEQ;
+    DevParams &D = b->D;
+    D.affine = params->affine; D.local = params->local; D.terminal = params->terminal_penalty;
+    D.use_matrix = 1; D.banded = 0; D.score_only = 1;
+    D.gap_open = params->gap_open; D.gap_ext = params->affine ? params->gap_ext : params->gap_open;
+    D.neg_inf = reference_neg_inf(*params, mn);
+    D.n_rows = params->n_rows; D.n_cols = params->n_cols; D.code_bytes = 1;
+    CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&b->ev0));
+    CUDA_TRY(cudaEventCreate(&b->ev1));
+    cudaStream_t s = b->stream;
+    const size_t mb = (size_t)params->n_rows * params->n_cols * 4;
+    CUDA_TRY(b->codes1.alloc((size_t)b->total1));
+    CUDA_TRY(b->codes2.alloc((size_t)b->total2));
+    CUDA_TRY(b->off1.alloc((size_t)(n_seq1 + 1) * 8));
+    CUDA_TRY(b->off2.alloc((size_t)(n_seq2 + 1) * 8));
+    CUDA_TRY(b->matrix.alloc(mb));
+    CUDA_TRY(b->score.alloc((size_t)std::max<int64_t>(n_pairs, 1) * 4));
+    CUDA_TRY(b->is_start.alloc((size_t)std::max<int64_t>(n_pairs, 1) * 8));
+    CUDA_TRY(b->idx1.alloc((size_t)std::max<int64_t>(n_pairs, 1) * 4));
+    CUDA_TRY(b->idx2.alloc((size_t)std::max<int64_t>(n_pairs, 1) * 4));
+    CUDA_TRY(b->flag.alloc(32));
+    CUDA_TRY(cudaMemsetAsync(b->flag.ptr, 0, 32, s));
+    CUDA_TRY(cudaMemcpyAsync(b->codes1.ptr, codes1, (size_t)b->total1, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->codes2.ptr, codes2, (size_t)b->total2, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->off1.ptr, off1, (size_t)(n_seq1 + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->off2.ptr, off2, (size_t)(n_seq2 + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->matrix.ptr, matrix, mb, cudaMemcpyHostToDevice, s));
+    if (b->total1 > 0)
+        validate_codes_kernel<<<(int)std::min<int64_t>(1184, (b->total1 + 255) / 256), 256, 0, s>>>(
+            b->codes1.ptr, b->total1, 1, (uint64_t)params->n_rows, b->flag.as<int>());
+    if (b->total2 > 0)
+        validate_codes_kernel<<<(int)std::min<int64_t>(1184, (b->total2 + 255) / 256), 256, 0, s>>>(
+            b->codes2.ptr, b->total2, 1, (uint64_t)params->n_cols, b->flag.as<int>());
+    CUDA_TRY(cudaGetLastError());
+
+    InterseqPlan &plan = b->interseq;
+    interseq_setup(plan, *params, n_pairs, 1, mn);
+    const int64_t per_window = interseq_pairs_per_window(std::max<int64_t>(n_pairs, 1), 4, plan.warps_per_sm);
+    const int64_t groups_per_window = per_window / 64;
+    // flag words: [0] invalid code, [2..3] cells, [4..5] pairs for the 32-bit kernels
+    unsigned long long *d_cells = (unsigned long long *)(b->flag.as<char>() + 8);
+    unsigned long long *d_others = d_cells + 1;
+    struct { int32_t flag, pad; unsigned long long cells, others; } counts{};
+    DevicePlanner dp;
+    if (n_pairs > 0) {
+        CUDA_TRY(dp.reserve(n_pairs));
+        dplan_generate_kernel<<<DevicePlanner::blocks_for(n_pairs), DP_THREADS, 0, s>>>(
+            pair_kind, b->off1.as<int64_t>(), n_seq1, b->off2.as<int64_t>(), n_seq2, n_pairs, short_max, long_max,
+            b->idx1.as<int32_t>(), b->idx2.as<int32_t>(), dp.keys_a.as<uint32_t>(), dp.vals_a.as<int32_t>(), d_cells, d_others);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(dp.sort_pairs(n_pairs, s));
+    }
+    CUDA_TRY(cudaMemcpyAsync(&counts, b->flag.ptr, sizeof(counts), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (counts.flag) return fail(BT_ERR_INVALID_CODE, "a sequence code is outside the substitution matrix");
+    b->cells = (int64_t)counts.cells;
+    const int64_t n_other = (int64_t)counts.others, n_packed = n_pairs - n_other;
+    const int64_t groups = (n_packed + 63) / 64;
+    const int64_t n_windows = groups ? (groups + groups_per_window - 1) / groups_per_window : 0;
+    plan.n_groups = groups;
+    if (groups > 0) {
+        DevBuf d_totals;
+        CUDA_TRY(plan.d_order.alloc((size_t)groups * 64 * 4));
+        CUDA_TRY(plan.d_desc.alloc((size_t)groups * sizeof(WarpDesc)));
+        CUDA_TRY(d_totals.alloc((size_t)n_windows * sizeof(DplanTotals)));
+        int64_t launches = 0;
+        CUDA_TRY(dp.layout(n_packed, groups_per_window, 1, params->affine ? 4 : 2, plan.d_desc.as<WarpDesc>(),
+                           plan.d_order.as<int32_t>(), d_totals.as<DplanTotals>(), s, &launches));
+        std::vector<DplanTotals> totals((size_t)n_windows);
+        CUDA_TRY(cudaMemcpyAsync(totals.data(), d_totals.ptr, (size_t)n_windows * sizeof(DplanTotals), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        plan.windows.clear();
+        for (int64_t w = 0; w < n_windows; w++) {
+            Window win{};
+            win.pair_begin = 0; win.pair_end = 0;
+            win.group_begin = w * groups_per_window; win.group_end = std::min(groups, (w + 1) * groups_per_window);
+            win.dir_words = 0; win.rowbuf_entries = totals[(size_t)w].rowbuf;
+            win.rowcodes = totals[(size_t)w].rowcodes; win.colcodes = totals[(size_t)w].colcodes;
+            plan.max_rowbuf = std::max(plan.max_rowbuf, win.rowbuf_entries);
+            plan.max_rowcodes = std::max(plan.max_rowcodes, win.rowcodes);
+            plan.max_colcodes = std::max(plan.max_colcodes, win.colcodes);
+            plan.windows.push_back(win);
+        }
+        SlotBuffers &sb = plan.slots[0];
+        CUDA_TRY(sb.rowcodes.alloc((size_t)plan.max_rowcodes * 2));
+        CUDA_TRY(sb.colcodes.alloc((size_t)(plan.max_colcodes + IS_SLACK * 32) * 2));
+        CUDA_TRY(sb.rowbuf.alloc((size_t)(plan.max_rowbuf + IS_SLACK * 32) * 12));
+        CUDA_TRY(sb.dirs.alloc(16));
+        CUDA_TRY(sb.ctl.alloc(16));
+        if (plan.C.mode == IS_SEMI) {
+            CUDA_TRY(sb.lastrow.alloc((size_t)plan.max_rowbuf * 8));
+            CUDA_TRY(sb.lastcol.alloc((size_t)plan.max_rowcodes * 8));
+        }
+    }
+    if (n_other > 0) {
+        // ids of the other pairs: the tail of the sorted order (ascending ids: the sort is stable)
+        b->other_ids.resize((size_t)n_other);
+        CUDA_TRY(cudaMemcpyAsync(b->other_ids.data(), dp.vals_b.as<int32_t>() + n_packed, (size_t)n_other * 4, cudaMemcpyDeviceToHost, s));
+        std::vector<int32_t> i1((size_t)n_other), i2((size_t)n_other);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        for (int64_t k = 0; k < n_other; k++) {
+            const int64_t p = b->other_ids[(size_t)k];
+            int64_t a, c;
+            if (pair_kind == DP_PAIRS_CROSS) { a = p / n_seq2; c = p - a * n_seq2; }
+            else {
+                // row of the triangle by bisection over triangle_row_begin
+                int64_t lo = 0, hi = n_seq1 - 1;
+                while (lo < hi) { const int64_t mid = (lo + hi + 1) / 2; if (triangle_row_begin(mid, n_seq1) <= p) lo = mid; else hi = mid - 1; }
+                a = lo; c = a + (p - triangle_row_begin(a, n_seq1));
+                if (off1[a + 1] - off1[a] > off2[c + 1] - off2[c]) std::swap(a, c);
+            }
+            i1[(size_t)k] = (int32_t)a; i2[(size_t)k] = (int32_t)c;
+        }
+        BtBatch *raw = nullptr;
+        st = batch_create_impl(params, codes1, off1, n_seq1, codes2, off2, n_seq2, i1.data(), i2.data(), n_other, matrix,
+                               nullptr, 1, true, &raw);
+        if (st) return st;
+        b->other.reset(raw);
+    }
+    *batch_out = b.release();
+    return BT_OK;
+}
+
+// Scores of a TRIANGLE batch as the symmetric (n, n) int32 matrix (built on the device).
+extern "C" int bt_batch_fetch_score_matrix(BtBatch *b, int32_t *matrix_out) {
+    if (!b || !matrix_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (!b->ran) return fail(BT_ERR_INVALID_ARG, "bt_batch_run has not been called");
+    if (b->pair_kind != DP_PAIRS_TRIANGLE) return fail(BT_ERR_INVALID_ARG, "not a triangular generated batch");
+    DeviceGuard device_guard(b->device);
+    const int64_t n = b->n_seq1;
+    if (n == 0) return BT_OK;
+    DevBuf d_matrix;
+    struct Drain { cudaStream_t s; ~Drain() { cudaStreamSynchronize(s); cudaGetLastError(); } } guard{b->stream};
+    CUDA_TRY(d_matrix.alloc((size_t)(n * n) * 4));
+    symmetrize_kernel<<<DevicePlanner::blocks_for(b->n_pairs), DP_THREADS, 0, b->stream>>>(
+        b->score.as<int32_t>(), b->idx1.as<int32_t>(), b->idx2.as<int32_t>(), b->n_pairs, n, d_matrix.as<int32_t>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(matrix_out, d_matrix.ptr, (size_t)(n * n) * 4, cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (b->other) {
+        std::vector<int32_t> part(b->other_ids.size());
+        int st = bt_batch_fetch_scores(b->other.get(), part.data());
+        if (st) return st;
+        for (size_t k = 0; k < part.size(); k++) {
+            const int64_t a = b->other->h_idx1[k], c = b->other->h_idx2[k];
+            matrix_out[a * n + c] = part[k];
+            matrix_out[c * n + a] = part[k];
+        }
+    }
+    return BT_OK;
+}
+
+// Test hook: the device planner's result for the pairs of a plain batch as ONE window (slot ->
+// pair id, and nmax << 16 | mmax per group), to be compared with the host planner / a restatement.
+extern "C" int bt_debug_device_plan(const int64_t *off1, const int64_t *off2, int64_t n_pairs, int32_t score_only,
+                                    int32_t affine, int32_t *order_out, uint32_t *group_nm_out, int64_t *dir_off_out) {
+    if (!off1 || !off2 || n_pairs < 1 || !order_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (bt_device_count() <= 0) return fail(BT_ERR_CUDA, "no CUDA device available (libb200align has no CPU fallback)");
+    const int64_t groups = (n_pairs + 63) / 64;
+    DevBuf d_off1, d_off2, d_order, d_desc;
+    cudaStream_t s = nullptr;
+    struct Drain { cudaStream_t *s; ~Drain() { if (*s) { cudaStreamSynchronize(*s); cudaStreamDestroy(*s); } cudaGetLastError(); } } guard{&s};
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    CUDA_TRY(d_off1.alloc((size_t)(n_pairs + 1) * 8));
+    CUDA_TRY(d_off2.alloc((size_t)(n_pairs + 1) * 8));
+    CUDA_TRY(d_order.alloc((size_t)groups * 64 * 4));
+    CUDA_TRY(d_desc.alloc((size_t)groups * sizeof(WarpDesc)));
+    CUDA_TRY(cudaMemcpyAsync(d_off1.ptr, off1, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
+    DevicePlanner dp;
+    CUDA_TRY(dp.reserve(n_pairs));
+    PairMap dm;
+    dm.off1 = d_off1.as<int64_t>(); dm.off2 = d_off2.as<int64_t>();
+    CUDA_TRY(dp.plan_window(dm, 0, n_pairs, score_only, affine ? 4 : 2, d_desc.as<WarpDesc>(), d_order.as<int32_t>(), s, nullptr));
+    std::vector<WarpDesc> desc((size_t)groups);
+    CUDA_TRY(cudaMemcpyAsync(order_out, d_order.ptr, (size_t)groups * 64 * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(desc.data(), d_desc.ptr, (size_t)groups * sizeof(WarpDesc), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int64_t g = 0; g < groups; g++) {
+        if (group_nm_out) group_nm_out[g] = (uint32_t)desc[(size_t)g].nmax << 16 | (uint32_t)desc[(size_t)g].mmax;
+        if (dir_off_out) dir_off_out[g] = desc[(size_t)g].dir_off;
+    }
     return BT_OK;
 }
 
@@ -912,6 +1190,7 @@ extern "C" int bt_debug_plan(const BtParams *params, const int64_t *off1, const 
 
 extern "C" int64_t bt_batch_cells(const BtBatch *b) { return b ? b->cells : 0; }
 extern "C" int64_t bt_batch_launches(const BtBatch *b) { return b ? b->launches : 0; }
+extern "C" int64_t bt_batch_windows(const BtBatch *b) { return b ? (int64_t)(b->phase_used / 3) : 0; }
 extern "C" const char *bt_batch_kernel(const BtBatch *b) {
     if (!b) return "";
     return b->route == ROUTE_INTERSEQ ? "interseq_s16x2" : (b->route == ROUTE_BANDED ? "banded_i32" : "general_i32");
@@ -963,6 +1242,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     const bool compact = out.compact && !score_only;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
+    NvtxRange nvtx_call("bt_align_batch (streamed windows)");
     DevBuf d_codes1, d_codes2, d_off1, d_off2, d_matrix, d_score, d_len, d_first, d_ops, d_flag, d_start;
     DevBuf d_len32, d_packed, d_bsums[2], d_total;
     PinnedBuf h_total;
@@ -1015,7 +1295,18 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     interseq_enable_tags(plan, *params, scan, mn, mx);
     const char *waves_env = getenv("B200ALIGN_WAVES");
     const int waves = waves_env ? std::max(1, atoi(waves_env)) : 3;
-    StreamingPlanner planner(plan, hm, n_pairs, waves, params->affine != 0);
+    // windows are planned on the device, on the compute stream, right before they are packed
+    // (B200ALIGN_PLAN=host: the host-thread planner, kept for A/B measurements)
+    const char *plan_env = getenv("B200ALIGN_PLAN");
+    const bool device_plan = !(plan_env && strcmp(plan_env, "host") == 0);
+    StreamingPlanner planner(plan, hm, n_pairs, waves, params->affine != 0, device_plan);
+    DevicePlanner dplanner;
+    if (device_plan) {
+        int64_t max_np = 0;
+        for (int64_t w = 0; w < planner.n_windows; w++)
+            max_np = std::max(max_np, planner.bounds[(size_t)w + 1] - planner.bounds[(size_t)w]);
+        CUDA_TRY(dplanner.reserve(max_np));
+    }
     if (compact) {
         int64_t max_np = 0;
         for (int64_t w = 0; w < planner.n_windows; w++)
@@ -1089,6 +1380,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
         }
     };
     auto drain = [&](size_t w) -> int {
+        NvtxRange nvtx_drain("window D2H");
         const Window &win = plan.windows[w];
         const int64_t p0 = win.pair_begin, np = win.pair_end - win.pair_begin;
         cudaStream_t r = st.d2h;
@@ -1140,7 +1432,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
         // the next window's fill slows that fill by as much as it saves (measured)
         const int slot = 0;
         cudaStream_t s = st.s[0];
-        CUDA_TRY(planner.take((int64_t)w, st.h2d));
+        { NvtxRange r("wait for window plan"); CUDA_TRY(planner.take((int64_t)w, st.h2d)); }
         if (trace) host_t[w * 3] = now() - t0;
         CUDA_TRY(cudaEventRecord(st.plan_ready[w], st.h2d));
         if ((int64_t)w + 1 < planner.n_windows) CUDA_TRY(enqueue_inputs((int64_t)w + 1));
@@ -1150,8 +1442,14 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
         const int64_t np = win.pair_end - win.pair_begin;
         CUDA_TRY(cudaStreamWaitEvent(s, st.in_ready[w], 0));
         mark(w, 1, s);
-        CUDA_TRY(interseq_fill_window(plan, win, slot, io, s, &launches));
-        CUDA_TRY(interseq_traceback_window(plan, win, slot, io, s, &launches));
+        if (device_plan) {
+            NvtxRange r("device plan");
+            CUDA_TRY(dplanner.plan_window(dm, win.pair_begin, np, plan.C.score_only, params->affine ? 4 : 2,
+                                          plan.d_desc.as<WarpDesc>() + win.group_begin,
+                                          plan.d_order.as<int32_t>() + win.group_begin * 64, s, &launches));
+        }
+        { NvtxRange r("pack + fill"); CUDA_TRY(interseq_fill_window(plan, win, slot, io, s, &launches)); }
+        { NvtxRange r("traceback"); CUDA_TRY(interseq_traceback_window(plan, win, slot, io, s, &launches)); }
         if (compact) {
             CompactArgs ca{d_len.as<int64_t>(), d_ops.as<uint8_t>(), dm, win.pair_begin, np, d_len32.as<int32_t>(),
                            d_bsums[slot].as<int64_t>(),

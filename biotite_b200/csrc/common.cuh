@@ -2,8 +2,18 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <nvtx3/nvToolsExt.h>
 
 namespace bt {
+
+// NVTX range of one host-side phase (plan / pack + fill / traceback / copies): header-only NVTX 3,
+// a no-op unless a profiler has injected its library.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 // Direction bits, identical to the reference's bitflags
 // (src/rust/sequence/align/cell.rs:44-80) so that direction tables can be

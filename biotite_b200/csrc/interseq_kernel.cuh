@@ -1609,9 +1609,11 @@ struct StreamingPlanner {
     PinnedBuf staging;                          // page-locked copies of order / descriptors (async H2D)
     std::vector<std::thread> threads;
     std::atomic<int64_t> next{0};
+    bool on_device;                             // windows are planned by device_plan.cuh on the compute stream
 
-    StreamingPlanner(InterseqPlan &p, const PairMap &map, int64_t n, int waves, bool affine)
-        : plan(p), hm(map), n_pairs(n), no_dirs(p.C.score_only), dir_words_per_lane(affine ? 4 : 2) {
+    StreamingPlanner(InterseqPlan &p, const PairMap &map, int64_t n, int waves, bool affine, bool device_plan)
+        : plan(p), hm(map), n_pairs(n), no_dirs(p.C.score_only), dir_words_per_lane(affine ? 4 : 2),
+          on_device(device_plan) {
         per_window = interseq_pairs_per_window(n_pairs, waves, p.warps_per_sm);
         // Windows are whole waves of the fill kernel (a partial wave leaves warps idle for the
         // 3 - 4 ms a group takes).  The first window is a single wave, so that the kernels start
@@ -1655,7 +1657,7 @@ struct StreamingPlanner {
         cudaError_t e;
         if ((e = plan.d_order.alloc((size_t)plan.n_groups * 64 * 4)) != cudaSuccess) return e;
         if ((e = plan.d_desc.alloc((size_t)plan.n_groups * sizeof(WarpDesc))) != cudaSuccess) return e;
-        if ((e = staging.alloc((size_t)plan.n_groups * (64 * 4 + sizeof(WarpDesc)))) != cudaSuccess) return e;
+        if (!on_device && (e = staging.alloc((size_t)plan.n_groups * (64 * 4 + sizeof(WarpDesc)))) != cudaSuccess) return e;
         for (int sl = 0; sl < n_slots; sl++) {
             SlotBuffers &b = plan.slots[sl];
             if ((e = b.rowcodes.alloc((size_t)plan.max_rowcodes * 2)) != cudaSuccess) return e;
@@ -1671,6 +1673,7 @@ struct StreamingPlanner {
         return cudaSuccess;
     }
     void start() {
+        if (on_device) return;
         const unsigned hw = interseq_host_threads();
         const int n_threads = (int)std::min<int64_t>(std::min<unsigned>(hw, 8u), n_windows);
         for (int t = 0; t < n_threads; t++) {
@@ -1690,8 +1693,16 @@ struct StreamingPlanner {
     }
     // blocks until window w is planned; uploads its order / descriptors on `stream`
     cudaError_t take(int64_t w, cudaStream_t stream) {
-        while (!ready[(size_t)w].load(std::memory_order_acquire)) std::this_thread::yield();
         WindowPlan &wp = wps[(size_t)w];
+        if (on_device) {
+            // pair and group ranges follow from the counts alone; the rest is built on the device
+            wp.win.pair_begin = bounds[(size_t)w]; wp.win.pair_end = bounds[(size_t)w + 1];
+            wp.win.group_begin = group_begin[(size_t)w];
+            wp.win.group_end = group_begin[(size_t)w + 1];
+            plan.windows[(size_t)w] = wp.win;
+            return cudaSuccess;
+        }
+        while (!ready[(size_t)w].load(std::memory_order_acquire)) std::this_thread::yield();
         wp.win.group_begin = group_begin[(size_t)w];
         wp.win.group_end = group_begin[(size_t)w + 1];
         plan.windows[(size_t)w] = wp.win;

@@ -104,16 +104,24 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
             # the devices work side by side: the batch takes as long as the slowest of them
             timings["device_ms"] = max((t.get("device_ms", 0.0) for t in results), default=0.0)
             timings["cells"] = sum(t.get("cells", 0) for t in results)
+            timings["kernel"] = "+".join(sorted({t["kernel"] for t in results if t.get("kernel")}))
         return scores
     # a batch holds at most 2^31 - 1 pairs; 64 database sequences are the smallest useful chunk
     chunk_size = int(max(1, min(chunk_size, (2**31 - 1) // max(n_q, 1))))
     chunks = [(c, min(end, c + chunk_size)) for c in range(begin, end, chunk_size)]
-    total_ms, total_cells = 0.0, 0
+    total_ms, total_cells, kernels = 0.0, 0, set()
 
     def prepare(lo, hi):
         # database chunk as its own pool: offsets rebased, codes sliced (views, no copies)
         off = d.offsets[lo:hi + 1] - d.offsets[lo]
         codes = d.codes[d.offsets[lo]:d.offsets[hi]]
+        if not isinstance(scoring, tuple) and q.codes.dtype == np.uint8 and codes.dtype == np.uint8:
+            # the cross product is enumerated, sorted and packed on the GPU: no index arrays
+            try:
+                return DeviceBatch.generated(q.codes, q.offsets, codes, off, scoring, gap_penalty, terminal_penalty,
+                                             local, kind="cross")
+            except ValueError:
+                pass   # a mode outside the packed kernels
         idx1 = np.repeat(np.arange(n_q, dtype=np.int32), hi - lo)
         idx2 = np.tile(np.arange(hi - lo, dtype=np.int32), n_q)
         return DeviceBatch(q.codes, q.offsets, codes, off, scoring, gap_penalty, terminal_penalty, local,
@@ -150,6 +158,7 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
             t0 = time.perf_counter()
             total_ms += batch.run()
             total_cells += batch.cells
+            kernels.add(batch.kernel)
             t1 = time.perf_counter()
             part = staging[:n_q * (hi - lo)]
             batch.fetch(out=(part, None, None, None))
@@ -166,11 +175,13 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
     if timings is not None:
         timings["device_ms"] = total_ms
         timings["cells"] = total_cells
+        timings["kernel"] = "+".join(sorted(kernels))
     return scores
 
 
 def search_scores_sharded(queries, database, matrix, gap_penalty=(-10, -1), local=True,
-                          terminal_penalty=True, chunk_size=100_000, group=None, compute=None, dst=0):
+                          terminal_penalty=True, chunk_size=100_000, group=None, compute=None, dst=0,
+                          timings=None):
     """
     Collective call (one process per GPU, ``torch.distributed``): rank ``r`` scores all queries
     against its :func:`database_shard`; rank `dst` receives the full ``(n_queries, n_db)``
@@ -188,7 +199,10 @@ def search_scores_sharded(queries, database, matrix, gap_penalty=(-10, -1), loca
         from . import _cabi
         _cabi.check(_cabi.load().bt_set_device(int(os.environ.get("LOCAL_RANK", rank))))
         compute = search_scores
-    part = compute(queries, d, matrix, gap_penalty, local, terminal_penalty, chunk_size, (lo, hi))
+    if timings is not None and compute is search_scores:
+        part = compute(queries, d, matrix, gap_penalty, local, terminal_penalty, chunk_size, (lo, hi), timings=timings)
+    else:
+        part = compute(queries, d, matrix, gap_penalty, local, terminal_penalty, chunk_size, (lo, hi))
     # the only exchange: the score columns of every rank's database slice, as int32 tensors
     from .distributed import gather_arrays
     n_q = part.shape[0]

@@ -137,6 +137,25 @@ int bt_batch_create_indexed(const BtParams *params, const void *codes1, const in
                             const int32_t *idx1, const int32_t *idx2, int64_t n_pairs,
                             const int32_t *matrix, const int64_t *bands, int32_t score_only,
                             BtBatch **batch_out);
+/*
+ * Generated batch: the pairs are not listed by the caller but enumerated on the device, which
+ * also sorts, groups and packs them (csrc/device_plan.cuh) - the host never holds a per-pair
+ * array.  BT_PAIRS_CROSS: pair p = i * n_seq2 + j aligns sequence i of pool 1 with sequence j of
+ * pool 2 (one-vs-many searches, BASELINE config 3: the loop over align_optimal(q, d, ...,
+ * score_only=True) of a database scan).  BT_PAIRS_TRIANGLE: both pools are the same n sequences
+ * and pair p is the p-th (i, j), i <= j, in row-major order - the guide-tree loop of the reference
+ * (src/biotite/sequence/align/multiple.pyx:322-333); every pair is aligned shorter sequence first,
+ * so the matrix must be symmetric.  score_only must be 1.  Scores come back in pair order
+ * (bt_batch_fetch_scores) or, for a triangle, as the symmetric (n, n) matrix
+ * (bt_batch_fetch_score_matrix).  Modes outside the packed 16-bit kernels (no matrix, banded,
+ * wide codes, linear semi-global) are refused with BT_ERR_INVALID_ARG: use the indexed form.
+ */
+typedef enum BtPairKind { BT_PAIRS_CROSS = 0, BT_PAIRS_TRIANGLE = 1 } BtPairKind;
+int bt_batch_create_generated(const BtParams *params, const void *codes1, const int64_t *off1,
+                              int64_t n_seq1, const void *codes2, const int64_t *off2, int64_t n_seq2,
+                              int32_t pair_kind, const int32_t *matrix, int32_t score_only,
+                              BtBatch **batch_out);
+int bt_batch_fetch_score_matrix(BtBatch *batch, int32_t *matrix_out);
 int64_t bt_batch_ops_bytes(const BtBatch *batch);
 int bt_batch_run(BtBatch *batch, float *device_ms);
 int bt_batch_fetch_scores(BtBatch *batch, int32_t *scores_out);
@@ -170,6 +189,8 @@ int bt_batch_timings(const BtBatch *batch, float *fill_ms, float *traceback_ms);
 int64_t bt_batch_cells(const BtBatch *batch);
 /* launches issued by the last bt_batch_run (this library's own kernels only) */
 int64_t bt_batch_launches(const BtBatch *batch);
+/* fill launches of the last bt_batch_run: one per window (packed routes) or chunk (general route) */
+int64_t bt_batch_windows(const BtBatch *batch);
 /* name of the fill kernel family the batch was routed to ("general_i32", "interseq_s16x2", ...) */
 const char *bt_batch_kernel(const BtBatch *batch);
 void bt_batch_destroy(BtBatch *batch);
@@ -259,6 +280,15 @@ int bt_debug_plan(const BtParams *params, const int64_t *off1, const int64_t *of
                   int64_t *n_groups_out, int64_t *window_groups_out, int64_t *window_dir_bytes_out,
                   int64_t window_cap, int64_t *n_windows_out, int64_t *cells_out,
                   uint64_t *layout_hash_out);
+
+/*
+ * Test hook: the device planner's plan of the pairs (off1, off2) as one window: order_out receives
+ * ceil(n_pairs / 64) * 64 slot -> pair ids (-1 = padding), group_nm_out (optional) nmax << 16 |
+ * mmax per group, dir_off_out (optional) the first direction word of every group.  The GPU tests
+ * compare it with the host planner (bt_debug_plan) and a numpy restatement.
+ */
+int bt_debug_device_plan(const int64_t *off1, const int64_t *off2, int64_t n_pairs, int32_t score_only,
+                         int32_t affine, int32_t *order_out, uint32_t *group_nm_out, int64_t *dir_off_out);
 
 /*
  * Roofline denominators measured on the current device: register-only loops of
