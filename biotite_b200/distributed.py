@@ -17,7 +17,7 @@ import numpy as np
 
 from .batch import BatchResult, align_batch_arrays
 
-__all__ = ["shard_bounds", "gather_arrays", "align_batch_sharded", "bind_to_gpu_numa_node"]
+__all__ = ["shard_bounds", "gather_arrays", "gather_columns", "align_batch_sharded", "bind_to_gpu_numa_node"]
 
 
 def shard_bounds(off1, off2, world_size):
@@ -65,6 +65,43 @@ def gather_arrays(array, dst=0, group=None):
         return None
     parts = [t[:n].cpu().numpy() for t, n in zip(bucket, sizes)]
     return [p.view(np.uint32) if dtype == np.uint32 else p for p in parts]
+
+
+def gather_columns(part, dst=0, group=None):
+    """
+    Gather the column blocks of a row-major matrix: every rank holds ``part`` of shape
+    ``(rows, width_r)`` (ideally page-locked, ``_cabi.pinned_empty``); rank `dst` receives the
+    ``(rows, sum(width_r))`` matrix, the others ``None``.  The blocks travel as device tensors
+    (NVLink under NCCL), are joined on the device and leave it through one page-locked copy.
+    """
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    nccl = dist.get_backend(group) == "nccl"
+    device = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+    part = np.ascontiguousarray(part, dtype=np.int32)
+    rows = part.shape[0]
+    width = torch.tensor([part.shape[1]], dtype=torch.int64, device=device)
+    widths = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(widths, width, group=group)
+    widths = [int(t.item()) for t in widths]
+    widest = max(max(widths), 1)
+    padded = torch.zeros(rows * widest, dtype=torch.int32, device=device)
+    if part.size:
+        padded[:part.size] = torch.from_numpy(part.reshape(-1)).to(device, non_blocking=True)
+    bucket = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bucket, dst=dst, group=group)
+    if rank != dst:
+        return None
+    joined = torch.cat([t[:rows * w].view(rows, w) for t, w in zip(bucket, widths)], dim=1)
+    if not nccl:
+        return joined.numpy()
+    from . import _cabi
+    out = _cabi.pinned_empty((rows, sum(widths)), np.int32)
+    torch.from_numpy(out).copy_(joined, non_blocking=True)
+    torch.cuda.synchronize()
+    return out
 
 
 def align_batch_sharded(codes1, off1, codes2, off2, scoring, gap_penalty, terminal_penalty=True,

@@ -199,14 +199,14 @@ def search_scores_sharded(queries, database, matrix, gap_penalty=(-10, -1), loca
         from . import _cabi
         _cabi.check(_cabi.load().bt_set_device(int(os.environ.get("LOCAL_RANK", rank))))
         compute = search_scores
-    if timings is not None and compute is search_scores:
-        part = compute(queries, d, matrix, gap_penalty, local, terminal_penalty, chunk_size, (lo, hi), timings=timings)
+    if compute is search_scores:
+        # page-locked result block: it goes back to the device for the gather at copy-engine speed
+        from . import _cabi
+        q = queries if hasattr(queries, "offsets") else pack_sequences(queries)
+        part = _cabi.pinned_empty((len(q), hi - lo), np.int32)
+        compute(q, d, matrix, gap_penalty, local, terminal_penalty, chunk_size, (lo, hi), out=part, timings=timings)
     else:
         part = compute(queries, d, matrix, gap_penalty, local, terminal_penalty, chunk_size, (lo, hi))
-    # the only exchange: the score columns of every rank's database slice, as int32 tensors
-    from .distributed import gather_arrays
-    n_q = part.shape[0]
-    parts = gather_arrays(np.ascontiguousarray(part, dtype=np.int32), dst, group)
-    if rank != dst:
-        return None
-    return np.concatenate([p.reshape(n_q, -1) for p in parts], axis=1)
+    # the only exchange: the score columns of every rank's database slice, joined on the device
+    from .distributed import gather_columns
+    return gather_columns(part, dst, group)

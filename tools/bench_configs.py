@@ -152,12 +152,15 @@ def config_c3(n_db, chunk, peaks, threads, dist=None, rank=0, world=1):
     database = _pool(rng, np.clip(np.rint(rng.lognormal(np.log(270), 0.7, n_db)), 30, 5000).astype(np.int64))
     matrix = bt.SubstitutionMatrix.std_protein_matrix()
     timings = {}
+    if world > 1:
+        # first use of the gather's point-to-point connections (NCCL sets them up lazily)
+        from biotite_b200.distributed import gather_columns
+        gather_columns(np.zeros((4, 4), dtype=np.int32))
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
     if world > 1:
-        from biotite_b200.search import database_shard, search_scores_sharded
-        lo, hi = database_shard(database.lengths, rank, world)
+        from biotite_b200.search import search_scores_sharded
         scores = search_scores_sharded(queries, database, matrix, GAP, chunk_size=chunk, timings=timings)
     else:
         scores = bt.search_scores(queries, database, matrix, GAP, chunk_size=chunk, timings=timings)
@@ -184,7 +187,7 @@ def config_c3(n_db, chunk, peaks, threads, dist=None, rank=0, world=1):
                              + (f"; database sharded over {world} ranks, gather of the score columns timed" if world > 1 else ""),
                  "pairs": n_q * n_db, "cells": cells, "kernel": kernel,
                  "gcups_device": cells / device_s * 1e-9, "gcups_wall": cells / wall * 1e-9, "wall_s": wall,
-                 "roofline_frac": roofline_frac(kernel, True, cells / device_s, peaks),
+                 "roofline_frac": roofline_frac(kernel, True, cells / device_s / world, peaks),
                  "cpu_port_gcups": cpu, "cpu_port_sample_pairs": n_cpu, "parity_checked": 1000, "parity_ok": ok}
     return entry
 

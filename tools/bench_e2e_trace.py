@@ -11,6 +11,8 @@ import bench  # noqa: E402
 import biotite_b200 as bt  # noqa: E402
 from biotite_b200 import _cabi  # noqa: E402
 
+import os  # noqa: E402
+_cabi.check(_cabi.load().bt_set_device(int(os.environ.get("LOCAL_RANK", "0"))))   # one process per GPU under torchrun
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 compact = (sys.argv[2] != "classic") if len(sys.argv) > 2 else True
 codes1, off1, codes2, off2 = bench.make_c2(n, 0)
