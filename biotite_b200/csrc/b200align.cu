@@ -21,6 +21,7 @@
 #include "pool.cuh"
 #include "general_kernel.cuh"
 #include "wavefront_kernel.cuh"
+#include "strip_kernel.cuh"
 #include "host_trace.hpp"
 #include "interseq_kernel.cuh"
 #include "banded_kernel.cuh"
@@ -317,8 +318,31 @@ static cudaError_t dispatch_wavefront_mode(const DevParams &D, const BatchView &
                         : launch_wavefront_fill<AFFINE, BANDED, WF_GLOBAL, true>(D, V, A, grid, threads, smem, s);
 }
 
+template <int MODE, bool TRACED>
+static cudaError_t launch_strip_fill(const DevParams &D, const BatchView &V, const WfArgs &A, int grid, int threads,
+                                     size_t smem, cudaStream_t s) {
+    auto kernel = A.lean_rows == 8 ? strip_fill_kernel<MODE, TRACED, 8> : strip_fill_kernel<MODE, TRACED, 4>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kernel<<<grid, threads, smem, s>>>(D, V, A);
+    return cudaGetLastError();
+}
+
 static cudaError_t dispatch_wavefront_fill(const DevParams &D, const BatchView &V, const WfArgs &A, int grid,
                                            int threads, size_t smem, cudaStream_t s) {
+    if (D.lean) {
+        // lean first-optimal kernel (strip_kernel.cuh): same launch shape, same outputs
+        if (D.local)
+            return D.score_only ? launch_strip_fill<WF_LOCAL, false>(D, V, A, grid, threads, smem, s)
+                                : launch_strip_fill<WF_LOCAL, true>(D, V, A, grid, threads, smem, s);
+        if (!D.terminal)
+            return D.score_only ? launch_strip_fill<WF_SEMI, false>(D, V, A, grid, threads, smem, s)
+                                : launch_strip_fill<WF_SEMI, true>(D, V, A, grid, threads, smem, s);
+        return D.score_only ? launch_strip_fill<WF_GLOBAL, false>(D, V, A, grid, threads, smem, s)
+                            : launch_strip_fill<WF_GLOBAL, true>(D, V, A, grid, threads, smem, s);
+    }
     if (D.affine) {
         return D.banded ? dispatch_wavefront_mode<true, true>(D, V, A, grid, threads, smem, s)
                         : dispatch_wavefront_mode<true, false>(D, V, A, grid, threads, smem, s);
@@ -333,10 +357,14 @@ static int wavefront_launch(const BtParams &P, const DevParams &D, BatchView V, 
                             int max_n, int max_m, DevBuf &gscratch, cudaStream_t stream, int64_t *launches) {
     const int NS = P.affine ? 3 : 1;
     const int mat_ints = P.use_matrix ? P.n_rows * P.n_cols : 0;
-    const int R = P.banded ? 2 : 4;   // rows per lane (launch_wavefront_fill)
+    // rows per lane (launch_wavefront_fill); the lean kernel takes 8 once the pairs span several stripes
+    // and there are enough of them to fill the machine (half the per-step overhead per cell), else 4
+    // a handful of pairs cannot fill the SMs: more, shorter stripes (more warps in flight) win there
+    const int R = P.banded ? 2 : (D.lean && max_n > 128 && end - begin >= 64 ? 8 : 4);
     const int rows = 32 * R;
     const int nw = std::max(1, std::min(WF_MAX_WARPS, (max_n + rows - 1) / rows));
     WfArgs A{};
+    A.lean_rows = R;
     A.bnd_cols = max_m + 8;
     A.mat_smem = (mat_ints > 0 && mat_ints <= 4096) ? 1 : 0;
     const int64_t bnd_ints = (int64_t)nw * A.bnd_cols * NS;
@@ -374,6 +402,13 @@ static int run_general(BtBatch *b, bool traceback) {
     for (const Chunk &c : b->chunks) {
         BatchView V = make_view(b);
         DevParams D = b->D;
+        // batches return the first-optimal trace only: the lean kernel's direction bytes suffice
+        {
+            const char *forced = getenv("B200ALIGN_GENERAL");
+            D.lean = b->wavefront && (traceback || b->score_only) && !D.mark &&
+                     !(forced && strcmp(forced, "full") == 0) &&
+                     strip_eligible(b->P, (int64_t)c.max_n + c.max_m, b->min_score, b->max_score);
+        }
         if (b->wavefront) {
             // never-filled band cells and the padding behind every row read as "no direction"
             if (!b->score_only) CUDA_TRY(cudaMemsetAsync(b->dirs.ptr, 0, (size_t)c.dir_bytes, b->stream));
@@ -2082,6 +2117,11 @@ static int align_pair_fast(const BtParams &P, const void *code1, int64_t len1, c
     D.neg_inf = reference_neg_inf(P, mn);
     D.n_rows = P.n_rows; D.n_cols = P.n_cols; D.code_bytes = P.code_bytes;
     D.dir_pad = 1;
+    {
+        const char *forced = getenv("B200ALIGN_GENERAL");
+        D.lean = (score_only || max_number == 1) && !(forced && strcmp(forced, "full") == 0) &&
+                 strip_eligible(P, len1 + len2, mn, mx);
+    }
     char *din = (char *)C.d_in, *dout = (char *)C.d_out;
     BatchView V{};
     V.codes1 = din + in_c1; V.codes2 = din + in_c2;

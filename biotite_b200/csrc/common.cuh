@@ -36,6 +36,7 @@ struct DevParams {
     int matrix_in_smem;  // matrix staged in shared memory
     int stats;           // traceback emits GapStats (in `first`) instead of step bytes
     int dir_pad;         // direction tables have their row stride rounded up to 16 (wavefront kernel)
+    int lean;            // first-optimal directions suffice and the mode fits strip_kernel.cuh
 };
 
 // row stride of a direction table with `cols` columns

@@ -40,6 +40,7 @@ struct WfArgs {
     int64_t bnd_block;   // ints per block in `bnd`
     int32_t bnd_cols;    // columns per boundary slot
     int32_t mat_smem;    // matrix staged in shared memory
+    int32_t lean_rows;   // rows per lane of the lean kernel (strip_kernel.cuh): 4 or 8
 };
 
 // closed forms of the first row (pairwise.rs:452-467, :747-780) and first column (:434-450, :707-745)
