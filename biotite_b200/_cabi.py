@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "bt_batch_fetch_traces", "bt_batch_fetch_cigar", "bt_batch_fetch_gapped", "bt_batch_timings", "bt_microbench", "bt_batch_cells", "bt_batch_launches", "bt_batch_kernel",
     "bt_batch_destroy", "bt_align_batch", "bt_xdrop_regions", "bt_debug_plan", "bt_expand_traces", "bt_pinned_alloc",
     "bt_pinned_free", "bt_pool_trim", "bt_ops2_capacity", "bt_align_batch_compact", "bt_expand_traces2", "bt_align_batch_multi", "bt_batch_windows",
-    "bt_batch_create_generated", "bt_batch_fetch_score_matrix", "bt_debug_device_plan",
+    "bt_batch_create_generated", "bt_batch_fetch_score_matrix", "bt_debug_device_plan", "bt_batch_fetch_topk",
 ]
 
 
@@ -96,6 +96,7 @@ def load():
     lib.bt_batch_create_generated.argtypes = [
         ctypes.POINTER(BtParams), _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _i32, ctypes.POINTER(_vp)]
     lib.bt_batch_fetch_score_matrix.argtypes = [_vp, _vp]
+    lib.bt_batch_fetch_topk.argtypes = [_vp, _i32, _vp, _vp]
     lib.bt_debug_device_plan.argtypes = [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]
     lib.bt_batch_ops_bytes.restype = _i64
     lib.bt_batch_ops_bytes.argtypes = [_vp]

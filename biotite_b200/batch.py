@@ -175,6 +175,17 @@ class DeviceBatch:
         self._handle = handle
         return self
 
+    def top_k(self, k):
+        """``(scores, columns)``, each ``(n1, k)`` int32: the `k` best pool-2 hits of every pool-1
+        sequence of a ``kind="cross"`` generated batch after :meth:`run`, selected on the GPU and
+        sorted here (higher score first, equal scores by ascending index; ``-1`` pads short rows)."""
+        n1 = len(self.off1) - 1
+        scores = np.empty((n1, k), dtype=np.int32)
+        cols = np.empty((n1, k), dtype=np.int32)
+        _cabi.check(self._lib.bt_batch_fetch_topk(self._handle, int(k), _cabi.ptr(scores), _cabi.ptr(cols)))
+        order = np.argsort(-scores.astype(np.int64), axis=1, kind="stable")   # rows arrive in ascending column order
+        return np.take_along_axis(scores, order, axis=1), np.take_along_axis(cols, order, axis=1)
+
     def score_matrix(self, out=None):
         """Symmetric ``(n, n)`` score matrix of a ``kind="triangle"`` generated batch after :meth:`run`."""
         n = len(self.off1) - 1

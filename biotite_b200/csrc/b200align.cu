@@ -30,6 +30,7 @@
 #include "compact_kernel.cuh"
 #include "xdrop_kernel.cuh"
 #include "device_plan.cuh"
+#include "topk_kernel.cuh"
 
 using namespace bt;
 
@@ -1048,6 +1049,40 @@ extern "C" int bt_batch_fetch_score_matrix(BtBatch *b, int32_t *matrix_out) {
             matrix_out[c * n + a] = part[k];
         }
     }
+    return BT_OK;
+}
+
+// The k best database hits of every query of a CROSS batch: the selection runs on the device over
+// the (n_seq1, n_seq2) score matrix, 8 k bytes per query come back instead of 4 n_seq2.
+extern "C" int bt_batch_fetch_topk(BtBatch *b, int32_t k, int32_t *scores_out, int32_t *index_out) {
+    if (!b || !scores_out || !index_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (!b->ran) return fail(BT_ERR_INVALID_ARG, "bt_batch_run has not been called");
+    if (b->pair_kind != DP_PAIRS_CROSS) return fail(BT_ERR_INVALID_ARG, "not a cross-product generated batch");
+    if (k < 1) return fail(BT_ERR_INVALID_ARG, "k must be at least 1");
+    DeviceGuard device_guard(b->device);
+    const int64_t rows = b->n_seq1, cols = b->n_seq2;
+    if (rows == 0) return BT_OK;
+    cudaStream_t s = b->stream;
+    struct Drain { cudaStream_t s; ~Drain() { cudaStreamSynchronize(s); cudaGetLastError(); } } guard{s};
+    DevBuf d_ids, d_vals, d_scores, d_cols;
+    if (b->other) {
+        // scores of the pairs the 32-bit kernels ran go into the matrix first
+        const int64_t cnt = (int64_t)b->other_ids.size();
+        CUDA_TRY(d_ids.alloc((size_t)cnt * 4));
+        CUDA_TRY(cudaMemcpyAsync(d_ids.ptr, b->other_ids.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, s));
+        // the other batch has its own stream: its scores are complete (bt_batch_run synchronised it)
+        scatter_scores_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(d_ids.as<int32_t>(), b->other->score.as<int32_t>(),
+                                                                            cnt, b->score.as<int32_t>());
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(d_scores.alloc((size_t)(rows * k) * 4));
+    CUDA_TRY(d_cols.alloc((size_t)(rows * k) * 4));
+    topk_rows_kernel<<<(unsigned)rows, TK_THREADS, 0, s>>>(b->score.as<int32_t>(), cols, k, d_scores.as<int32_t>(),
+                                                           d_cols.as<int32_t>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(scores_out, d_scores.ptr, (size_t)(rows * k) * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(index_out, d_cols.ptr, (size_t)(rows * k) * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return BT_OK;
 }
 

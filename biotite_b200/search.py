@@ -37,8 +37,19 @@ def database_shard(db_lengths, rank, world_size):
     return int(bounds[rank]), int(bounds[rank + 1])
 
 
+def _merge_top(best, new, k):
+    """Stable merge of two ``(scores, indices)`` candidate lists per row: higher score first, equal
+    scores in the order given (callers append candidates with ascending database indices)."""
+    if best is None:
+        return new
+    scores = np.concatenate((best[0], new[0]), axis=1)
+    index = np.concatenate((best[1], new[1]), axis=1)
+    order = np.argsort(-scores.astype(np.int64), axis=1, kind="stable")[:, :k]
+    return np.take_along_axis(scores, order, axis=1), np.take_along_axis(index, order, axis=1)
+
+
 def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, terminal_penalty=True,
-                  chunk_size=100_000, db_range=None, out=None, timings=None, devices=None):
+                  chunk_size=100_000, db_range=None, out=None, timings=None, devices=None, top_k=None):
     """
     Optimal alignment score of every query against every database sequence.
 
@@ -59,10 +70,19 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
         Several GPUs of the node from this one process: the database slice is cut into
         :func:`database_shard` parts, one host thread per device scores its part into its own
         columns of the result (no exchange between devices).
+    top_k : int, optional
+        Keep only the `top_k` best database hits of every query: the selection runs on the GPU
+        chunk by chunk (``bt_batch_fetch_topk``), the score matrix is never materialised - a
+        10^3 x 10^7 search returns 8 `top_k` bytes per query instead of 40 GB.
 
     Returns
     -------
     scores : ndarray, shape=(len(queries), n_db), dtype=int32
+        Without `top_k`.
+    (scores, indices) : ndarrays, shape=(len(queries), top_k), dtype=int32
+        With `top_k`: the best scores of every query in descending order (equal scores by
+        ascending database index) and the database indices they belong to; rows are padded with
+        index -1 when the database slice holds fewer than `top_k` sequences.
     """
     _check_gap_penalty(gap_penalty)
     q = queries if hasattr(queries, "offsets") else pack_sequences(queries)
@@ -70,9 +90,17 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
     scoring = _resolve_scoring(matrix, q, d)
     begin, end = (0, len(d)) if db_range is None else (int(db_range[0]), int(db_range[1]))
     n_q, n_db = len(q), end - begin
-    scores = np.empty((n_q, n_db), dtype=np.int32) if out is None else out
-    if scores.shape != (n_q, n_db):
-        raise ValueError(f"out must have shape {(n_q, n_db)}")
+    if top_k is not None:
+        top_k = int(top_k)
+        if top_k < 1:
+            raise ValueError("top_k must be at least 1")
+        if devices is not None and len(devices) > 1:
+            raise ValueError("top_k with several devices: use search_scores_sharded (one process per GPU)")
+        scores = None
+    else:
+        scores = np.empty((n_q, n_db), dtype=np.int32) if out is None else out
+        if scores.shape != (n_q, n_db):
+            raise ValueError(f"out must have shape {(n_q, n_db)}")
     if devices is not None and len(devices) > 1:
         from . import _cabi
         lib = _cabi.load()
@@ -130,8 +158,9 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
     # one page-locked staging buffer for the chunks' scores (a pageable D2H target costs
     # more than the GPU work of small chunks)
     from . import _cabi
-    staging = _cabi.pinned_empty((n_q * min(chunk_size, max(n_db, 1)),), np.int32)
+    staging = None if top_k is not None else _cabi.pinned_empty((n_q * min(chunk_size, max(n_db, 1)),), np.int32)
     pending = {}
+    best = None
 
     device = _cabi.load().bt_get_device()
 
@@ -160,9 +189,20 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
             total_cells += batch.cells
             kernels.add(batch.kernel)
             t1 = time.perf_counter()
-            part = staging[:n_q * (hi - lo)]
-            batch.fetch(out=(part, None, None, None))
-            scores[:, lo - begin:hi - begin] = part.reshape(n_q, hi - lo)
+            if top_k is not None:
+                if getattr(batch, "kind", None) == 0:
+                    cand_scores, cand_cols = batch.top_k(top_k)
+                else:   # index-array batch (a mode outside the packed kernels): select on the host
+                    full = batch.fetch().scores.reshape(n_q, hi - lo)
+                    kk = min(top_k, hi - lo)
+                    cand_cols = np.argsort(-full.astype(np.int64), axis=1, kind="stable")[:, :kk].astype(np.int32)
+                    cand_scores = np.take_along_axis(full, cand_cols, axis=1)
+                cand_index = np.where(cand_cols >= 0, cand_cols + lo, -1).astype(np.int32)
+                best = _merge_top(best, (cand_scores, cand_index), top_k)
+            else:
+                part = staging[:n_q * (hi - lo)]
+                batch.fetch(out=(part, None, None, None))
+                scores[:, lo - begin:hi - begin] = part.reshape(n_q, hi - lo)
             t2 = time.perf_counter()
         finally:
             batch.close()
@@ -176,12 +216,20 @@ def search_scores(queries, database, matrix, gap_penalty=(-10, -1), local=True, 
         timings["device_ms"] = total_ms
         timings["cells"] = total_cells
         timings["kernel"] = "+".join(sorted(kernels))
+    if top_k is not None:
+        if best is None:
+            best = (np.zeros((n_q, 0), dtype=np.int32), np.zeros((n_q, 0), dtype=np.int32))
+        if best[0].shape[1] < top_k:   # fewer database sequences than top_k: pad
+            pad = top_k - best[0].shape[1]
+            best = (np.pad(best[0], ((0, 0), (0, pad)), constant_values=np.iinfo(np.int32).min),
+                    np.pad(best[1], ((0, 0), (0, pad)), constant_values=-1))
+        return best
     return scores
 
 
 def search_scores_sharded(queries, database, matrix, gap_penalty=(-10, -1), local=True,
                           terminal_penalty=True, chunk_size=100_000, group=None, compute=None, dst=0,
-                          timings=None):
+                          timings=None, top_k=None):
     """
     Collective call (one process per GPU, ``torch.distributed``): rank ``r`` scores all queries
     against its :func:`database_shard`; rank `dst` receives the full ``(n_queries, n_db)``
@@ -199,6 +247,21 @@ def search_scores_sharded(queries, database, matrix, gap_penalty=(-10, -1), loca
         from . import _cabi
         _cabi.check(_cabi.load().bt_set_device(int(os.environ.get("LOCAL_RANK", rank))))
         compute = search_scores
+    if top_k is not None:
+        # every rank keeps the best hits of its slice (database indices are global); the exchange
+        # is 8 top_k bytes per query and rank, merged on `dst` in rank order = ascending indices
+        from .distributed import gather_arrays
+        kw = {} if compute is not search_scores else {"timings": timings}
+        part = compute(queries, d, matrix, gap_penalty, local, terminal_penalty, chunk_size, (lo, hi), top_k=top_k, **kw)
+        n_q = part[0].shape[0]
+        both = np.concatenate((part[0].reshape(-1), part[1].reshape(-1))).astype(np.int32)
+        parts = gather_arrays(both, dst, group)
+        if rank != dst:
+            return None
+        best = None
+        for p in parts:
+            best = _merge_top(best, (p[:n_q * top_k].reshape(n_q, top_k), p[n_q * top_k:].reshape(n_q, top_k)), top_k)
+        return best
     if compute is search_scores:
         # page-locked result block: it goes back to the device for the gather at copy-engine speed
         from . import _cabi

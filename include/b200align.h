@@ -156,6 +156,15 @@ int bt_batch_create_generated(const BtParams *params, const void *codes1, const 
                               int32_t pair_kind, const int32_t *matrix, int32_t score_only,
                               BtBatch **batch_out);
 int bt_batch_fetch_score_matrix(BtBatch *batch, int32_t *matrix_out);
+/*
+ * The k best hits of every sequence of pool 1 of a BT_PAIRS_CROSS batch, selected on the device
+ * (a database scan keeps its best hits, not 4 bytes per database sequence): scores_out and
+ * index_out receive n_seq1 * k entries, row i holding the k highest scores of sequence i against
+ * pool 2 and the pool-2 indices they belong to - higher score first is the caller's sort; among
+ * equal scores the lower indices are kept; rows are in ascending index order, padded with
+ * (INT32_MIN, -1) when n_seq2 < k.
+ */
+int bt_batch_fetch_topk(BtBatch *batch, int32_t k, int32_t *scores_out, int32_t *index_out);
 int64_t bt_batch_ops_bytes(const BtBatch *batch);
 int bt_batch_run(BtBatch *batch, float *device_ms);
 int bt_batch_fetch_scores(BtBatch *batch, int32_t *scores_out);

@@ -167,3 +167,25 @@ def test_streamed_windows_planned_on_the_device_equal_the_host_planned_ones():
     ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, matrix, (-10, -1), True, False)
     assert np.array_equal(dev.scores, ref_scores)
     assert all(np.array_equal(dev.trace(k), ref_traces[k]) for k in range(0, n, 37))
+
+
+@pytest.mark.parametrize("k,chunk", [(1, 1000), (10, 333), (64, 5000), (700, 256)])
+def test_top_k_selection_on_the_device(k, chunk):
+    """search_scores(top_k=...) equals a stable descending sort of the full score matrix (many ties:
+    short sequences over four letters), including chunk seams, rows shorter than k and the pairs
+    that run on the 32-bit kernels."""
+    rng = np.random.default_rng(k)
+    q = _pool(rng, rng.integers(5, 60, 33))
+    lengths = np.concatenate((rng.integers(1, 80, 600), [0, 9000]))
+    d = PackedSequences(rng.integers(0, 4, int(lengths.sum())).astype(np.uint8),
+                        np.concatenate(([0], np.cumsum(lengths))).astype(np.int64), bt.ProteinSequence.alphabet)
+    q = PackedSequences(q.codes % 4, q.offsets, q.alphabet)
+    matrix = bt.SubstitutionMatrix.std_protein_matrix()
+    full = bt.search_scores(q, d, matrix, (-10, -1), chunk_size=chunk)
+    scores, index = bt.search_scores(q, d, matrix, (-10, -1), chunk_size=chunk, top_k=k)
+    kk = min(k, len(d))
+    order = np.argsort(-full.astype(np.int64), axis=1, kind="stable")[:, :kk]
+    assert scores.shape == (len(q), k) and index.shape == (len(q), k)
+    assert np.array_equal(index[:, :kk], order)
+    assert np.array_equal(scores[:, :kk], np.take_along_axis(full, order, axis=1))
+    assert np.all(index[:, kk:] == -1)

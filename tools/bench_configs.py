@@ -138,6 +138,27 @@ def single_pair_latencies(threads):
         cells = len(x) * len(y) if band is None else len(x) * 101
         out[name] = {"gpu_ms": gpu_ms, "cpu_port_ms": cpu_ms, "cells": cells,
                      "gcups_wall": cells / gpu_ms * 1e-6, "parity_checked": 1, "parity_ok": bool(ok)}
+    # 256 Cas9-sized pairs through the batch API: too few for the inter-sequence kernels' groups of 64
+    # pairs per warp, so the intra-pair kernels run them (one block per pair)
+    n_pairs = 256
+    len1, len2 = rng.integers(1300, 1400, n_pairs), rng.integers(1300, 1400, n_pairs)
+    off1 = np.concatenate(([0], np.cumsum(len1))).astype(np.int64)
+    off2 = np.concatenate(([0], np.cumsum(len2))).astype(np.int64)
+    codes1, codes2 = bench.draw_residues(rng, int(off1[-1])), bench.draw_residues(rng, int(off2[-1]))
+    for score_only in (False, True):
+        with bt.DeviceBatch(codes1, off1, codes2, off2, m, GAP, True, False, score_only=score_only) as batch:
+            batch.run()
+            ms = min(batch.run() for _ in range(3))
+            res = batch.fetch()
+            cells, kernel = batch.cells, batch.kernel
+        ref_scores, ref_traces = oracle.batch(codes1[:off1[16]], off1[:17], codes2[:off2[16]], off2[:17], m, GAP, True, False,
+                                              score_only=score_only, n_threads=threads)
+        ok = bool(np.array_equal(res.scores[:16], ref_scores))
+        if not score_only:
+            ok &= all(np.array_equal(res.trace(k), ref_traces[k]) for k in range(16))
+        out["cas9_256_pairs_" + ("score_only" if score_only else "traced")] = {
+            "device_ms": ms, "cells": cells, "kernel": kernel, "gcups_device": cells / ms * 1e-6,
+            "parity_checked": 16, "parity_ok": ok}
     out["workload"] = ("C1: avidin x streptavidin (README call, semi-global affine BLOSUM62); Cas9-sized 1368 x 1345 "
                        "synthetic pair (benchmark_pairwise.py shapes), global affine, and align_banded +-50; "
                        "median wall clock of the single-pair API call, CPU port on one thread beside it")
