@@ -9,8 +9,16 @@
 // so that row r of the stripe is in the band iff r <= c <= r + W - 1: the stripe visits
 // c = 0 .. R + W - 2, a parallelogram of (W + R - 1) x R cells for W x R useful ones.
 // State of the previous column (M, F1, H per row) lives in registers; the row above the
-// stripe comes from a ring buffer indexed by r0 + c (only W + R entries are ever live);
-// substitution scores come from the per-lane shared-memory table of the packed kernels.
+// stripe comes from a ring buffer indexed by r0 + c (only W + R entries are ever live) that
+// holds two values per column: H of the stripe's last row and t = 2 F2' + flag, where
+// F2' = max(M, F2 + ext) is already the vertical gap state of the row BELOW and flag says
+// that M attained it (the direction bit of that row) - the producer does the next stripe's
+// first vertical step, so 8 bytes per column cross a stripe seam instead of 12.  The entries
+// of the next BD_STAGE columns are copied to shared memory with cp.async while the current
+// column is computed: a ring entry is usually in HBM by the time it is needed again (the
+// rings of all resident warps exceed L2), and a plain load one or two columns ahead left
+// that latency exposed (the top stall site of the round-1 profile).
+// Substitution scores come from the per-lane shared-memory table of the packed kernels.
 //
 // Band semantics of the reference (banded.rs:184-214): cells outside the band are sentinels
 // (all states -inf, :474-484); cells inside the band but outside the sequences - row 0 and
@@ -40,10 +48,19 @@ constexpr int BD_THREADS = 128;
 constexpr int BD_MAX_LEN = 65535;
 constexpr int BD_MAX_W = 4096;
 constexpr int32_t BD_NEG = -(1 << 29);
+constexpr int BD_STAGE = 8;          // columns of ring look-ahead staged in shared memory
+
+__device__ __forceinline__ void bd_cp_async8(void *smem_dst, const void *gmem_src) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void bd_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bd_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct BandDesc {          // one group of 32 pairs = one warp
     int64_t dir_off;       // uint32 words
-    int64_t ring_off;      // entries (x3 planes)
+    int64_t ring_off;      // int2 entries ([slot][lane])
     int64_t rowcode_off;   // bytes
     int64_t colcode_off;   // bytes
     int64_t lastrow_off;   // int32 entries, [seq_j][lane]
@@ -128,10 +145,11 @@ banded_fill_kernel(const BandConst C, const BandArgs A) {
     const char *tbase = (const char *)btable + lane * 4;
     const uint8_t *rc = A.rowcodes + d.rowcode_off + lane;
     const uint8_t *cc = A.colcodes + d.colcode_off + lane;
-    const int ring_mask = d.ring - 1;
-    int32_t *rg_m = A.ring + d.ring_off * 3 + lane;   // planes [slot][lane]: M, F2, H
-    int32_t *rg_f = rg_m + (int64_t)d.ring * 32;
-    int32_t *rg_h = rg_f + (int64_t)d.ring * 32;
+    const int ring = d.ring;
+    int2 *const rg = (int2 *)A.ring + d.ring_off + lane;   // [slot][lane]: {H, t} of the stripe's last row
+    // this lane's staging slots: [column & (BD_STAGE - 1)][lane] behind the score table
+    int2 *const stage = (int2 *)(btable + C.n_rows * C.n_cols * 32) + (threadIdx.x >> 5) * (BD_STAGE * 32) + lane;
+    const int32_t T_NEG = 2 * BD_NEG + 1;                  // t of a sentinel above: F2' = -inf, "M attains it"
     uint2 *dir = TRACED ? (uint2 *)(A.dirs + d.dir_off) + lane : nullptr;
     int32_t *lastrow = A.lastrow + d.lastrow_off + lane;
     int32_t *lastcol = A.lastcol + d.lastcol_off + lane;
@@ -161,46 +179,53 @@ banded_fill_kernel(const BandConst C, const BandArgs A) {
             const bool inb = cb >= r && cb - r <= W - 1;
             Ml[r] = inb ? 0 : NEG; F1l[r] = NEG; Hl[r] = inb ? 0 : NEG;
         }
-        // row above the stripe at column c: table row 0 (all edge, banded.rs:184) for the
-        // first stripe, else the ring; in band iff c <= W - 2
-        auto above = [&](int c, int32_t &um, int32_t &uf, int32_t &uh) {
-            // the row above is in the band iff -1 <= c <= W - 2; inside the band it is an edge
-            // cell when it is table row 0 or lies left of the sequence, else the previous
-            // stripe's last row (ring).  Out-of-band columns may never have been visited by the
-            // previous stripe, so they are synthesised, not read.
+        // row above the stripe at column c: in the band iff -1 <= c <= W - 2; inside the band it is
+        // an edge cell (M = H = 0, gaps -inf: F2' = 0 opened from M) when it is table row 0 or lies
+        // left of the sequence (banded.rs:184), else the previous stripe's last row (ring).
+        // Out-of-band columns may never have been visited by the previous stripe, so they are
+        // synthesised, not read.  Returns true when (uh, ut) are synthesised.
+        auto synth = [&](int c, int32_t &uh, int32_t &ut) -> bool {
             const bool inb = c >= -1 && c <= W - 2;
-            if (!inb) { um = NEG; uf = NEG; uh = NEG; }
-            else if (s == 0 || base_j + c < 0) { um = 0; uf = NEG; uh = 0; }
-            else {
-                const int slot = (r0 + c) & ring_mask;
-                um = rg_m[(int64_t)slot * 32]; uf = rg_f[(int64_t)slot * 32]; uh = rg_h[(int64_t)slot * 32];
-            }
+            if (!inb) { uh = NEG; ut = T_NEG; return true; }
+            if (s == 0 || base_j + c < 0) { uh = 0; ut = 1; return true; }
+            return false;
         };
         int32_t hu_prev;
-        { int32_t t0, t1; above(c_first - 1, t0, t1, hu_prev); }
+        {
+            int32_t t0;
+            if (!synth(c_first - 1, hu_prev, t0)) hu_prev = rg[(int64_t)((r0 + c_first - 1) % ring) * 32].x;
+        }
         auto col_code = [&](int c) -> uint32_t {
             const int sjc = min(max(base_j + c, 0), d.mmax - 1);
             return cc[(int64_t)sjc * 32];
         };
-        // The row above and the column letters are fetched BD_PF columns ahead; the column loop is
-        // unrolled BD_PF times so that the look-ahead registers need no rotation (a register
-        // move would wait for the load it forwards - the top stall site before).
-        int32_t q_m[BD_PF], q_f[BD_PF], q_h[BD_PF];
+        // ring slots of the column being written and of the column being staged
+        int w_slot = (r0 + c_first) % ring, pf_slot = w_slot, pf_c = c_first;
+        auto stage_next = [&]() {       // asynchronous copy of the ring entry of column pf_c; one group per column
+            int32_t a, b;
+            if (pf_c <= c_last && !synth(pf_c, a, b)) bd_cp_async8(stage + (pf_c & (BD_STAGE - 1)) * 32, rg + (int64_t)pf_slot * 32);
+            bd_cp_async_commit();
+            pf_c++;
+            if (++pf_slot == ring) pf_slot = 0;
+        };
+#pragma unroll
+        for (int k = 0; k < BD_STAGE - 1; k++) stage_next();
+        // the column letters are fetched BD_PF columns ahead
         uint32_t q_code[BD_PF];
 #pragma unroll
-        for (int k = 0; k < BD_PF; k++) {
-            q_m[k] = q_f[k] = q_h[k] = NEG; q_code[k] = 0;
-            if (c_first + k <= c_last) { above(c_first + k, q_m[k], q_f[k], q_h[k]); q_code[k] = col_code(c_first + k); }
-        }
+        for (int k = 0; k < BD_PF; k++) q_code[k] = c_first + k <= c_last ? col_code(c_first + k) : 0;
         for (int c0 = c_first; c0 <= c_last; c0 += BD_PF) {
 #pragma unroll
         for (int u = 0; u < BD_PF; u++) {
             const int c = c0 + u;
             if (u > 0 && c > c_last) break;
-            int32_t up_m = q_m[u], up_f2 = q_f[u];
-            const int32_t hu = q_h[u];
+            stage_next();                               // column c + BD_STAGE - 1
+            bd_cp_async_wait<BD_STAGE - 1>();           // the group of column c has landed
+            int32_t hu, ut;
+            if (!synth(c, hu, ut)) { const int2 v = stage[(c & (BD_STAGE - 1)) * 32]; hu = v.x; ut = v.y; }
+            int32_t up_m = 0, up_f2 = ut >> 1;          // F2 of the stripe's first row: done by the row above
             const uint32_t code = q_code[u];
-            if (c + BD_PF <= c_last) { above(c + BD_PF, q_m[u], q_f[u], q_h[u]); q_code[u] = col_code(c + BD_PF); }
+            if (c + BD_PF <= c_last) q_code[u] = col_code(c + BD_PF);
             const int sj = base_j + c;
             const char *t_col = tbase + code * col_stride;
             uint32_t acc0 = 0, acc1 = 0;   // nibbles of rows 0-7 and 8-15
@@ -229,7 +254,12 @@ banded_fill_kernel(const BandConst C, const BandArgs A) {
                     const int32_t fv = up_f2 + ext;
                     if (TRACED) {
                         int32_t t;
-                        if (r < 8) {
+                        if (r == 0) {
+                            acc0 += (uint32_t)(ut & 1) << 3;
+                            BD_MAX_PRED(t, F1l[r], up_f2, acc0, BD_BIT(r, 1));
+                            const int32_t to = t + open;
+                            BD_MAX_PRED(Hl[r], Ml[r], to, acc0, BD_BIT(r, 0));
+                        } else if (r < 8) {
                             BD_MAX_PRED(up_f2, up_m, fv, acc0, BD_BIT(r, 3));
                             BD_MAX_PRED(t, F1l[r], up_f2, acc0, BD_BIT(r, 1));
                             const int32_t to = t + open;
@@ -241,7 +271,7 @@ banded_fill_kernel(const BandConst C, const BandArgs A) {
                             BD_MAX_PRED(Hl[r], Ml[r], to, acc1, BD_BIT(r, 0));
                         }
                     } else {
-                        up_f2 = max(up_m, fv);
+                        if (r > 0) up_f2 = max(up_m, fv);
                         Hl[r] = __viaddmax_s32(max(F1l[r], up_f2), open, Ml[r]);
                     }
                     up_m = Ml[r];
@@ -257,7 +287,8 @@ banded_fill_kernel(const BandConst C, const BandArgs A) {
                     int32_t mcell = diag + sim[r];
                     uint32_t bits = 0;
                     BD_MAX_PRED(f1, Ml[r], fe, bits, 4u);
-                    BD_MAX_PRED(f2, up_m, fv, bits, 8u);
+                    if (r == 0) { f2 = up_f2; bits += (uint32_t)(ut & 1) << 3; }
+                    else { BD_MAX_PRED(f2, up_m, fv, bits, 8u); }
                     BD_MAX_PRED(t, f1, f2, bits, 2u);
                     const int32_t to = t + open;
                     BD_MAX_PRED(h, mcell, to, bits, 1u);
@@ -273,8 +304,10 @@ banded_fill_kernel(const BandConst C, const BandArgs A) {
             hu_prev = hu;
             // the stripe's last row feeds the next stripe (forced values included)
             {
-                const int slot = (r0 + c) & ring_mask;
-                rg_m[(int64_t)slot * 32] = up_m; rg_f[(int64_t)slot * 32] = up_f2; rg_h[(int64_t)slot * 32] = Hl[BD_R - 1];
+                const int32_t fvn = up_f2 + ext;
+                const int32_t tn = 2 * max(up_m, fvn) + (up_m >= fvn ? 1 : 0);
+                rg[(int64_t)w_slot * 32] = make_int2(Hl[BD_R - 1], tn);
+                if (++w_slot == ring) w_slot = 0;
             }
             if (TRACED) dir[((int64_t)s * d.cw + c) * 32] = make_uint2(acc0, acc1);
             // end candidates (banded.rs:598-638): H along the last row and the last column
@@ -536,8 +569,7 @@ inline int banded_prepare(BandedPlan &plan, const BtParams &P, const PairMap &hm
         d.nmax = nmax; d.mmax = mmax; d.wmax = wmax;
         d.stripes = (nmax + BD_R - 1) / BD_R;
         d.cw = BD_R + wmax - 1;
-        int ring = 32;
-        while (ring < BD_R + wmax + 2) ring <<= 1;
+        const int ring = (BD_R + wmax + 2 + 7) / 8 * 8;   // live entries of a stripe seam, no power of two needed
         d.ring = ring;
         const int64_t dir_words = score_only ? 0 : (int64_t)d.stripes * d.cw * 64;
         if (win.group_begin < g && (win.dir_words + dir_words > dir_budget_words || g - win.group_begin >= groups_per_window)) close(g);
@@ -558,7 +590,7 @@ inline int banded_prepare(BandedPlan &plan, const BtParams &P, const PairMap &hm
     if ((e = plan.d_desc.alloc(plan.desc.size() * sizeof(BandDesc))) != cudaSuccess) goto fail;
     if ((e = plan.rowcodes.alloc((size_t)max_rowc)) != cudaSuccess) goto fail;
     if ((e = plan.colcodes.alloc((size_t)max_colc)) != cudaSuccess) goto fail;
-    if ((e = plan.ring.alloc((size_t)max_ring * 12)) != cudaSuccess) goto fail;
+    if ((e = plan.ring.alloc((size_t)max_ring * 8)) != cudaSuccess) goto fail;
     if ((e = plan.dirs.alloc((size_t)max_dir * 4)) != cudaSuccess) goto fail;
     if ((e = plan.lastrow.alloc((size_t)max_lr * 4)) != cudaSuccess) goto fail;
     if ((e = plan.lastcol.alloc((size_t)max_lc * 4)) != cudaSuccess) goto fail;
@@ -592,7 +624,8 @@ inline cudaError_t banded_fill_window(BandedPlan &plan, const BandWindow &win, c
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     (*launches)++;
-    const size_t smem = (size_t)plan.C.n_rows * plan.C.n_cols * 128;
+    // score table (one copy per lane) + the ring staging slots of the block's warps
+    const size_t smem = (size_t)plan.C.n_rows * plan.C.n_cols * 128 + (size_t)(BD_THREADS / 32) * BD_STAGE * 32 * 8;
     const unsigned grid = (unsigned)((A.n_groups + BD_THREADS / 32 - 1) / (BD_THREADS / 32));
     if (plan.C.score_only) {
         e = cudaFuncSetAttribute(banded_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
