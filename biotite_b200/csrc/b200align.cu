@@ -77,9 +77,9 @@ extern "C" int bt_get_device(void) {
     return d;
 }
 
-extern "C" void *bt_pinned_alloc(size_t bytes) {
+static void *pinned_alloc(size_t bytes, unsigned flags) {
     void *p = nullptr;
-    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, flags);
     if (e != cudaSuccess) {
         cudaGetLastError();
         fail(BT_ERR_OOM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
@@ -87,6 +87,8 @@ extern "C" void *bt_pinned_alloc(size_t bytes) {
     }
     return p;
 }
+extern "C" void *bt_pinned_alloc(size_t bytes) { return pinned_alloc(bytes, cudaHostAllocDefault); }
+extern "C" void *bt_pinned_alloc_input(size_t bytes) { return pinned_alloc(bytes, cudaHostAllocWriteCombined); }
 extern "C" void bt_pinned_free(void *ptr) {
     if (ptr) cudaFreeHost(ptr);
 }
@@ -272,7 +274,9 @@ static cudaError_t dispatch_general_traceback(const DevParams &D, const BatchVie
     if (D.dir_pad) {
         // padded tables (wavefront route): one warp per pair walks a cached tile
         const int grid = (int)((count + 3) / 4);
-        if (D.affine) {
+        if (D.lean) {
+            wavefront_traceback_kernel<true, false, true><<<grid, 128, 0, s>>>(D, V);
+        } else if (D.affine) {
             if (D.banded) wavefront_traceback_kernel<true, true><<<grid, 128, 0, s>>>(D, V);
             else wavefront_traceback_kernel<true, false><<<grid, 128, 0, s>>>(D, V);
         } else {

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -65,7 +66,7 @@ public:
 private:
     std::mutex mutex_;
     std::map<std::pair<int, size_t>, std::vector<void *>> free_;
-    size_t cached_bytes_ = 0;
+    std::atomic<size_t> cached_bytes_{0};
 };
 
 // Page-locked host staging buffers, cached the same way (cudaHostAlloc costs milliseconds).

@@ -11,21 +11,25 @@
 //
 //   * affine 3-state recurrence (pairwise.rs:608-681) on full tables, 8-bit codes, matrix scoring;
 //     every other mode stays on wavefront_fill_kernel;
-//   * scores are carried scaled by 8 with the state in the low bits - M' = 8 M + 7,
-//     G1' = 8 G1 + 6, G2' = 8 G2 + 4 - so that H' = max3(M', G1', G2') (one VIMNMX3) is the
-//     best state's score AND, in its low three bits, exactly the direction bits
-//     A_MM | A_G1M | A_G2M (7), A_G1M | A_G2M (6) or A_G2M (4) the next diagonal cell stores:
-//     ties resolve M > G1 > G2 as the reference's first-optimal walk does (cell.rs:219-254);
-//   * the gap states are two adds and a maximum each; the "opened from M" bit is one compare, and
-//     the vertical one is computed by the row above (Strip2), so two values cross a lane boundary;
-//   * the byte holds the first-priority choice plus the lower-priority bits below it, which the
-//     first-optimal walk never reaches: the trace of index 0 (trace.rs:59-90) is identical to the
-//     one the full tie sets give, which is all a batch (max_number = 1) returns.  Callers that
-//     enumerate co-optimal traces (max_number > 1) keep the full-set kernel;
+//   * scores are carried scaled by 32 with the state and the gap flags in the low five bits:
+//         M'  = 32 M  + 0x1f            (state tag 7 in bits 2-4)
+//         G1' = 32 G1 + 0x18 + f1       (tag 6; f1 = 1: opened from M, ties included)
+//         G2' = 32 G2 + 0x10 + 2 f2     (tag 4; f2 likewise in bit 1)
+//     so that every maximum says by itself which candidate won, with the reference's priorities
+//     (cell.rs:219-254: Match from M before G1 before G2, a gap opened from M before it is
+//     extended): H' = max3(M', G1', G2') is one VIMNMX3 whose bits 2-4 are the state the next
+//     diagonal cell comes from, G1' = max(M' + 32 open - 6, (G1' & ~1) + 32 ext) carries f1, the
+//     vertical state likewise.  No compare, no select: the direction byte of a cell is two LOP3 -
+//     bits 2-4 of the diagonal H', bit 0 of G1', bit 1 of G2' (bits 5-7 are not defined) - a
+//     layout of its own that wavefront_traceback_kernel<.., LEAN = true> decodes; the walk
+//     (trace.rs:59-90 with max_number = 1) is the reference's.  Callers that enumerate co-optimal
+//     traces (max_number > 1) keep the full-set kernel and the reference's byte layout;
+//   * the vertical gap state of the row below is computed by the row above (Strip2), so two
+//     values cross a lane / stripe boundary;
 //   * local mode clamps M only: a gap state <= 0 can never win a maximum or be walked into when
 //     gap penalties are <= 0, so leaving it unclamped changes no score and no visited byte.
 //
-// Exact while 8 |value| stays far from 2^29 (checked by the router: strip_eligible).
+// Exact while 32 |value| stays far from 2^29 (checked by the router: strip_eligible).
 #pragma once
 #include "common.cuh"
 #include "general_kernel.cuh"
@@ -37,17 +41,17 @@ constexpr int SK_CHUNK = 16;                  // steps between progress updates 
 constexpr int32_t SK_NEG = -(1 << 29);        // "minus infinity" of the scaled scores
 
 // What the row below needs of a cell (i, j): h = H'(i, j) (diagonal input of (i + 1, j + 1)) and
-// t = G2'(i + 1, j) = max(M'(i, j) + 8 open - 3, G2'(i, j) + 8 ext) with bit 0 set when the gap
-// was opened from M (ties included): the vertical recurrence of the row below, done by the
-// producer, so that two values cross a lane / stripe boundary instead of three.
+// t = G2'(i + 1, j) = max(M'(i, j) + 32 open - 13, (G2'(i, j) & ~2) + 32 ext), flag included: the
+// vertical recurrence of the row below, done by the producer, so that two values cross a lane /
+// stripe boundary instead of three.
 struct Strip2 { int32_t h, t; };
 
 // row 0 of the table (pairwise.rs:747-780) as seen from row 1
 __device__ __forceinline__ Strip2 sk_row0(const DevParams &P, int j, int32_t o2c, int32_t e2c) {
     Strip2 c;
-    if (j == 0) { c.h = 7; c.t = (7 + o2c) | 1; return c; }       // M(0, 0) = 0: G2(1, 0) opens from it
-    c.h = (P.local || !P.terminal) ? 6 : 8 * (P.gap_open + (j - 1) * P.gap_ext) + 6;
-    c.t = (SK_NEG + o2c) | 1;                                     // M(0, j) = G2(0, j) = -inf
+    if (j == 0) { c.h = 0x1f; c.t = 0x1f + o2c; return c; }        // M(0, 0) = 0: G2(1, 0) opens from it
+    c.h = (P.local || !P.terminal) ? 0x18 : 32 * (P.gap_open + (j - 1) * P.gap_ext) + 0x18;
+    c.t = SK_NEG + 0x1f + o2c;                                    // M(0, j) = G2(0, j) = -inf
     return c;
 }
 
@@ -68,29 +72,26 @@ strip_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
     const int64_t o1 = V.map.beg1(p), o2 = V.map.beg2(p);
     const int n = (int)V.map.len1(p), m = (int)V.map.len2(p);
     const int64_t rs = table_stride(1, (int64_t)m + 1);
+    const uint32_t rs32 = (uint32_t)rs;           // m < 2^30 (checked by the router)
     uint8_t *const dir = TRACED ? V.dirs + V.dir_off[p] : nullptr;
 
-    // shared memory: [matrix, scaled by 8] [boundary slots]
+    // shared memory: [matrix, scaled by 32] [boundary slots]
     int32_t *const mat8 = wf_smem;
     const int mat_n = P.n_rows * P.n_cols;
-    for (int k = tid; k < mat_n; k += nthr) mat8[k] = V.matrix[k] * 8;
+    for (int k = tid; k < mat_n; k += nthr) mat8[k] = V.matrix[k] * 32;
     volatile int32_t *const bnd = W_.bnd ? W_.bnd + (int64_t)blockIdx.x * W_.bnd_block : wf_smem + mat_n;
     const int bnd_cols = W_.bnd_cols;
     if (tid < WF_MAX_WARPS) prog[tid] = 0ull;
-    if (TRACED) {
-        // table row 0: leading gap in sequence 1 (pairwise.rs:747-780); local: no directions
-        for (int j = tid; j < (int)rs; j += nthr)
-            dir[j] = (uint8_t)((j == 0 || j > m || LOCAL) ? 0 : (j == 1 ? A_MG1 : A_G1G1));
-    }
+    // (table row 0 and column 0 need no direction bytes: the lean traceback walks the borders by rule)
     __syncthreads();
 
-    const int32_t open8 = 8 * P.gap_open, ext8 = 8 * P.gap_ext;
+    const int32_t open8 = 32 * P.gap_open, ext8 = 32 * P.gap_ext;
     const int n_stripes = (n + ROWS - 1) / ROWS;
     const int lane_cols = (m | 3) + 1;            // table columns 0 .. (m | 3): whole direction words
     const int n_steps = 31 + lane_cols;
     const uint8_t *const codes1 = (const uint8_t *)V.codes1 + o1;
     const uint8_t *const codes2 = (const uint8_t *)V.codes2 + o2;
-    int32_t best = 7;                              // local: first maximum in row-major order, M'(0, 0) = 7
+    int32_t best = 0x1f;                           // local: first maximum in row-major order, M'(0, 0) = 0x1f
     int best_i = 0, best_j = 0;
 
     for (int q = warp; q < n_stripes; q += nw) {
@@ -109,7 +110,7 @@ strip_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
             rowmat[r] = mat8 + (i <= n ? (int)codes1[i - 1] : 0) * P.n_cols;
             M[r] = G1[r] = H[r] = SK_NEG;
             simn[r] = 0; dw[r] = 0;
-            rbest[r] = 7; rcol[r] = 0;
+            rbest[r] = 0x1f; rcol[r] = 0;
         }
         // the last row of the table inside this lane (semi-global: its horizontal steps are free)
         const int r_last = (SEMI && n >= i0 && n < i0 + R) ? n - i0 : -1;
@@ -129,7 +130,7 @@ strip_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
         fetch_sims(0);
         auto above = [&](int j) -> Strip2 {        // cell (base, j): the row above the stripe
             if (j < 0 || j > m) return Strip2{SK_NEG, SK_NEG};
-            const int32_t o2c = ((SEMI && j == m) ? 0 : open8) - 3, e2c = (SEMI && j == m) ? 0 : ext8;
+            const int32_t o2c = ((SEMI && j == m) ? 0 : open8) - 13, e2c = (SEMI && j == m) ? 0 : ext8;
             if (base == 0) return sk_row0(P, j, o2c, e2c);
             Strip2 c;
             c.h = bnd_in[(int64_t)j * NS]; c.t = bnd_in[(int64_t)j * NS + 1];
@@ -141,9 +142,14 @@ strip_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
             if (q > 0) {
                 if (lane == 0) {
                     const unsigned long long want = want_tag | (unsigned long long)(k0 + SK_CHUNK - 1 + 32);
-                    const volatile unsigned long long *flag = &prog[(q - 1) % nw];
-                    while (*flag < want) __nanosleep(100);
-                    __threadfence_block();
+                    // acquire: the producer's boundary entries are visible once its counter is
+                    const uint32_t flag = (uint32_t)__cvta_generic_to_shared(&prog[(q - 1) % nw]);
+                    for (;;) {
+                        unsigned long long seen;
+                        asm volatile("ld.acquire.cta.shared.u64 %0, [%1];" : "=l"(seen) : "r"(flag) : "memory");
+                        if (seen >= want) break;
+                        __nanosleep(100);
+                    }
                 }
                 __syncwarp();
             }
@@ -162,45 +168,43 @@ strip_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
                 for (int r = 0; r < R; r++) sim[r] = simn[r];
                 if (k + 1 < n_steps) fetch_sims(k + 1);
                 if (j >= 1 && j <= m) {
-                    // vertical step: M' + 8 open - 3 (state bits 7 -> 4), G2' + 8 ext; waived in the last column
-                    const int32_t o2c = ((SEMI && j == m) ? 0 : open8) - 3, e2c = (SEMI && j == m) ? 0 : ext8;
+                    // vertical step: M' + 32 open - 13 (tag 7 -> 4, flag bit 1), G2' + 32 ext; waived in the last column
+                    const int32_t o2c = ((SEMI && j == m) ? 0 : open8) - 13, e2c = (SEMI && j == m) ? 0 : ext8;
                     int32_t dh = diag_h, t = up_t;
 #pragma unroll
                     for (int r = 0; r < R; r++) {
-                        int32_t mn = (dh | 7) + sim[r];
-                        uint32_t byte = (uint32_t)dh & 7u;
+                        int32_t mn = (dh | 0x1f) + sim[r];
+                        int32_t msrc = dh;                            // bits 2-4: where M comes from
                         if (LOCAL) {
-                            if (mn <= 7) { mn = 7; byte = 0; }       // M <= 0: trace ends here (pairwise.rs:661-666)
+                            if (mn <= 0x1f) { mn = 0x1f; msrc = 0; }  // M <= 0: trace ends here (pairwise.rs:661-666)
                         }
-                        // horizontal step: M' + 8 open - 1 (state bits 7 -> 6), G1' + 8 ext; free in the last row
+                        // horizontal step: M' + 32 open - 6 (tag 7 -> 6, flag bit 0), G1' + 32 ext; free in the last row
                         const bool free1 = SEMI && r == r_last;
-                        const int32_t a1 = M[r] + (free1 ? -1 : open8 - 1), b1 = G1[r] + (free1 ? 0 : ext8);
-                        const int32_t g1 = max(a1, b1);
-                        byte |= a1 >= b1 ? (uint32_t)(A_MG1 | A_G1G1) : (uint32_t)A_G1G1;
-                        byte |= (t & 1) ? (uint32_t)(A_MG2 | A_G2G2) : (uint32_t)A_G2G2;
-                        const int32_t g2 = t & ~1;
+                        const int32_t g1 = max(M[r] + (free1 ? -6 : open8 - 6), (G1[r] & ~1) + (free1 ? 0 : ext8));
+                        const int32_t g2 = t & ~2;
                         const int32_t h = __vimax3_s32(mn, g1, g2);
+                        if (TRACED) {
+                            // bit 0: G1 opened, bit 1: G2 opened, bits 2-4: source of M; bits 5-7 undefined
+                            const uint32_t byte = (((uint32_t)g1 & ~2u) | ((uint32_t)t & 2u)) & ~0x1cu | ((uint32_t)msrc & 0x1cu);
+                            dw[r] = __byte_perm(dw[r], byte, 0x4321);
+                        }
                         // G2' of the row below in this column
-                        const int32_t a2 = mn + o2c, b2 = g2 + e2c;
-                        t = max(a2, b2) | (a2 >= b2 ? 1 : 0);
+                        t = max(mn + o2c, g2 + e2c);
                         dh = H[r];
                         M[r] = mn; G1[r] = g1; H[r] = h;
                         if (LOCAL) { if (mn > rbest[r]) { rbest[r] = mn; rcol[r] = j; } }
-                        if (TRACED) dw[r] = __byte_perm(dw[r], byte, 0x4321);
                     }
                     last_t = t;
                 } else if (j == 0) {
                     // table column 0 (pairwise.rs:707-745): leading gap in sequence 2
-                    const int32_t e2c = (SEMI && m == 0) ? 0 : ext8;
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const int i = i0 + r;
                         M[r] = SK_NEG; G1[r] = SK_NEG;
-                        H[r] = (LOCAL || !P.terminal) ? 4 : 8 * (P.gap_open + (i - 1) * P.gap_ext) + 4;
-                        const uint32_t byte = LOCAL ? 0u : (i == 1 ? (uint32_t)A_MG2 : (uint32_t)A_G2G2);
-                        if (TRACED) dw[r] = __byte_perm(dw[r], byte, 0x4321);
+                        H[r] = (LOCAL || !P.terminal) ? 0x10 : 32 * (P.gap_open + (i - 1) * P.gap_ext) + 0x10;
+                        if (TRACED) dw[r] = __byte_perm(dw[r], 0u, 0x4321);
                     }
-                    last_t = H[R - 1] + e2c;        // G2(i + 1, 0) extends G2(i, 0): never read (column 0 is closed-form)
+                    last_t = H[R - 1];              // never read: column 0 of the row below is closed-form too
                 } else if (j > m && j < lane_cols) {
                     if (TRACED) {
 #pragma unroll
@@ -208,15 +212,17 @@ strip_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
                     }
                 }
                 if (TRACED && (j & 3) == 3 && (unsigned)j < (unsigned)lane_cols) {
-                    // four columns of every row as one word; rows below the table have no storage
+                    // four columns of every row as one word; rows below the table have no storage.
+                    // (Because of the lane skew a quarter of the lanes stores at every step: the
+                    // address is one 32 x 32 + 64 bit multiply-add per row.)
                     uint8_t *const at = dir_lane + (j - 3);
                     if (rows_in) {
 #pragma unroll
-                        for (int r = 0; r < R; r++) *(uint32_t *)(at + (int64_t)r * rs) = dw[r];
+                        for (int r = 0; r < R; r++) *(uint32_t *)(at + (uint32_t)r * rs32) = dw[r];
                     } else {
 #pragma unroll
                         for (int r = 0; r < R; r++)
-                            if (r < rows_here) *(uint32_t *)(at + (int64_t)r * rs) = dw[r];
+                            if (r < rows_here) *(uint32_t *)(at + (uint32_t)r * rs32) = dw[r];
                     }
                 }
                 diag_h = up_h;
@@ -228,9 +234,11 @@ strip_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
             if (q + 1 < n_stripes) {
                 __syncwarp();
                 if (lane == 31) {
-                    __threadfence_block();
-                    *(volatile unsigned long long *)&prog[q % nw] =
+                    // release: the lane's boundary entries are visible before the counter says so
+                    const unsigned long long done =
                         ((unsigned long long)q << 32) | (unsigned long long)(k1 >= n_steps ? 0xffffffffu : (unsigned)k1);
+                    const uint32_t flag = (uint32_t)__cvta_generic_to_shared(&prog[q % nw]);
+                    asm volatile("st.release.cta.shared.u64 [%0], %1;" ::"r"(flag), "l"(done) : "memory");
                 }
             }
         }
@@ -241,10 +249,11 @@ strip_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
             for (int r = 0; r < R; r++) {
                 if (i0 + r != n) continue;
                 const int32_t h = H[r];
-                V.score[p] = h >> 3;
+                const int tag = (h >> 2) & 7;
+                V.score[p] = h >> 5;
                 V.start_idx[p] = (int64_t)n * rs + m;
-                V.start_state[p] = (h & 7) == 7 ? ST_MATCH : ((h & 7) == 6 ? ST_GAP1 : ST_GAP2);
-                V.end_vals[3 * p] = M[r] >> 3; V.end_vals[3 * p + 1] = G1[r] >> 3; V.end_vals[3 * p + 2] = h >> 3;
+                V.start_state[p] = tag == 7 ? ST_MATCH : (tag == 6 ? ST_GAP1 : ST_GAP2);
+                V.end_vals[3 * p] = M[r] >> 5; V.end_vals[3 * p + 1] = G1[r] >> 5; V.end_vals[3 * p + 2] = h >> 5;
             }
         }
         if (LOCAL) {
@@ -269,10 +278,10 @@ strip_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
         __syncthreads();
         if (tid == 0) {
             for (int k = 1; k < nw; k++) bb.offer(red_score[k], red_idx[k]);
-            V.score[p] = bb.score >> 3;
+            V.score[p] = bb.score >> 5;
             V.start_idx[p] = bb.idx;
             V.start_state[p] = ST_MATCH;
-            V.end_vals[3 * p] = bb.score >> 3; V.end_vals[3 * p + 1] = P.neg_inf; V.end_vals[3 * p + 2] = P.neg_inf;
+            V.end_vals[3 * p] = bb.score >> 5; V.end_vals[3 * p + 1] = P.neg_inf; V.end_vals[3 * p + 2] = P.neg_inf;
         }
     } else if (tid == 0 && (n == 0 || m == 0)) {
         // the end cell lies on the table's border (closed forms of wavefront_kernel.cuh)
@@ -292,7 +301,7 @@ inline bool strip_eligible(const BtParams &P, int64_t max_span, int32_t min_scor
     if ((int64_t)P.n_rows * P.n_cols > 4096) return false;
     const int64_t step = std::max<int64_t>({std::abs((int64_t)min_score), std::abs((int64_t)max_score),
                                             std::abs((int64_t)P.gap_open), std::abs((int64_t)P.gap_ext)});
-    return step * (max_span + 4) < (1ll << 24);
+    return step * (max_span + 4) < (1ll << 22);
 }
 
 }  // namespace bt

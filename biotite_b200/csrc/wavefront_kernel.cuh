@@ -535,7 +535,11 @@ wavefront_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
 // ---------------------------------------------------------------------------------------
 constexpr int WT_ROWS = 32, WT_COLS = 128;
 
-template <bool AFFINE, bool BANDED>
+// LEAN: the table was written by strip_fill_kernel (strip_kernel.cuh): bit 0 = Gap1 opened from
+// Match, bit 1 = Gap2 opened from Match, bits 2-4 = state the Match value came from (7 Match,
+// 6 Gap1, 4 Gap2, 0: the local alignment starts here), no bytes for table row 0 / column 0, which
+// are walked by rule (pairwise.rs:707-780: a leading gap down to the origin; local: the end).
+template <bool AFFINE, bool BANDED, bool LEAN = false>
 __global__ void __launch_bounds__(128)
 wavefront_traceback_kernel(const DevParams P, const BatchView V) {
     __shared__ uint4 tiles[4][WT_ROWS * WT_COLS / 16];
@@ -577,7 +581,20 @@ wavefront_traceback_kernel(const DevParams P, const BatchView V) {
                 if (i < ti || j < tj || j >= tj + WT_COLS) { leave = 1; break; }
                 const uint32_t d = tile[(i - ti) * WT_COLS + (j - tj)];
                 int op, ns = 0;
-                if (AFFINE) {
+                if (LEAN) {
+                    if (i == 0 || j == 0) {
+                        if (P.local || (i == 0 && j == 0)) { leave = 2; break; }
+                        if (i == 0) { op = OP_TO1; ns = ST_GAP1; } else { op = OP_TO2; ns = ST_GAP2; }
+                    } else if (st == ST_MATCH) {
+                        const uint32_t tag = (d >> 2) & 7u;
+                        if (tag == 0) { leave = 2; break; }
+                        op = OP_DIAG; ns = tag == 7u ? ST_MATCH : (tag == 6u ? ST_GAP1 : ST_GAP2);
+                    } else if (st == ST_GAP1) {
+                        op = OP_TO1; ns = (d & 1u) ? ST_MATCH : ST_GAP1;
+                    } else {
+                        op = OP_TO2; ns = (d & 2u) ? ST_MATCH : ST_GAP2;
+                    }
+                } else if (AFFINE) {
                     if (st == ST_MATCH) {
                         if (d & A_MM) { op = OP_DIAG; ns = ST_MATCH; }
                         else if (d & A_G1M) { op = OP_DIAG; ns = ST_GAP1; }
