@@ -204,8 +204,6 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU (config 2: 10^6)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--wc-inputs", action="store_true",
-                    help="end-to-end inputs in write-combined page-locked memory (bt_pinned_alloc_input)")
     ap.add_argument("--configs", default="all", choices=["all", "none"],
                     help="also run C1 / Cas9 latencies, C3, C4, C5 (JSON key `configs`)")
     ap.add_argument("--c3-db", type=int, default=200_000, help="database sequences of the C3 entry")
@@ -232,7 +230,6 @@ def main():
         "global_pairs": args.pairs * world,
         "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective",
         "l2": "inputs + direction store far larger than the 126 MB L2, no explicit flush needed",
-        "e2e_input_memory": "page-locked, write-combined" if args.wc_inputs else "page-locked",
     }
 
     import biotite_b200 as bt
@@ -309,9 +306,8 @@ def main():
 
     codes1, off1, codes2, off2 = make_c2(args.pairs, seed=rank)
     # pinned host staging for the end-to-end path
-    wc = bool(args.wc_inputs)
-    p_codes1 = _cabi.pinned_empty(codes1.shape, np.uint8, input_only=wc); p_codes1[:] = codes1
-    p_codes2 = _cabi.pinned_empty(codes2.shape, np.uint8, input_only=wc); p_codes2[:] = codes2
+    p_codes1 = _cabi.pinned_empty(codes1.shape, np.uint8); p_codes1[:] = codes1
+    p_codes2 = _cabi.pinned_empty(codes2.shape, np.uint8); p_codes2[:] = codes2
     p_off1 = _cabi.pinned_empty(off1.shape, np.int64); p_off1[:] = off1
     p_off2 = _cabi.pinned_empty(off2.shape, np.int64); p_off2[:] = off2
     n = args.pairs

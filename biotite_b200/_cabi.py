@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "bt_batch_fetch_traces", "bt_batch_fetch_cigar", "bt_batch_fetch_gapped", "bt_batch_timings", "bt_microbench", "bt_batch_cells", "bt_batch_launches", "bt_batch_kernel",
     "bt_batch_destroy", "bt_align_batch", "bt_xdrop_regions", "bt_debug_plan", "bt_expand_traces", "bt_pinned_alloc",
     "bt_pinned_free", "bt_pool_trim", "bt_ops2_capacity", "bt_align_batch_compact", "bt_expand_traces2", "bt_align_batch_multi", "bt_batch_windows",
-    "bt_batch_create_generated", "bt_batch_fetch_score_matrix", "bt_debug_device_plan", "bt_batch_fetch_topk", "bt_pinned_alloc_input",
+    "bt_batch_create_generated", "bt_batch_fetch_score_matrix", "bt_debug_device_plan", "bt_batch_fetch_topk",
 ]
 
 
@@ -136,8 +136,6 @@ def load():
     lib.bt_expand_traces.argtypes = [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     lib.bt_pinned_alloc.restype = _vp
     lib.bt_pinned_alloc.argtypes = [ctypes.c_size_t]
-    lib.bt_pinned_alloc_input.restype = _vp
-    lib.bt_pinned_alloc_input.argtypes = [ctypes.c_size_t]
     lib.bt_pinned_free.restype = None
     lib.bt_pinned_free.argtypes = [_vp]
     lib.bt_pool_trim.restype = None
@@ -195,18 +193,17 @@ def make_params(scoring, gap_penalty, terminal_penalty, local, banded, code_dtyp
     return P, matrix
 
 
-def pinned_empty(shape, dtype, input_only=False):
+def pinned_empty(shape, dtype):
     """
     A NumPy array backed by page-locked host memory (``cudaHostAlloc``), for
     full-speed asynchronous H2D / D2H copies.  Freed when the array is garbage
-    collected.  `input_only`: write-combined memory for arrays the host only
-    fills (sequence codes, offsets) - slow to read back on the host.
+    collected.
     """
     lib = load()
     dtype = np.dtype(dtype)
     count = int(np.prod(shape))
     nbytes = max(1, count * dtype.itemsize)
-    address = (lib.bt_pinned_alloc_input if input_only else lib.bt_pinned_alloc)(nbytes)
+    address = lib.bt_pinned_alloc(nbytes)
     if not address:
         raise MemoryError(lib.bt_last_error().decode())
     buf = (ctypes.c_char * nbytes).from_address(address)

@@ -88,7 +88,6 @@ static void *pinned_alloc(size_t bytes, unsigned flags) {
     return p;
 }
 extern "C" void *bt_pinned_alloc(size_t bytes) { return pinned_alloc(bytes, cudaHostAllocDefault); }
-extern "C" void *bt_pinned_alloc_input(size_t bytes) { return pinned_alloc(bytes, cudaHostAllocWriteCombined); }
 extern "C" void bt_pinned_free(void *ptr) {
     if (ptr) cudaFreeHost(ptr);
 }

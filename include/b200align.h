@@ -68,9 +68,6 @@ int bt_get_device(void);
 
 /* page-locked host memory for full-speed asynchronous copies (cudaHostAlloc / cudaFreeHost) */
 void *bt_pinned_alloc(size_t bytes);
-/* the same, write-combined: for INPUT arrays the host only writes (codes, offsets) - the device
- * reads them without snooping the CPU caches; reading such memory on the host is very slow */
-void *bt_pinned_alloc_input(size_t bytes);
 void bt_pinned_free(void *ptr);
 
 /* Device buffers of finished batches are cached per device for reuse; this returns them to

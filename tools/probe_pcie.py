@@ -19,17 +19,7 @@ h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
 d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
 d_out = torch.zeros(n, dtype=torch.uint8, device="cuda")
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-# the same H2D source as write-combined page-locked memory (cudaHostAllocWriteCombined through libb200align)
-import sys
-from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-import numpy as np  # noqa: E402
-from biotite_b200 import _cabi  # noqa: E402
-_cabi.check(_cabi.load().bt_set_device(local))
-wc = _cabi.pinned_empty((n,), np.uint8, input_only=True)
-wc[:] = 1
-h_wc = torch.from_numpy(wc)
-for mode in ("h2d", "h2d_wc", "d2h", "both", "both_wc"):
+for mode in ("h2d", "d2h", "both"):
     for rep in range(3):
         if world > 1:
             dist.barrier()
@@ -38,10 +28,7 @@ for mode in ("h2d", "h2d_wc", "d2h", "both", "both_wc"):
         if mode in ("h2d", "both"):
             with torch.cuda.stream(s1):
                 d_in.copy_(h_in, non_blocking=True)
-        if mode in ("h2d_wc", "both_wc"):
-            with torch.cuda.stream(s1):
-                d_in.copy_(h_wc, non_blocking=True)
-        if mode in ("d2h", "both", "both_wc"):
+        if mode in ("d2h", "both"):
             with torch.cuda.stream(s2):
                 h_out.copy_(d_out, non_blocking=True)
         torch.cuda.synchronize()
