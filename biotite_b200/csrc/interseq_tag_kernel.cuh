@@ -49,6 +49,18 @@ inline bool interseq_tag_eligible(const BtParams &P, const PairScan &scan, int32
     return lowest > neg + 1 && highest < 8190;
 }
 
+// cm = max(cm, v) per half; where v is strictly larger the row index r replaces ri_lo / ri_hi
+// (ptxas fuses max + compares into one VIMNMX.S16x2 with two predicate outputs)
+#define TG_MAX_ARG(cm, v, ri_lo, ri_hi, r)                                                \
+    asm("{\n\t.reg .pred pl, ph;\n\t.reg .s16 x0, x1, y0, y1;\n\t.reg .b32 t;\n\t"        \
+        "max.s16x2 t, %0, %3;\n\t"                                                       \
+        "mov.b32 {x0, x1}, t;\n\tmov.b32 {y0, y1}, %0;\n\t"                              \
+        "setp.eq.s16 pl, x0, y0;\n\tsetp.eq.s16 ph, x1, y1;\n\t"                         \
+        "@!pl mov.u32 %1, %4;\n\t@!ph mov.u32 %2, %4;\n\t"                               \
+        "mov.b32 %0, t;\n\t}"                                                            \
+        : "+r"(cm), "+r"(ri_lo), "+r"(ri_hi)                                               \
+        : "r"(v), "r"(r))
+
 // decode one half of a tagged register
 __device__ __forceinline__ int tg_lo(uint32_t x) { return (int)(int16_t)(x & 0xffffu) >> 2; }
 __device__ __forceinline__ int tg_hi(uint32_t x) { return (int)(int16_t)(x >> 16) >> 2; }
@@ -105,6 +117,7 @@ interseq_tag_fill_kernel(const InterseqConst C, const InterseqArgs A, const int 
     uint32_t *lastcol_hi = MODE == IS_SEMI ? lastcol_lo + (int64_t)d.stripes * IS_R * 32 : nullptr;
 
     int32_t best_lo = 0, best_hi = 0, bidx_lo = 0, bidx_hi = 0, brow_lo = 0, brow_hi = 0;
+    uint32_t best2 = 0x00010001u;      // local: 4 best + 1 of both pairs, the form the M1 registers have
     // table row 0 through the row buffer (pairwise.rs:747-780): M = G2 = -inf, so row 1 takes
     // F2 = -inf "from M" (the first kernel's o2 = [neg >= neg + ext]); H = open + (j-1) ext or 0
     {
@@ -224,7 +237,45 @@ interseq_tag_fill_kernel(const InterseqConst C, const InterseqArgs A, const int 
             *dirp = make_uint4(acc[0], acc[1], acc[2], acc[3]);
             dirp += 32;
             ccp += 32; rbp += 64;
-            if (!CAPTURE) return;
+            if (!CAPTURE) {
+                if (MODE == IS_LOCAL) {
+                    // Local, stripes whose 16 rows are table rows of every pair of the warp: the first
+                    // maximum of M in row-major order (pairwise.rs:849-865) without leaving the column's
+                    // basic block - a packed arg-max over the rows, then one predicated scalar update per
+                    // pair.  (The capture path below, which also knows about rows past the end of a pair,
+                    // ran on every column before: homologous pairs raise their maximum at almost every
+                    // column, so some lane always took its 16-row scalar scan and the traced local fill
+                    // ran at half the rate of the global one.)
+                    // Columns in which no pair of the warp reaches its running maximum (most of them: the
+                    // pairs of a group are alike, their maxima grow in the same few columns of a stripe)
+                    // cost 15 maxima and a vote; the others the arg-max with the rows.
+                    uint32_t cm = M1l[0];
+#pragma unroll
+                    for (int r = 1; r < IS_R; r++) cm = __vmaxs2(cm, M1l[r]);
+                    bool ge_hi, ge_lo;
+                    (void)__vibmax_s16x2(cm, best2, &ge_hi, &ge_lo);              // cm >= best, per half
+                    const bool need = (ge_lo & (j < m_lo) & ((cm & 0xffffu) > 1u)) | (ge_hi & (j < m_hi) & ((cm >> 16) > 1u));
+                    if (__any_sync(0xffffffffu, need)) {
+                        uint32_t cm2 = M1l[0];
+                        int ri_lo = 0, ri_hi = 0;
+#pragma unroll
+                        for (int r = 1; r < IS_R; r++) TG_MAX_ARG(cm2, M1l[r], ri_lo, ri_hi, r);
+                        const int c_lo = tg_lo(cm2), c_hi = tg_hi(cm2);
+                        const int row_lo = r0 + ri_lo + 1, row_hi = r0 + ri_hi + 1;
+                        // a later cell with the same score comes first in row-major order only in a higher row
+                        const bool up_lo = (j < m_lo) & ((c_lo > best_lo) | ((c_lo == best_lo) & (c_lo > 0) & (row_lo < brow_lo)));
+                        const bool up_hi = (j < m_hi) & ((c_hi > best_hi) | ((c_hi == best_hi) & (c_hi > 0) & (row_hi < brow_hi)));
+                        best_lo = up_lo ? c_lo : best_lo;
+                        brow_lo = up_lo ? row_lo : brow_lo;
+                        bidx_lo = up_lo ? row_lo * (m_lo + 1) + j + 1 : bidx_lo;
+                        best_hi = up_hi ? c_hi : best_hi;
+                        brow_hi = up_hi ? row_hi : brow_hi;
+                        bidx_hi = up_hi ? row_hi * (m_hi + 1) + j + 1 : bidx_hi;
+                        best2 = ((uint32_t)(4 * best_lo + 1) & 0xffffu) | ((uint32_t)(4 * best_hi + 1) << 16);
+                    }
+                }
+                return;
+            }
 
             if (MODE == IS_GLOBAL) {
                 if (j == j_lo || j == j_hi) {
@@ -294,6 +345,10 @@ interseq_tag_fill_kernel(const InterseqConst C, const InterseqArgs A, const int 
             if (p_lo >= 0) mine = min(mine, m_lo - 1);
             if (p_hi >= 0) mine = min(mine, m_hi - 1);
             jcut = __reduce_min_sync(0xffffffffu, mine);
+        } else {
+            // local: the capture-free columns track the optimum themselves when every lane's rows are real
+            jcut = __all_sync(0xffffffffu, rows_valid) ? d.mmax : 0;
+            best2 = ((uint32_t)(4 * best_lo + 1) & 0xffffu) | ((uint32_t)(4 * best_hi + 1) << 16);
         }
         int j0 = 0;
         for (; j0 + PF <= jcut; j0 += PF) {
