@@ -61,6 +61,11 @@ constexpr int IS_PREFETCH = BT_L2PF;  // columns of L2 prefetch distance for the
 #define BT_PF_SCORE 2
 #endif
 constexpr int IS_WARPS_PER_SM = 9;  // affine kernels: one warp per block, 24 KiB of profile each
+constexpr int IS_SMEM_BYTES = 226 * 1024;   // per SM: 227 KiB less the block's reserved KiB
+constexpr int IS_SMALL_LETTERS = 20;        // the standard amino acids: 11 warps per SM instead of 9
+
+// warps per SM whose stripe profiles of n_eff letters fit (one signed byte per row: 1 KiB per letter)
+inline int interseq_profile_warps(int n_eff) { return std::max(1, std::min(16, IS_SMEM_BYTES / (2 * n_eff * 512))); }
 constexpr int IS_SLACK = 32;        // columns of slack behind the row buffer / column codes: the
                                     // column loop reads ahead without bounds checks
 
@@ -308,15 +313,34 @@ struct InterseqArgs {
 // traceback kernel from the captured border M values, see there), IS_LOCAL = Smith-Waterman
 // (M clamped at 0, :659-666; clamping the gap states is not needed for scores or for the
 // first-priority trace because M >= 0 always wins a tie against a non-positive gap state).
-template <int MODE, bool TRACED, int PF>
-__global__ void __launch_bounds__(32, IS_WARPS_PER_SM)
-interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
-    // One warp per block.  Shared memory: the stripe profile prof[half][b][lane][16 rows] (one
-    // signed byte per row: the score of the stripe's row letter against column letter b),
-    // rebuilt for every stripe from the matrix in global memory (L1-resident).
-    extern __shared__ uint4 smem_prof[];
-    const int lane = threadIdx.x;
-    const int64_t g = blockIdx.x;
+// One group of 64 pairs per warp, `blockDim.x / 32` warps per block (one block per SM slot: the
+// 1 KiB of shared memory the system reserves per block is paid once, which is what lets 11 stripe
+// profiles of 20 letters fit an SM instead of 9 of 24).  The profile holds the first `n_eff` column
+// letters only; `ctl[0]` carries the largest column letter the packer saw in this window, so a
+// variant built for fewer letters than the matrix has steps aside when a rarer letter turns up
+// and the variant for all letters, launched right after it, does the work (as in
+// interseq_tag_kernel.cuh).
+template <int MODE, bool TRACED, int PF, int MAXW>
+__global__ void __launch_bounds__(32 * MAXW, 1)
+interseq_fill_kernel(const InterseqConst C, const InterseqArgs A, const int n_eff, const int small_letters,
+                     int *const ctl, const int counter_slot) {
+    // Shared memory per warp: the stripe profile prof[half][b][lane][16 rows] (one signed byte per
+    // row: the score of the stripe's row letter against column letter b), rebuilt for every
+    // stripe from the matrix in global memory (L1-resident).
+    extern __shared__ uint4 smem_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        const int maxcol = ctl[0];
+        if (n_eff < C.n_cols ? maxcol >= n_eff : (small_letters > 0 && maxcol < small_letters)) return;
+    }
+    uint4 *const smem_prof = smem_all + (size_t)warp * 2 * n_eff * 32;
+  // persistent: one block per SM, every warp takes the next group of 64 pairs from a counter until
+  // none is left (no partial last wave, no block waiting for its slowest warp)
+  for (;;) {
+    int64_t g = 0;
+    if (lane == 0) g = atomicAdd(ctl + counter_slot, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= A.n_groups) break;
     const WarpDesc d = A.desc[g];
     const int32_t p_lo = A.order[g * 64 + 2 * lane], p_hi = A.order[g * 64 + 2 * lane + 1];
     int n_lo = 0, n_hi = 0, m_lo = 0, m_hi = 0;
@@ -329,9 +353,9 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
     // packed zero the compiler cannot see through: with a literal 0 ptxas rebuilds the operand
     // (PRMT RZ) for every VIADDMNMX / VIMNMX3 that clamps at zero, one ALU instruction per row
     const uint32_t zero2 = (uint32_t)C.n_cols >> 31;
-    // this lane's 16 profile bytes of (half, letter b): pbase + (half * n_cols + b) * 512
+    // this lane's 16 profile bytes of (half, letter b): pbase + (half * n_eff + b) * 512
     const uint32_t pbase = (uint32_t)__cvta_generic_to_shared(smem_prof) + lane * 16;
-    const uint32_t pbase_hi = pbase + (uint32_t)C.n_cols * 512u;
+    const uint32_t pbase_hi = pbase + (uint32_t)n_eff * 512u;
 
     const uint16_t *rc = A.rowcodes + d.rowcode_off + lane;
     const uint16_t *cc = A.colcodes + d.colcode_off + lane;
@@ -379,7 +403,7 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                 a_hi[r] = (v >> 8) * (uint32_t)C.n_cols;
             }
             __syncwarp();
-            for (int b = 0; b < C.n_cols; b++) {
+            for (int b = 0; b < n_eff; b++) {
                 const int32_t *col = A.matrix + b;
                 uint32_t w_lo[4], w_hi[4];
 #pragma unroll
@@ -392,7 +416,7 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
                     }
                 }
                 smem_prof[b * 32 + lane] = make_uint4(w_lo[0], w_lo[1], w_lo[2], w_lo[3]);
-                smem_prof[(C.n_cols + b) * 32 + lane] = make_uint4(w_hi[0], w_hi[1], w_hi[2], w_hi[3]);
+                smem_prof[(n_eff + b) * 32 + lane] = make_uint4(w_hi[0], w_hi[1], w_hi[2], w_hi[3]);
             }
             __syncwarp();
         }
@@ -590,6 +614,8 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A) {
         if (p_lo >= 0) { A.start[2 * p_lo] = bidx_lo / (m_lo + 1); A.start[2 * p_lo + 1] = bidx_lo % (m_lo + 1); }
         if (p_hi >= 0) { A.start[2 * p_hi] = bidx_hi / (m_hi + 1); A.start[2 * p_hi + 1] = bidx_hi % (m_hi + 1); }
     }
+    __syncwarp();   // the next group's profile overwrites this one's
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1283,6 +1309,9 @@ inline int interseq_setup(InterseqPlan &plan, const BtParams &P, int64_t n_pairs
     plan.C.score_only = trace_mode == 1;
     plan.C.mode = P.local ? IS_LOCAL : (P.terminal_penalty ? IS_GLOBAL : IS_SEMI);
     plan.C.dir_layout = 0;
+    // windows are whole waves of the kernel that will run: size them for profiles of the 20
+    // standard letters (windows with rarer letters run the 9-warp variant on slightly odd waves)
+    if (P.affine) plan.warps_per_sm = interseq_profile_warps(std::min<int>(P.n_cols, IS_SMALL_LETTERS));
     return plan.C.score_only;
 }
 
@@ -1500,19 +1529,45 @@ inline cudaError_t interseq_launch_linear_fill(const InterseqConst &C, const Int
 template <bool TRACED> constexpr int interseq_pf() { return TRACED ? BT_PF_TRACED : BT_PF_SCORE; }
 
 template <int MODE, bool TRACED>
-inline cudaError_t interseq_launch_fill(const InterseqConst &C, const InterseqArgs &A, cudaStream_t stream) {
-    // profile: 2 halves x n_cols letters x 32 lanes x 16 rows
-    const size_t smem = (size_t)2 * C.n_cols * 512;
-    auto kernel = interseq_fill_kernel<MODE, TRACED, interseq_pf<TRACED>()>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    kernel<<<(unsigned)A.n_groups, 32, smem, stream>>>(C, A);
+inline cudaError_t interseq_launch_fill_variant(const InterseqConst &C, const InterseqArgs &A, int n_eff,
+                                                int small_letters, int *ctl, int counter_slot, cudaStream_t stream) {
+    // profile: 2 halves x n_eff letters x 32 lanes x 16 rows, per warp
+    const int warps = interseq_profile_warps(n_eff);
+    const size_t smem = (size_t)warps * 2 * n_eff * 512;
+    const int64_t sms = interseq_wave_groups() / IS_WARPS_PER_SM;
+    const unsigned grid = (unsigned)std::min<int64_t>(sms, (A.n_groups + warps - 1) / warps);
+    cudaError_t e;
+    if (warps > 11) {   // small alphabets: up to 16 warps (128 registers each)
+        auto kernel = interseq_fill_kernel<MODE, TRACED, interseq_pf<TRACED>(), 16>;
+        if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        kernel<<<grid, 32 * warps, smem, stream>>>(C, A, n_eff, small_letters, ctl, counter_slot);
+    } else {
+        auto kernel = interseq_fill_kernel<MODE, TRACED, interseq_pf<TRACED>(), 11>;
+        if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        kernel<<<grid, 32 * warps, smem, stream>>>(C, A, n_eff, small_letters, ctl, counter_slot);
+    }
     return cudaGetLastError();
 }
 
-// pack + fill of one window into the scratch of `slot`
+// Two launches when the matrix has more letters than the 20 standard amino acids (B, Z, X, * of the
+// protein alphabet): the variant whose profiles hold 20 letters (more warps per SM) runs for windows
+// that use only those, else it returns at once and the variant for all letters does the work.
+template <int MODE, bool TRACED>
+inline cudaError_t interseq_launch_fill(const InterseqConst &C, const InterseqArgs &A, int *ctl,
+                                        cudaStream_t stream, int64_t *launches) {
+    int small_letters = 0;
+    cudaError_t e = cudaSuccess;
+    if (C.n_cols > IS_SMALL_LETTERS && interseq_profile_warps(IS_SMALL_LETTERS) > interseq_profile_warps(C.n_cols)) {
+        small_letters = IS_SMALL_LETTERS;
+        e = interseq_launch_fill_variant<MODE, TRACED>(C, A, small_letters, small_letters, ctl, 1, stream);
+        if (e != cudaSuccess) return e;
+        (*launches)++;
+    }
+    e = interseq_launch_fill_variant<MODE, TRACED>(C, A, C.n_cols, small_letters, ctl, 2, stream);
+    if (e == cudaSuccess) (*launches)++;
+    return e;
+}
+
 inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, int slot, const InterseqIO &io,
                                         cudaStream_t stream, int64_t *launches) {
     const InterseqArgs A = interseq_args(plan, win, slot, io);
@@ -1551,19 +1606,18 @@ inline cudaError_t interseq_fill_window(InterseqPlan &plan, const Window &win, i
     }
     switch (plan.C.mode) {
     case IS_GLOBAL:
-        e = traced ? interseq_launch_fill<IS_GLOBAL, true>(plan.C, A, stream)
-                   : interseq_launch_fill<IS_GLOBAL, false>(plan.C, A, stream);
+        e = traced ? interseq_launch_fill<IS_GLOBAL, true>(plan.C, A, ctl, stream, launches)
+                   : interseq_launch_fill<IS_GLOBAL, false>(plan.C, A, ctl, stream, launches);
         break;
     case IS_SEMI:
-        e = traced ? interseq_launch_fill<IS_SEMI, true>(plan.C, A, stream)
-                   : interseq_launch_fill<IS_SEMI, false>(plan.C, A, stream);
+        e = traced ? interseq_launch_fill<IS_SEMI, true>(plan.C, A, ctl, stream, launches)
+                   : interseq_launch_fill<IS_SEMI, false>(plan.C, A, ctl, stream, launches);
         break;
     default:
-        e = traced ? interseq_launch_fill<IS_LOCAL, true>(plan.C, A, stream)
-                   : interseq_launch_fill<IS_LOCAL, false>(plan.C, A, stream);
+        e = traced ? interseq_launch_fill<IS_LOCAL, true>(plan.C, A, ctl, stream, launches)
+                   : interseq_launch_fill<IS_LOCAL, false>(plan.C, A, ctl, stream, launches);
         break;
     }
-    if (e == cudaSuccess) (*launches)++;
     return e;
 }
 
