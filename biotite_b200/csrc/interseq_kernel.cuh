@@ -359,8 +359,12 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A, const int n_ef
 
     const uint16_t *rc = A.rowcodes + d.rowcode_off + lane;
     const uint16_t *cc = A.colcodes + d.colcode_off + lane;
-    // row buffer: [j][plane][lane], planes M, F2, H of the row above the current stripe
-    uint32_t *const rb = A.rowbuf + d.rowbuf_off * 3 + lane;
+    // row buffer: [j][plane][lane].  Traced: planes M, F2, H of the row above the current stripe
+    // (the first row's o2 bit needs M and F2).  Score only: two planes - the F2 of the stripe's
+    // first row, already formed by the row above (max(M, F2 + ext)), and H.
+    constexpr int RBS = TRACED ? 96 : 64;          // words per column
+    constexpr int RB_H = TRACED ? 64 : 32;         // plane of H
+    uint32_t *const rb = A.rowbuf + d.rowbuf_off * (TRACED ? 3 : 2) + lane;
     uint4 *dir = TRACED ? (uint4 *)(A.dirs + d.dir_off) + lane : nullptr;
     // two planes each (low / high pair): their last rows / columns are captured at different times
     uint32_t *lastrow_lo = MODE == IS_SEMI ? A.lastrow + d.rowbuf_off * 2 + lane : nullptr;
@@ -378,8 +382,9 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A, const int n_ef
     {
         uint32_t h_row0 = MODE == IS_GLOBAL ? open2 : 0u;
         uint32_t *w = rb;
-        for (int j = 0; j < d.mmax; j++, w += 96) {
-            w[0] = neg2; w[32] = neg2; w[64] = h_row0;
+        for (int j = 0; j < d.mmax; j++, w += RBS) {
+            w[0] = neg2; if (TRACED) w[32] = neg2;   // score only: F2 of row 1 = max(-inf, -inf + ext) = -inf
+            w[RB_H] = h_row0;
             if (MODE == IS_GLOBAL) h_row0 = __vadd2(h_row0, ext2);
         }
     }
@@ -440,7 +445,7 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A, const int n_ef
         uint32_t q_c[PF], q_m[PF], q_f[PF], q_h[PF];
 #pragma unroll
         for (int k = 0; k < PF; k++) {
-            q_c[k] = ccp[k * 32]; q_m[k] = rbp[k * 96]; q_f[k] = rbp[k * 96 + 32]; q_h[k] = rbp[k * 96 + 64];
+            q_c[k] = ccp[k * 32]; q_m[k] = rbp[k * RBS]; q_f[k] = TRACED ? rbp[k * RBS + 32] : 0u; q_h[k] = rbp[k * RBS + RB_H];
         }
         // the column loop is unrolled PF times so that the look-ahead registers need no rotation
         // (a register move would wait for the load it forwards)
@@ -450,15 +455,16 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A, const int n_ef
             const int j = j0 + u;
             if (u > 0 && j >= d.mmax) break;
             const uint32_t v = q_c[u];
-            uint32_t up_m = q_m[u], up_f2 = q_f[u];
+            // traced: M and F2 of the row above; score only: plane 0 is this stripe's first-row F2 itself
+            uint32_t up_m = TRACED ? q_m[u] : 0u, up_f2 = TRACED ? q_f[u] : q_m[u];
             const uint32_t hu = q_h[u];
             q_c[u] = ccp[PF * 32];
-            q_m[u] = rbp[PF * 96]; q_f[u] = rbp[PF * 96 + 32]; q_h[u] = rbp[PF * 96 + 64];
+            q_m[u] = rbp[PF * RBS]; if (TRACED) q_f[u] = rbp[PF * RBS + 32]; q_h[u] = rbp[PF * RBS + RB_H];
             if (IS_PREFETCH > 0) {
                 // pull the row buffer towards L2 well ahead of the register prefetch
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rbp + (PF + IS_PREFETCH) * 96));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rbp + (PF + IS_PREFETCH) * 96 + 32));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rbp + (PF + IS_PREFETCH) * 96 + 64));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rbp + (PF + IS_PREFETCH) * RBS));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rbp + (PF + IS_PREFETCH) * RBS + 32));
+                if (TRACED) asm volatile("prefetch.global.L2 [%0];" ::"l"(rbp + (PF + IS_PREFETCH) * RBS + 64));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ccp + (PF + IS_PREFETCH) * 32));
             }
             // the 16 + 16 profile bytes of this column's letters
@@ -505,12 +511,13 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A, const int n_ef
                     const uint32_t to = __vadd2(t, open2);
                     BT_MAX_PRED(Hl[r], Ml[r], to, BT_ACC_LO(r, 0), BT_ACC_HI(r, 0), BT_BIT(r, 0));   // hM
                 } else {
-                    up_f2 = __vmaxs2(up_m, fv);
+                    if (r > 0) up_f2 = __vmaxs2(up_m, fv);
                     Hl[r] = __viaddmax_s16x2(__vmaxs2(F1l[r], up_f2), open2, Ml[r]);
                 }
                 up_m = Ml[r];
             }
-            rbp[0] = up_m; rbp[32] = up_f2; rbp[64] = Hl[IS_R - 1];
+            if (TRACED) { rbp[0] = up_m; rbp[32] = up_f2; rbp[64] = Hl[IS_R - 1]; }
+            else { rbp[0] = __viaddmax_s16x2(up_f2, ext2, up_m); rbp[32] = Hl[IS_R - 1]; }   // F2 of the row below
             if (TRACED) {
 #pragma unroll
                 for (int k = 1; k < BT_ACC_SPLIT; k++) {
@@ -598,7 +605,7 @@ interseq_fill_kernel(const InterseqConst C, const InterseqArgs A, const int n_ef
                     }
                 }
             }
-            ccp += 32; rbp += 96;
+            ccp += 32; rbp += RBS;
         }
         }
     }
