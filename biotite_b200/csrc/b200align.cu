@@ -249,7 +249,7 @@ template <bool AFFINE, bool BANDED>
 static cudaError_t launch_general_fill(const DevParams &D, const BatchView &V, int grid, int threads,
                                        size_t smem, cudaStream_t s) {
     auto kernel = general_fill_kernel<AFFINE, BANDED>;
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {   // opt in early: static shared memory counts against the 48 KiB default too
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
@@ -301,7 +301,7 @@ static cudaError_t launch_wavefront_fill(const DevParams &D, const BatchView &V,
                                          size_t smem, cudaStream_t s) {
     // rows per lane: 2 under a band (its windows move two columns per lane), 4 on full tables
     auto kernel = wavefront_fill_kernel<AFFINE, BANDED, MODE, TRACED, BANDED ? 2 : 4>;
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {   // opt in early: static shared memory counts against the 48 KiB default too
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
@@ -326,7 +326,7 @@ template <int MODE, bool TRACED>
 static cudaError_t launch_strip_fill(const DevParams &D, const BatchView &V, const WfArgs &A, int grid, int threads,
                                      size_t smem, cudaStream_t s) {
     auto kernel = A.lean_rows == 8 ? strip_fill_kernel<MODE, TRACED, 8> : strip_fill_kernel<MODE, TRACED, 4>;
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {   // opt in early: static shared memory counts against the 48 KiB default too
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }

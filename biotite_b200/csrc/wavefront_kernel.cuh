@@ -529,9 +529,10 @@ wavefront_fill_kernel(const DevParams P, const BatchView V, const WfArgs W_) {
 // First-optimal traceback of one pair by one warp (trace.rs:59-90 with max_number = 1; step order
 // cell.rs:125-138, :219-254).  general_traceback_kernel walks a table with one thread and pays a
 // global-memory latency per step (0.4 ms for the 2700 steps of a Cas9-sized pair); here the warp
-// keeps the aligned 32 x 128 byte tile of the direction table around the current cell in shared
-// memory (one coalesced load per tile, loaded again only when the walk leaves it) and lane 0
-// walks inside it.  Same outputs as general_traceback_kernel.
+// keeps a 32 x 128 byte tile of the direction table in shared memory (one coalesced load per
+// tile, loaded again only when the walk leaves it).  Full tables: all lanes advance the walk in
+// lockstep and take runs of Match-to-Match diagonal steps 32 cells at a time (see below); bands:
+// lane 0 walks inside the tile.  Same outputs as general_traceback_kernel.
 // ---------------------------------------------------------------------------------------
 constexpr int WT_ROWS = 32, WT_COLS = 128;
 
@@ -559,6 +560,98 @@ wavefront_traceback_kernel(const DevParams P, const BatchView V) {
     int64_t i = start / rs, j = start % rs, last_i = 0, last_j = 0, len = 0;
     int st = V.start_state[p];
     int64_t ti = -1, tj = -1;      // origin of the cached tile
+    if (!BANDED) {
+        // Full tables: every lane holds the walk's state (i, j, st, len) and they advance it
+        // together.  The tile is anchored with the current cell in its bottom-right corner (the walk
+        // only moves up and left).  In state Match, lane t looks at the cell t steps up the diagonal:
+        // the leading lanes whose cells say "Match came from Match" are one run of diagonal steps,
+        // taken in one go (ballot + find-first-set) - most of an alignment of similar sequences.
+        // Everything else is one generic step, decided identically by all lanes from a broadcast
+        // shared-memory read.
+        for (;;) {
+            if (i < 0 || j < 0 || len >= cap) break;
+            if (ti < 0 || i < ti || i >= ti + WT_ROWS || j < tj || j >= tj + WT_COLS) {
+                ti = max((int64_t)0, i - (WT_ROWS - 1));
+                tj = max((int64_t)0, ((j + 16) & ~(int64_t)15) - WT_COLS);
+                __syncwarp();
+                for (int q = lane; q < WT_ROWS * (WT_COLS / 16); q += 32) {
+                    const int r = q >> 3, ch = q & 7;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (ti + r < n_rows && tj + ch * 16 < rs)
+                        v = *(const uint4 *)(dir + (ti + r) * rs + tj + ch * 16);
+                    tiles[warp][q] = v;
+                }
+                __syncwarp();
+            }
+            if (st == ST_MATCH && i >= 1 && j >= 1) {
+                // cells (i - t, j - t), t = lane: inside the table's interior and inside the tile?
+                const int64_t ii = i - lane, jj = j - lane;
+                bool go = ii >= 1 && jj >= 1 && ii >= ti && jj >= tj;
+                if (go) {
+                    const uint32_t dd = tile[(ii - ti) * WT_COLS + (jj - tj)];
+                    go = LEAN ? ((dd >> 2) & 7u) == 7u : (AFFINE ? (dd & A_MM) != 0 : (dd & L_MATCH) != 0);
+                }
+                const unsigned stop = ~__ballot_sync(0xffffffffu, go);
+                int run = stop ? __ffs((int)stop) - 1 : 32;          // leading lanes that continue the diagonal in Match
+                run = (int)min((int64_t)run, cap - len);
+                if (run > 0) {
+                    if (P.stats) { gs.push(OP_DIAG); gs.len += run - 1; }
+                    else if (lane < run) ops[len + lane] = (uint8_t)OP_DIAG;
+                    len += run;
+                    last_i = i - (run - 1); last_j = j - (run - 1);
+                    i -= run; j -= run;
+                    continue;
+                }
+            }
+            const uint32_t d = tile[(i - ti) * WT_COLS + (j - tj)];
+            int op, ns = 0;
+            bool done = false;
+            if (LEAN) {
+                if (i == 0 || j == 0) {
+                    if (P.local || (i == 0 && j == 0)) done = true;
+                    if (i == 0) { op = OP_TO1; ns = ST_GAP1; } else { op = OP_TO2; ns = ST_GAP2; }
+                } else if (st == ST_MATCH) {
+                    const uint32_t tag = (d >> 2) & 7u;
+                    if (tag == 0) done = true;
+                    op = OP_DIAG; ns = tag == 7u ? ST_MATCH : (tag == 6u ? ST_GAP1 : ST_GAP2);
+                } else if (st == ST_GAP1) {
+                    op = OP_TO1; ns = (d & 1u) ? ST_MATCH : ST_GAP1;
+                } else {
+                    op = OP_TO2; ns = (d & 2u) ? ST_MATCH : ST_GAP2;
+                }
+            } else if (AFFINE) {
+                op = OP_DIAG;
+                if (st == ST_MATCH) {
+                    if (d & A_MM) { op = OP_DIAG; ns = ST_MATCH; }
+                    else if (d & A_G1M) { op = OP_DIAG; ns = ST_GAP1; }
+                    else if (d & A_G2M) { op = OP_DIAG; ns = ST_GAP2; }
+                    else done = true;
+                } else if (st == ST_GAP1) {
+                    if (d & A_MG1) { op = OP_TO1; ns = ST_MATCH; }
+                    else if (d & A_G1G1) { op = OP_TO1; ns = ST_GAP1; }
+                    else done = true;
+                } else {
+                    if (d & A_MG2) { op = OP_TO2; ns = ST_MATCH; }
+                    else if (d & A_G2G2) { op = OP_TO2; ns = ST_GAP2; }
+                    else done = true;
+                }
+            } else {
+                op = OP_DIAG;
+                if (d & L_MATCH) op = OP_DIAG;
+                else if (d & L_GAP1) op = OP_TO1;
+                else if (d & L_GAP2) op = OP_TO2;
+                else done = true;
+            }
+            if (done) break;
+            if (P.stats) gs.push(op); else if (lane == 0) ops[len] = (uint8_t)op;
+            len++;
+            last_i = i; last_j = j;
+            if (op == OP_DIAG) { i--; j--; }
+            else if (op == OP_TO1) { j--; }
+            else { i--; }
+            st = ns;
+        }
+    } else
     for (;;) {
         // (re)load the tile around (i, j): rows ti .. ti + 31, byte columns tj .. tj + 127
         const int64_t wi = i & ~(int64_t)(WT_ROWS - 1), wj = j & ~(int64_t)(WT_COLS - 1);

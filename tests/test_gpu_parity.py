@@ -890,3 +890,51 @@ def test_batch_with_outlier_pairs_is_split():
     assert all(len(traces[k]) == res.trace_len[k] for k in range(200))
     only = bt.align_optimal_batch(seqs1, seqs2, BLOSUM(), (-10, -1), terminal_penalty=False, score_only=True)
     assert np.array_equal(only.scores, res.scores)
+
+
+def test_banded_c4_at_the_real_shape(monkeypatch):
+    """BASELINE config 4 at its real shape - 10 kb nucleotide pairs, band +-128, NUC, affine (-10,-1),
+    score + trace - on 256 pairs against the oracle (banded.rs:164-255, :598-638)."""
+    import sys
+    monkeypatch.setenv("B200ALIGN_ROUTE", "packed")   # 256 pairs: the cost model would take the intra-pair kernel
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import bench_configs
+    n = 256
+    codes1, off1, codes2, off2, bands = bench_configs.make_c4(n, 7)
+    matrix = NUC().score_matrix()
+    with bt.DeviceBatch(codes1, off1, codes2, off2, matrix, (-10, -1), True, False, bands) as batch:
+        assert batch.kernel == "banded_i32"
+        batch.run()
+        res = batch.fetch()
+    ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, matrix, (-10, -1), bands=bands)
+    assert np.array_equal(res.scores, ref_scores)
+    assert res.scores.min() > 30000          # far beyond 16-bit lanes
+    traces = res.traces()
+    for k in range(n):
+        assert np.array_equal(traces[k], ref_traces[k]), k
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint64])
+def test_two_and_eight_byte_codes(dtype):
+    """code_bytes = 2 and 8 (util.rs:37-52): the general route reads the codes at their width."""
+    rng = np.random.default_rng(9)
+    from biotite_b200.pairwise import _native_align_pair
+    matrix = BLOSUM().score_matrix()
+    for local, terminal in ((False, True), (False, False), (True, True)):
+        a = rng.integers(0, 20, 150).astype(dtype)
+        b = rng.integers(0, 20, 170).astype(dtype)
+        traces, score = _native_align_pair(a, b, matrix, (-10, -1), terminal, local, False, 3)
+        ref_traces, ref_score = oracle.align_optimal(a, b, matrix, (-10, -1), terminal, local, False, 3)
+        assert score == ref_score and len(traces) == len(ref_traces)
+        assert all(np.array_equal(x, y) for x, y in zip(traces, ref_traces))
+    # a batch of wide codes
+    lens1, lens2 = rng.integers(1, 200, 70), rng.integers(1, 200, 70)
+    off1 = np.concatenate(([0], np.cumsum(lens1))).astype(np.int64)
+    off2 = np.concatenate(([0], np.cumsum(lens2))).astype(np.int64)
+    c1, c2 = rng.integers(0, 20, off1[-1]).astype(dtype), rng.integers(0, 20, off2[-1]).astype(dtype)
+    res = bt.align_batch_arrays(c1, off1, c2, off2, matrix, (-10, -1), True, False)
+    ref_scores, ref_tr = oracle.batch(c1, off1, c2, off2, matrix, (-10, -1), True, False)
+    assert np.array_equal(res.scores, ref_scores)
+    got = res.traces()
+    assert all(np.array_equal(got[k], ref_tr[k]) for k in range(70))

@@ -93,3 +93,23 @@ def test_empty_sequences_and_single_pair_api():
         many = bt.align_optimal(s1, s2, matrix, (-10, -1), terminal_penalty=terminal, local=local, max_number=5)
         ref_many, _ = oracle.align_optimal(s1.code, s2.code, MATRIX, (-10, -1), terminal, local, False, 5)
         assert len(many) == len(ref_many) and all(np.array_equal(x.trace, t) for x, t in zip(many, ref_many))
+
+
+def test_shared_memory_just_below_the_opt_in_threshold():
+    """Boundary buffers of 48 KiB minus a little: dynamic + static shared memory cross the default
+    limit although the dynamic part alone does not (found by the fuzzer: linear gaps, 3000 ragged pairs)."""
+    rng = np.random.default_rng(1)
+    nuc = bt.SubstitutionMatrix.std_nucleotide_matrix().score_matrix()      # 225 matrix entries
+    for max_m in range(1190, 1200):          # 10 warps x (max_m + 8) boundary entries + 225: 49 000 .. 49 400 bytes
+        lens1 = np.array([1199, 30, 700]); lens2 = np.array([max_m, 40, 20])
+        codes1, off1, codes2, off2 = _batch(rng, lens1, lens2, alphabet=4)
+        os.environ["B200ALIGN_ROUTE"] = "general"
+        try:
+            with bt.DeviceBatch(codes1, off1, codes2, off2, nuc, -9, True, False) as batch:
+                batch.run()
+                res = batch.fetch()
+        finally:
+            os.environ.pop("B200ALIGN_ROUTE", None)
+        ref_scores, ref_traces = oracle.batch(codes1, off1, codes2, off2, nuc, -9, True, False)
+        assert np.array_equal(res.scores, ref_scores)
+        assert all(np.array_equal(res.trace(k), ref_traces[k]) for k in range(3))
