@@ -189,3 +189,24 @@ def test_top_k_selection_on_the_device(k, chunk):
     assert np.array_equal(index[:, :kk], order)
     assert np.array_equal(scores[:, :kk], np.take_along_axis(full, order, axis=1))
     assert np.all(index[:, kk:] == -1)
+
+
+def test_generated_batches_with_empty_and_tiny_pools():
+    """No pairs, one pair, a pool of empty sequences: the device planner and the 32-bit side batch."""
+    matrix = bt.SubstitutionMatrix.std_protein_matrix()
+    rng = np.random.default_rng(8)
+    empty = PackedSequences(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64), bt.ProteinSequence.alphabet)
+    one = _pool(rng, [37])
+    zeros = PackedSequences(np.zeros(0, dtype=np.uint8), np.zeros(4, dtype=np.int64), bt.ProteinSequence.alphabet)
+    few = _pool(rng, [12, 300, 1])
+    assert bt.search_scores(one, empty, matrix, (-10, -1)).shape == (1, 0)
+    assert bt.search_scores(empty, few, matrix, (-10, -1)).shape == (0, 3)
+    s, idx = bt.search_scores(one, empty, matrix, (-10, -1), top_k=3)
+    assert s.shape == (1, 3) and np.all(idx == -1)
+    got = bt.search_scores(few, zeros, matrix, (-10, -1), local=False)          # global against empty sequences
+    ref = np.array([[-10 - (n - 1)] * 3 for n in (12, 300, 1)])
+    assert np.array_equal(got, ref)
+    sq = bt.all_vs_all_scores(one, matrix, (-10, -1))
+    a = one.codes
+    _, score = oracle.align_optimal(a, a, matrix.score_matrix(), (-10, -1), True, False, True, 1)
+    assert sq.shape == (1, 1) and sq[0, 0] == score

@@ -47,6 +47,11 @@ if rank == 0:
     # the same database over the node's GPUs from this one process
     multi = bt.search_scores(queries, database, matrix, (-10, -1), chunk_size=2000, devices=list(range(world)))
     ok &= bool(np.array_equal(multi, ref))
+# per-query top-k over the sharded database against the top-k of the full matrix
+top = bt.search_scores_sharded(queries, database, matrix, (-10, -1), chunk_size=2000, top_k=25)
+if rank == 0:
+    order = np.argsort(-ref.astype(np.int64), axis=1, kind="stable")[:, :25]
+    ok &= bool(np.array_equal(top[1], order) and np.array_equal(top[0], np.take_along_axis(ref, order, axis=1)))
     print(f"sharded check on {world} ranks: {'ok' if ok else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
