@@ -947,6 +947,8 @@ extern "C" int bt_batch_create_generated(const BtParams *params, const void *cod
     unsigned long long *d_others = d_cells + 1;
     struct { int32_t flag, pad; unsigned long long cells, others; } counts{};
     DevicePlanner dp;
+    // declared after the planner: on every exit the stream is drained before its buffers return to the pool
+    struct Drain { cudaStream_t s; ~Drain() { cudaStreamSynchronize(s); cudaGetLastError(); } } drain{s};
     if (n_pairs > 0) {
         CUDA_TRY(dp.reserve(n_pairs));
         dplan_generate_kernel<<<DevicePlanner::blocks_for(n_pairs), DP_THREADS, 0, s>>>(
@@ -1097,6 +1099,7 @@ extern "C" int bt_debug_device_plan(const int64_t *off1, const int64_t *off2, in
     if (bt_device_count() <= 0) return fail(BT_ERR_CUDA, "no CUDA device available (libb200align has no CPU fallback)");
     const int64_t groups = (n_pairs + 63) / 64;
     DevBuf d_off1, d_off2, d_order, d_desc;
+    DevicePlanner dp;
     cudaStream_t s = nullptr;
     struct Drain { cudaStream_t *s; ~Drain() { if (*s) { cudaStreamSynchronize(*s); cudaStreamDestroy(*s); } cudaGetLastError(); } } guard{&s};
     CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -1106,7 +1109,6 @@ extern "C" int bt_debug_device_plan(const int64_t *off1, const int64_t *off2, in
     CUDA_TRY(d_desc.alloc((size_t)groups * sizeof(WarpDesc)));
     CUDA_TRY(cudaMemcpyAsync(d_off1.ptr, off1, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(d_off2.ptr, off2, (size_t)(n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
-    DevicePlanner dp;
     CUDA_TRY(dp.reserve(n_pairs));
     PairMap dm;
     dm.off1 = d_off1.as<int64_t>(); dm.off2 = d_off2.as<int64_t>();
@@ -1319,6 +1321,7 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     DevBuf d_codes1, d_codes2, d_off1, d_off2, d_matrix, d_score, d_len, d_first, d_ops, d_flag, d_start;
     DevBuf d_len32, d_packed, d_bsums[2], d_total;
     PinnedBuf h_total;
+    DevicePlanner dplanner;   // declared before the streams: they are drained before its buffers go back to the pool
     CUDA_TRY(d_codes1.alloc((size_t)total1));
     CUDA_TRY(d_codes2.alloc((size_t)total2));
     CUDA_TRY(d_off1.alloc((size_t)(n_pairs + 1) * 8));
@@ -1373,7 +1376,6 @@ static int align_batch_pipelined(const BtParams *params, const void *codes1, con
     const char *plan_env = getenv("B200ALIGN_PLAN");
     const bool device_plan = !(plan_env && strcmp(plan_env, "host") == 0);
     StreamingPlanner planner(plan, hm, n_pairs, waves, params->affine != 0, device_plan);
-    DevicePlanner dplanner;
     if (device_plan) {
         int64_t max_np = 0;
         for (int64_t w = 0; w < planner.n_windows; w++)
