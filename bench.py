@@ -472,13 +472,23 @@ def main():
         lib.bt_pool_trim()
         configs = {}
         threads = cpu_threads()
+        def guarded(name, fn):
+            # a failing side configuration must not cost the headline line
+            try:
+                return fn()
+            except Exception as exc:   # noqa: BLE001
+                print(f"[bench] config {name} failed: {type(exc).__name__}: {exc}", file=sys.stderr)
+                return {"error": f"{type(exc).__name__}: {exc}"}
+
+        # C3 is collective (every rank scores its database slice): an exception on one rank would leave
+        # the others in a collective, so it is not guarded per rank
         entry = bench_configs.config_c3(args.c3_db, 100_000, peak, threads, dist, rank, world)
         if rank == 0:
             configs["c3"] = entry
-            configs["latency"] = bench_configs.single_pair_latencies(threads)
-            configs["c4"] = bench_configs.config_c4(args.c4_pairs, peak, threads)
+            configs["latency"] = guarded("latency", lambda: bench_configs.single_pair_latencies(threads))
+            configs["c4"] = guarded("c4", lambda: bench_configs.config_c4(args.c4_pairs, peak, threads))
             lib.bt_pool_trim()
-            configs["c5"] = bench_configs.config_c5(args.c5_seqs, peak, threads)
+            configs["c5"] = guarded("c5", lambda: bench_configs.config_c5(args.c5_seqs, peak, threads))
             configs["note"] = ("C3 runs on all ranks (database-sharded), the other entries on rank 0's GPU; "
                                "roofline_frac = lane-instructions of the recurrence per cell x device-timed cells/s / "
                                "the DPX issue rate bt_microbench measured in this run")

@@ -157,3 +157,58 @@ def test_two_rank_gloo_database_search(tmp_path):
     ref = _oracle_search(queries, database, bt.SubstitutionMatrix.std_protein_matrix(), (-10, -1), True, True,
                          0, (0, len(database)))
     assert np.array_equal(np.load(out), ref)
+
+
+# ---- per-query top-k over a sharded database: every rank keeps its best hits, rank 0 merges ----------
+
+def _oracle_search_topk(queries, database, matrix, gap, local, term, chunk_size, db_range, top_k=None):
+    """Stand-in for search_scores(top_k=...): the slice's scores by the oracle, the selection by numpy."""
+    full = _oracle_search(queries, database, matrix, gap, local, term, chunk_size, db_range)
+    lo = db_range[0]
+    kk = min(top_k, full.shape[1])
+    order = np.argsort(-full.astype(np.int64), axis=1, kind="stable")[:, :kk]
+    scores = np.take_along_axis(full, order, axis=1)
+    index = (order + lo).astype(np.int32)
+    pad = top_k - kk
+    return (np.pad(scores, ((0, 0), (0, pad)), constant_values=np.iinfo(np.int32).min),
+            np.pad(index, ((0, 0), (0, pad)), constant_values=-1))
+
+
+def _topk_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    queries, database = _search_inputs()
+    res = bt.search_scores_sharded(queries, database, bt.SubstitutionMatrix.std_protein_matrix(), (-10, -1),
+                                   compute=_oracle_search_topk, top_k=30)
+    if rank == 0:
+        np.savez(out_path, scores=res[0], index=res[1])
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_top_k_merge(tmp_path):
+    """Rank order = ascending database indices, so the stable merge keeps equal scores in index order;
+    30 hits of a 41-sequence database make every rank's list longer than its slice (padding)."""
+    import torch.multiprocessing as mp
+    out = tmp_path / "topk.npz"
+    mp.spawn(_topk_worker, args=(2, _free_port(), str(out)), nprocs=2, join=True)
+    queries, database = _search_inputs()
+    ref = _oracle_search(queries, database, bt.SubstitutionMatrix.std_protein_matrix(), (-10, -1), True, True,
+                         0, (0, len(database)))
+    order = np.argsort(-ref.astype(np.int64), axis=1, kind="stable")[:, :30]
+    got = np.load(out)
+    assert np.array_equal(got["index"], order)
+    assert np.array_equal(got["scores"], np.take_along_axis(ref, order, axis=1))
+
+
+def test_merge_top_is_a_stable_descending_merge():
+    from biotite_b200.search import _merge_top
+    a = (np.array([[9, 7, 7, 1]], dtype=np.int32), np.array([[3, 0, 5, 2]], dtype=np.int32))
+    b = (np.array([[9, 7, 2]], dtype=np.int32), np.array([[11, 10, 12]], dtype=np.int32))
+    scores, index = _merge_top(a, b, 5)
+    assert scores.tolist() == [[9, 9, 7, 7, 7]] and index.tolist() == [[3, 11, 0, 5, 10]]
+    assert _merge_top(None, b, 2)[1].tolist() == [[11, 10, 12]]   # the first list is taken as is
