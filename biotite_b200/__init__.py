@@ -47,6 +47,7 @@ from .batch import (
 )
 from .localgapped import align_local_gapped, align_local_gapped_batch
 from .search import database_shard, search_scores, search_scores_sharded
+from .distributed import all_vs_all_scores_sharded
 from .statistics import EValueEstimator
 from .cigar import CigarOp, read_alignment_from_cigar, write_alignment_to_cigar
 from .fasta import alignment_from_fasta, alignment_to_fasta, alignments_to_fasta

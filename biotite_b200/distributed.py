@@ -17,7 +17,8 @@ import numpy as np
 
 from .batch import BatchResult, align_batch_arrays
 
-__all__ = ["shard_bounds", "gather_arrays", "gather_columns", "align_batch_sharded", "bind_to_gpu_numa_node"]
+__all__ = ["shard_bounds", "gather_arrays", "gather_columns", "align_batch_sharded", "triangle_tasks",
+           "all_vs_all_scores_sharded", "bind_to_gpu_numa_node"]
 
 
 def shard_bounds(off1, off2, world_size):
@@ -168,6 +169,134 @@ def align_batch_sharded(codes1, off1, codes2, off2, scoring, gap_penalty, termin
         result.ops2 = np.zeros(1, dtype=np.uint32)
     result.ops2_words = len(result.ops2)
     return result
+
+
+def triangle_tasks(lengths, world_size, blocks=None):
+    """
+    Cut the upper triangle of an all-vs-all job into block tasks and deal them to the ranks.
+
+    The sequences are split into `blocks` contiguous blocks of (nearly) equal residue counts
+    (default ``world_size``: with equal blocks a diagonal task costs half an off-diagonal one and
+    the ``W (W + 1) / 2`` tasks deal out evenly, ``W / 2`` units per rank); task ``(a, b)``, ``a <= b``, scores block `a` against
+    block `b` (``a == b``: the block's own triangle) and costs about the product of the residue
+    counts (half of it on the diagonal).  Tasks go to the ranks longest first, each to the least
+    loaded rank (deterministic: every rank computes the same assignment).  Returns
+    ``(bounds, tasks)`` with ``bounds`` the block boundaries (sequence indices; empty blocks are dropped) and ``tasks[r]`` the list
+    of ``(a, b)`` of rank `r`.
+    """
+    lengths = np.asarray(lengths, dtype=np.int64)
+    n_blocks = int(blocks) if blocks else int(world_size)
+    n_blocks = max(1, min(n_blocks, max(len(lengths), 1)))
+    prefix = np.concatenate(([0], np.cumsum(lengths)))
+    cuts = np.searchsorted(prefix, prefix[-1] * np.arange(1, n_blocks) / n_blocks, side="left")
+    bounds = np.unique(np.concatenate(([0], cuts, [len(lengths)]))).astype(np.int64)   # no empty blocks
+    n_blocks = len(bounds) - 1
+    residues = np.diff(prefix[bounds])
+    todo = []
+    for a in range(n_blocks):
+        for b in range(a, n_blocks):
+            cost = float(residues[a]) * float(residues[b]) * (0.5 if a == b else 1.0)
+            todo.append((-cost, a, b))
+    todo.sort()
+    load = [0.0] * int(world_size)
+    tasks = [[] for _ in range(int(world_size))]
+    for neg_cost, a, b in todo:
+        r = min(range(int(world_size)), key=lambda k: (load[k], k))
+        tasks[r].append((a, b))
+        load[r] -= neg_cost
+    return bounds, tasks
+
+
+def all_vs_all_scores_sharded(sequences, matrix, gap_penalty=-10, terminal_penalty=True, local=False,
+                              group=None, dst=0, blocks=None, compute=None, timings=None):
+    """
+    Collective :func:`~biotite_b200.all_vs_all_scores` (one process per GPU): the triangle of the
+    guide-tree loop (``multiple.pyx:322-333``) is cut into block tasks (:func:`triangle_tasks`),
+    every rank scores its tasks - a block's own triangle as a triangular generated batch, two
+    different blocks as a cross batch, all enumerated on the GPU - and rank `dst` receives the
+    symmetric ``(N, N)`` int32 matrix (the others ``None``).  No collective on the data path; the
+    only exchange is the final gather of the blocks.  Every rank holds all sequences (a few MB).
+    `compute(pool_a, pool_b_or_None)` defaults to the GPU entry points; the CPU test-suite injects
+    the oracle.  `timings` receives ``device_ms`` and ``cells`` of this rank and the wall clock of its
+    three phases (``compute_s``, ``gather_s``, ``assemble_s``).
+    """
+    import torch.distributed as dist
+
+    from .batch import all_vs_all_scores, pack_sequences, PackedSequences
+    from .search import search_scores
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    pool = sequences if hasattr(sequences, "offsets") else pack_sequences(sequences)
+    n = len(pool)
+    bounds, tasks = triangle_tasks(pool.lengths, world, blocks)
+
+    def block(a):
+        lo, hi = int(bounds[a]), int(bounds[a + 1])
+        return PackedSequences(pool.codes[pool.offsets[lo]:pool.offsets[hi]], pool.offsets[lo:hi + 1] - pool.offsets[lo],
+                               pool.alphabet)
+
+    if compute is None:
+        from . import _cabi
+        _cabi.check(_cabi.load().bt_set_device(int(os.environ.get("LOCAL_RANK", rank))))
+
+        def compute(pa, pb):
+            t = {}
+            if pb is None:
+                out = all_vs_all_scores(pa, matrix, gap_penalty, terminal_penalty, local, timings=t)
+            else:
+                out = search_scores(pa, pb, matrix, gap_penalty, local, terminal_penalty, timings=t)
+            if timings is not None:
+                timings["device_ms"] = timings.get("device_ms", 0.0) + t.get("device_ms", 0.0)
+                timings["cells"] = timings.get("cells", 0) + t.get("cells", 0)
+            return out
+    import time
+
+    import torch
+    nccl = dist.get_backend(group) == "nccl"
+    device = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+    size_of = lambda t: int(bounds[t[0] + 1] - bounds[t[0]]) * int(bounds[t[1] + 1] - bounds[t[1]])   # noqa: E731
+    longest = max(1, max(sum(size_of(t) for t in per_rank) for per_rank in tasks))
+    t0 = time.perf_counter()
+    # every block goes to the device as soon as it is scored (no joined host copy)
+    padded = torch.zeros(longest, dtype=torch.int32, device=device)
+    at = 0
+    for a, b in tasks[rank]:
+        pa = block(a)
+        res = compute(pa, None) if a == b else compute(pa, block(b))
+        res = np.ascontiguousarray(res, dtype=np.int32).reshape(-1)
+        if res.size != size_of((a, b)):
+            raise ValueError(f"block ({a}, {b}) has {res.size} scores, expected {size_of((a, b))}")
+        padded[at:at + res.size].copy_(torch.from_numpy(res), non_blocking=True)
+        at += res.size
+    t1 = time.perf_counter()
+    # the only exchange: the blocks of every rank, as device tensors (NVLink under NCCL)
+    bucket = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bucket, dst=dst, group=group)
+    t2 = time.perf_counter()
+    out = None
+    if rank == dst:
+        # both triangles are written on the device; the matrix leaves it through one page-locked copy
+        joined = torch.zeros((n, n), dtype=torch.int32, device=device)
+        for r in range(world):
+            at = 0
+            for a, b in tasks[r]:
+                ra, rb = int(bounds[a + 1] - bounds[a]), int(bounds[b + 1] - bounds[b])
+                blk = bucket[r][at:at + ra * rb].view(ra, rb)
+                at += ra * rb
+                joined[bounds[a]:bounds[a + 1], bounds[b]:bounds[b + 1]] = blk
+                if a != b:
+                    joined[bounds[b]:bounds[b + 1], bounds[a]:bounds[a + 1]] = blk.t()
+        if nccl:
+            from . import _cabi
+            out = _cabi.pinned_empty((n, n), np.int32)
+            torch.from_numpy(out).copy_(joined, non_blocking=True)
+            torch.cuda.synchronize()
+        else:
+            out = joined.numpy()
+    if timings is not None:
+        timings["compute_s"], timings["gather_s"], timings["assemble_s"] = t1 - t0, t2 - t1, time.perf_counter() - t2
+        timings["tasks"] = len(tasks[rank])
+    return out
 
 
 def bind_to_gpu_numa_node(local_rank):

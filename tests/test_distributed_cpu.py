@@ -212,3 +212,65 @@ def test_merge_top_is_a_stable_descending_merge():
     scores, index = _merge_top(a, b, 5)
     assert scores.tolist() == [[9, 9, 7, 7, 7]] and index.tolist() == [[3, 11, 0, 5, 10]]
     assert _merge_top(None, b, 2)[1].tolist() == [[11, 10, 12]]   # the first list is taken as is
+
+
+# ---- all-vs-all (config 5): the triangle is cut into block tasks, dealt to the ranks by cost ---------
+
+def test_triangle_tasks_cover_the_triangle_once_and_balance_cost():
+    from biotite_b200.distributed import triangle_tasks
+    rng = np.random.default_rng(4)
+    lengths = np.clip(rng.lognormal(np.log(270), 0.7, 3000), 30, 5000).astype(np.int64)
+    for world in (1, 2, 3, 8):
+        bounds, tasks = triangle_tasks(lengths, world)
+        assert bounds[0] == 0 and bounds[-1] == len(lengths) and np.all(np.diff(bounds) >= 0)
+        n_blocks = len(bounds) - 1
+        seen = sorted(t for per_rank in tasks for t in per_rank)
+        assert seen == [(a, b) for a in range(n_blocks) for b in range(a, n_blocks)]
+        res = np.array([lengths[bounds[a]:bounds[a + 1]].sum() for a in range(n_blocks)], dtype=np.float64)
+        load = np.array([sum(res[a] * res[b] * (0.5 if a == b else 1.0) for a, b in per_rank) for per_rank in tasks])
+        assert load.max() <= 1.15 * load.mean()
+    # fewer sequences than blocks, and none at all
+    bounds, tasks = triangle_tasks(np.array([5, 7]), 4)
+    assert bounds.tolist() == [0, 2] and sorted(t for r in tasks for t in r) == [(0, 0)]
+    bounds, tasks = triangle_tasks(np.array([5, 7, 6, 9]), 4, blocks=4)
+    assert bounds.tolist() == [0, 2, 3, 4] and len([t for r in tasks for t in r]) == 6
+    bounds, tasks = triangle_tasks(np.array([], dtype=np.int64), 2)
+    assert bounds.tolist() == [0] and all(len(r) == 0 for r in tasks)
+
+
+def _oracle_block(pool_a, pool_b, gap=(-10, -1), term=True, local=False):
+    """Stand-in for all_vs_all_scores (pool_b None) / search_scores: every pair by the oracle."""
+    from oracle import oracle
+    matrix = bt.SubstitutionMatrix.std_protein_matrix().score_matrix()
+    other = pool_a if pool_b is None else pool_b
+    out = np.zeros((len(pool_a), len(other)), dtype=np.int32)
+    for i in range(len(pool_a)):
+        a = pool_a.codes[pool_a.offsets[i]:pool_a.offsets[i + 1]]
+        for j in range(len(other)):
+            b = other.codes[other.offsets[j]:other.offsets[j + 1]]
+            out[i, j] = oracle.align_optimal(a, b, matrix, gap, term, local, True, 1)[1]
+    return out
+
+
+def _triangle_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from biotite_b200.distributed import all_vs_all_scores_sharded
+    _, pool = _search_inputs(seed=9, n_db=23)
+    res = all_vs_all_scores_sharded(pool, bt.SubstitutionMatrix.std_protein_matrix(), (-10, -1), compute=_oracle_block)
+    if rank == 0:
+        np.save(out_path, res)
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_all_vs_all(tmp_path):
+    import torch.multiprocessing as mp
+    out = tmp_path / "triangle.npy"
+    mp.spawn(_triangle_worker, args=(2, _free_port(), str(out)), nprocs=2, join=True)
+    _, pool = _search_inputs(seed=9, n_db=23)
+    assert np.array_equal(np.load(out), _oracle_block(pool, None))
