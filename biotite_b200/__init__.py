@@ -21,6 +21,7 @@ from .alignment import (
     find_terminal_gaps,
     get_codes,
     get_sequence_identity,
+    get_pairwise_sequence_identity,
     get_symbols,
     remove_gaps,
     remove_terminal_gaps,

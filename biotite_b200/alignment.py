@@ -23,6 +23,7 @@ __all__ = [
     "get_codes",
     "get_symbols",
     "get_sequence_identity",
+    "get_pairwise_sequence_identity",
     "score",
     "find_terminal_gaps",
     "remove_terminal_gaps",
@@ -193,6 +194,35 @@ def get_sequence_identity(alignment, mode="not_terminal"):
     matches = np.count_nonzero(
         np.all(codes == codes[0], axis=0) & (codes[0] != -1)
     )
+    return matches / length
+
+
+def get_pairwise_sequence_identity(alignment, mode="not_terminal"):
+    """
+    :func:`get_sequence_identity` of every pair of rows: an ``(n, n)`` float array
+    (reference ``alignment.py:485-560``; the denominator of a pair counts only the two rows).
+    """
+    codes = get_codes(alignment)
+    n = len(codes)
+    present = codes != -1
+    # columns where both rows carry the same symbol, summed per pair
+    matches = np.zeros((n, n), dtype=np.int64)
+    for i in range(n):
+        matches[i] = np.count_nonzero((codes == codes[i]) & present & present[i], axis=1)
+    if mode == "all":
+        return matches / len(alignment)
+    if mode == "shortest":
+        lengths = np.array([len(seq) for seq in alignment.sequences])
+        return matches / np.minimum.outer(lengths, lengths)
+    if mode != "not_terminal":
+        raise ValueError(f"'{mode}' is an invalid calculation mode")
+    # first and one-past-last column each row occupies; a pair overlaps on [max first, min stop)
+    any_present = present.any(axis=1)
+    first = np.where(any_present, present.argmax(axis=1), codes.shape[1])
+    stop = np.where(any_present, codes.shape[1] - present[:, ::-1].argmax(axis=1), 0)
+    length = np.minimum.outer(stop, stop) - np.maximum.outer(first, first)
+    if np.any(length <= 0):
+        raise ValueError("Cannot calculate non-terminal identity, as the two sequences have no overlap")
     return matches / length
 
 
