@@ -119,3 +119,88 @@ def test_local_scores_are_the_best_global_score_of_any_two_substrings(gap):
                     best = max(best, _column_score(p, sa, sb, matrix, gap_open, gap_ext, True))
         _, score = oracle.align_optimal(a, b, matrix, gap, True, True, True, 1)
         assert score == best, (a, b, matrix, gap)
+
+
+# ---- align_banded: the same enumeration restricted to the band ---------------------------------------
+# Path vertices (i, j) = symbols consumed of either sequence; banded.rs:199-214 fills only the cells
+# with lower <= j - i <= upper, the cells on the upper and left border keep the start value 0
+# (fill_edges, :334-337 / :462-472) and the end may be any cell of the last row or column inside the
+# band (:598-638): a semi-global alignment with every gap between start and end charged.
+
+def _band_paths(n, m, lower, upper, affine, local):
+    """(start vertex, column kinds) of every alignment inside the band."""
+    inside = lambda i, j: 0 <= i <= n and 0 <= j <= m and lower <= j - i <= upper   # noqa: E731
+    out = []
+
+    def walk(i, j, start, path):
+        if path and (local or i == n or j == m):
+            out.append((start, tuple(path)))
+        last = path[-1] if path else None
+        if inside(i + 1, j + 1):
+            walk(i + 1, j + 1, start, path + [DIAG])
+        if inside(i, j + 1) and not (affine and last == GAP2):
+            walk(i, j + 1, start, path + [GAP1])
+        if inside(i + 1, j) and not (affine and last == GAP1):
+            walk(i + 1, j, start, path + [GAP2])
+
+    for i in range(n + 1):
+        for j in range(m + 1):
+            if inside(i, j) and (local or i == 0 or j == 0):
+                walk(i, j, (i, j), [])
+    return out
+
+
+def _shown_trace(start, path):
+    """
+    The trace array the reference prints for a path (trace.rs:103-142): every cell the path enters
+    becomes the row (i - 1, j - 1) and a value seen before in its column becomes a gap.  The start
+    cell is not part of the path, so a path whose first step is a gap shows that column as the pair
+    of the two symbols in front of the cell it enters - a quirk of the reference that a drop-in has
+    to keep (it needs a band whose border start makes a leading gap cheaper than a mismatch).
+    """
+    (i, j), rows = start, []
+    seen = (set(), set())
+    for kind in path:
+        i += kind != GAP1
+        j += kind != GAP2
+        row = []
+        for value, column in zip((i - 1, j - 1), seen):
+            row.append(-1 if value in column else value)
+            column.add(value)
+        if row != [-1, -1]:
+            rows.append(tuple(row))
+    return tuple(rows)
+
+
+@pytest.mark.parametrize("gap", [-3, -1, (-4, -1), (-2, -2), (-3, 0)])
+@pytest.mark.parametrize("local", [False, True])
+def test_banded_scores_are_the_best_of_all_alignments_inside_the_band(gap, local):
+    affine = isinstance(gap, tuple)
+    gap_open, gap_ext = gap if affine else (gap, gap)
+    rng = np.random.default_rng(hash((gap, local)) % 2**32)
+    done = 0
+    while done < 40:
+        matrix = rng.integers(-4, 6, (3, 3)).astype(np.int32)
+        n = int(rng.integers(1, 5))
+        m = int(rng.integers(n, 6))
+        a, b = rng.integers(0, 3, n), rng.integers(0, 3, m)
+        band = tuple(sorted(rng.integers(-n - 1, m + 2, 2).tolist()))
+        try:
+            swapped, lower, upper = oracle.prepare_band(n, m, band)
+        except ValueError:
+            continue
+        assert not swapped
+        done += 1
+        best, best_set = (0, set()) if local else (None, set())
+        for (i0, j0), path in _band_paths(n, m, lower, upper, affine, local):
+            sa, sb = a[i0:], b[j0:]
+            s = _column_score(path, sa, sb, matrix, gap_open, gap_ext, True)
+            if best is None or s > best:
+                best, best_set = s, set()
+            if s == best:
+                best_set.add(_shown_trace((i0, j0), path))
+        traces, score = oracle.align_banded(a, b, matrix, gap, lower, upper, local, False, 10_000)
+        assert score == best, (a, b, matrix, gap, lower, upper)
+        for t in traces:
+            if len(t):
+                assert tuple(map(tuple, t.tolist())) in best_set, (a, b, matrix, gap, lower, upper)
