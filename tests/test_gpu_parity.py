@@ -938,3 +938,57 @@ def test_two_and_eight_byte_codes(dtype):
     assert np.array_equal(res.scores, ref_scores)
     got = res.traces()
     assert all(np.array_equal(got[k], ref_tr[k]) for k in range(70))
+
+
+def _leading_gap_cases(count=160):
+    """Banded pairs where starting with a gap beats starting with a mismatch (gap -3, NUC mismatch -4):
+    the second sequence is the first one with its head replaced, the band starts on the border."""
+    rng = np.random.default_rng(17)
+    seqs1, seqs2, bands = [], [], []
+    for _ in range(count):
+        n = int(rng.integers(8, 40))
+        s1 = _random_seq(rng, n)
+        code2 = s1.code.copy()
+        head = int(rng.integers(1, 3))
+        code2[:head] = (code2[:head] + 1 + rng.integers(0, 3, head)) % 4      # mismatching head
+        code2 = np.concatenate((rng.integers(0, 4, int(rng.integers(0, 3))), code2))
+        s2 = bt.NucleotideSequence()
+        s2.code = code2
+        lo = int(rng.integers(-3, 1))
+        seqs1.append(s1); seqs2.append(s2); bands.append((lo, lo + int(rng.integers(3, 9))))
+    return seqs1, seqs2, bands
+
+
+def test_banded_leading_gap_is_printed_as_a_pair(route):
+    """trace.rs:61-68: the start cell is not part of the path, so the column of a first gap step is
+    printed as the pair in front of the entered cell; re-scoring such a trace gives less than the
+    reported score.  The drop-in keeps that (tests/test_oracle_bruteforce.py pins it by enumeration)."""
+    seqs1, seqs2, bands = _leading_gap_cases()
+    for gap in (-3, (-3, -1)):
+        res = bt.align_banded_batch(seqs1, seqs2, NUC(), np.array(bands), gap, False)
+        odd = 0
+        for k in range(len(seqs1)):
+            ref = oracle_align_banded(seqs1[k], seqs2[k], NUC(), bands[k], gap_penalty=gap, local=False, max_number=1)[0]
+            assert res.scores[k] == ref.score
+            assert np.array_equal(res.trace(k), ref.trace)
+            odd += bt.score(ref, NUC(), gap) != ref.score
+        assert odd >= 5
+    for k in range(0, len(seqs1), 16):
+        got = bt.align_banded(seqs1[k], seqs2[k], NUC(), bands[k], gap_penalty=(-3, -1), max_number=10)
+        _same(got, oracle_align_banded(seqs1[k], seqs2[k], NUC(), bands[k], gap_penalty=(-3, -1), max_number=10))
+
+
+@pytest.mark.parametrize("local", [True, False])
+@pytest.mark.parametrize("term", [True, False])
+@pytest.mark.parametrize("gap", [-5, -10])
+def test_linear_penalty_equals_affine_with_equal_open_and_extension(local, term, gap):
+    """The reference's own property test (tests/sequence/align/test_pairwise.py:122-166): same score,
+    same number of alignments and, when all of them were enumerated, the same alignments."""
+    for seed in range(4):
+        rng = np.random.default_rng(seed)
+        s1, s2 = _random_seq(rng, rng.integers(10, 100)), _random_seq(rng, rng.integers(10, 100))
+        ref = bt.align_optimal(s1, s2, NUC(), gap, term, local, 1000)
+        test = bt.align_optimal(s1, s2, NUC(), (gap, gap), term, local, 1000)
+        assert test[0].score == ref[0].score and len(test) == len(ref)
+        if len(test) < 1000:
+            assert all(any(np.array_equal(t.trace, r.trace) for r in ref) for t in test)
