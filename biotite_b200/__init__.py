@@ -29,7 +29,7 @@ from .alignment import (
 )
 
 __version__ = "0.1.0"
-from .pairwise import align_optimal
+from .pairwise import align_optimal, align_ungapped
 from .banded import align_banded
 from .batch import (
     BatchResult,

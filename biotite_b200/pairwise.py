@@ -20,7 +20,27 @@ from . import _cabi
 from .alignment import Alignment
 from .matrix import SubstitutionMatrix
 
-__all__ = ["align_optimal", "prepare_scoring"]
+__all__ = ["align_optimal", "align_ungapped", "prepare_scoring"]
+
+
+def align_ungapped(seq1, seq2, matrix, score_only=False):
+    """
+    Score two equally long sequences position by position; the alignment has the trivial trace
+    ``[[0, 0], [1, 1], ...]`` (reference ``pairwise.py:36-92``: no table, one gather and a sum on
+    the host there as well).
+    """
+    if len(seq1) != len(seq2):
+        raise ValueError(f"Different sequence lengths ({len(seq1):d} and {len(seq2):d})")
+    scoring = prepare_scoring(matrix, seq1, seq2)
+    if isinstance(scoring, tuple):
+        n_equal = int(np.count_nonzero(seq1.code == seq2.code))
+        score = n_equal * scoring[0] + (len(seq1) - n_equal) * scoring[1]
+    else:
+        score = int(scoring[seq1.code, seq2.code].sum(dtype=np.int64))
+    if score_only:
+        return score
+    positions = np.arange(len(seq1), dtype=np.int64)
+    return Alignment([seq1, seq2], np.stack((positions, positions), axis=1), score)
 
 
 def _check_gap_penalty(gap_penalty):

@@ -109,3 +109,18 @@ def test_rescorer_agrees_with_the_oracle_on_random_pairs():
             traces, best = oracle.align_optimal(a.code, b.code, matrix.score_matrix(), gap, terminal, False, False, 1)
             ali = bt.Alignment([a, b], traces[0], best)
             assert bt.score(ali, matrix, gap, terminal) == best
+
+
+def test_align_ungapped():
+    """The known answer of the reference's test (tests/sequence/align/test_pairwise.py:14-23) and the error paths."""
+    seq1, seq2 = bt.NucleotideSequence("ACCTGA"), bt.NucleotideSequence("ACTGGT")
+    matrix = bt.SubstitutionMatrix.std_nucleotide_matrix()
+    ali = bt.align_ungapped(seq1, seq2, matrix)
+    assert ali.score == 3 and str(ali) == "ACCTGA\nACTGGT"
+    assert ali.trace.tolist() == [[k, k] for k in range(6)]
+    assert bt.align_ungapped(seq1, seq2, matrix, score_only=True) == 3
+    assert bt.align_ungapped(seq1, seq2, (2, -1), score_only=True) == 3 * 2 + 3 * -1
+    with pytest.raises(ValueError):
+        bt.align_ungapped(seq1, bt.NucleotideSequence("ACT"), matrix)
+    with pytest.raises(ValueError):
+        bt.align_ungapped(bt.ProteinSequence("ACDEFG"), seq2, matrix)
