@@ -992,3 +992,62 @@ def test_linear_penalty_equals_affine_with_equal_open_and_extension(local, term,
         assert test[0].score == ref[0].score and len(test) == len(ref)
         if len(test) < 1000:
             assert all(any(np.array_equal(t.trace, r.trace) for r in ref) for t in test)
+
+
+def test_size_independent_score_properties_at_batch_scale():
+    """20 000 ragged protein pairs per mode, more than the oracle checks in reasonable time: properties
+    that hold for every pair whatever its size.  (a) swapping the sequences keeps the score (symmetric
+    matrix; the 3-state recurrence is symmetric in G1 / G2, pairwise.rs:608-681); (b) a linear penalty
+    g scores like the affine penalty (g, g) (the reference's test_pairwise.py:122-166); (c) the score of
+    a traced run is the score of the score-only run; (d) local >= semi-global >= global, since each
+    search space contains the next and the freed gaps cost <= 0."""
+    rng = np.random.default_rng(8)
+    n_pairs = 20000
+    codes1, off1, codes2, off2 = _random_batch(rng, n_pairs, 30, 420)
+    # half of the pairs related (mutated copies), so that scores are not all near the noise floor
+    for k in range(0, n_pairs, 2):
+        n = min(off1[k + 1] - off1[k], off2[k + 1] - off2[k])
+        keep = rng.random(n) > 0.15
+        codes2[off2[k]:off2[k] + n][keep] = codes1[off1[k]:off1[k] + n][keep]
+    matrix = BLOSUM().score_matrix()
+
+    def scores(c1, o1, c2, o2, gap, term, local, score_only=True):
+        return bt.align_batch_arrays(c1, o1, c2, o2, matrix, gap, term, local, score_only=score_only).scores
+
+    by_mode = {}
+    for term, local in ((True, False), (False, False), (True, True)):
+        s = scores(codes1, off1, codes2, off2, (-10, -1), term, local)
+        assert np.array_equal(s, scores(codes2, off2, codes1, off1, (-10, -1), term, local)), (term, local)
+        assert np.array_equal(s, scores(codes1, off1, codes2, off2, (-10, -1), term, local, score_only=False)), (term, local)
+        lin = scores(codes1, off1, codes2, off2, -6, term, local)
+        assert np.array_equal(lin, scores(codes1, off1, codes2, off2, (-6, -6), term, local)), (term, local)
+        assert np.array_equal(lin, scores(codes2, off2, codes1, off1, -6, term, local)), (term, local)
+        by_mode[(term, local)] = s
+    assert np.all(by_mode[(True, True)] >= by_mode[(False, False)])
+    assert np.all(by_mode[(False, False)] >= by_mode[(True, False)])
+    assert np.all(by_mode[(True, True)] >= 0)
+
+
+def test_sharded_all_vs_all_block_tasks_on_one_rank():
+    """all_vs_all_scores_sharded with the real GPU entry points (triangular and cross generated batches)
+    in a one-rank gloo group: three blocks give three diagonal and three cross tasks; the assembled
+    matrix must be the one-batch triangle's.  (Two ranks on two GPUs: tools/check_sharded_gpu.py.)"""
+    import socket
+
+    import torch.distributed as dist
+
+    from biotite_b200.distributed import all_vs_all_scores_sharded
+    rng = np.random.default_rng(23)
+    pool = _random_proteins(rng, 240, 20, 400)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        timings = {}
+        got = all_vs_all_scores_sharded(pool, BLOSUM(), (-10, -1), terminal_penalty=False, blocks=3, timings=timings)
+    finally:
+        dist.destroy_process_group()
+    ref = bt.all_vs_all_scores(pool, BLOSUM(), (-10, -1), terminal_penalty=False)
+    assert timings["tasks"] == 6 and timings["cells"] > 0
+    assert np.array_equal(got, ref) and np.array_equal(got, got.T)
