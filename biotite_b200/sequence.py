@@ -111,6 +111,8 @@ class Sequence:
         else:
             if isinstance(item, Sequence):
                 self._seq_code[index] = item.code
+            elif isinstance(item, np.ndarray):
+                self._seq_code[index] = item          # an array is taken as codes (sequence.py:312-313)
             else:
                 self._seq_code[index] = alph.encode_multiple(item)
 
