@@ -124,3 +124,17 @@ def test_align_ungapped():
         bt.align_ungapped(seq1, bt.NucleotideSequence("ACT"), matrix)
     with pytest.raises(ValueError):
         bt.align_ungapped(bt.ProteinSequence("ACDEFG"), seq2, matrix)
+
+
+def test_reference_known_answers():
+    """tests/sequence/align/test_alignment.py:11-57: strings round trip, symbol tables, identity values."""
+    rows = ["A-CCTGA----", "----T-ATGCT"]
+    assert str(bt.Alignment.from_strings(rows, bt.NucleotideSequence)).split("\n") == rows
+    rows = ["HAKLPRDD--WKL--", "HA--PRDDADWKLHH", "HA----DDADWKLHH"]
+    symbols = bt.get_symbols(_alignment(rows))
+    assert ["".join(s if s is not None else "-" for s in row) for row in symbols] == rows
+    ali = _alignment(["--HAKLPRDD--WL--", "FRHA--QRTDADWLHH"])
+    for mode, value in zip(("all", "not_terminal", "shortest"), (6 / 16, 6 / 12, 6 / 10)):
+        assert bt.get_sequence_identity(ali, mode=mode) == value
+        assert bt.get_pairwise_sequence_identity(ali, mode=mode)[0, 1] == value
+    assert np.all(np.diag(bt.get_pairwise_sequence_identity(ali, "shortest")) == 1)
